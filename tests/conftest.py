@@ -1,0 +1,61 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests fail (not skip) on a box without a device unless deselected
+    with -m "not gpu": the product has no CPU fallback."""
+
+
+def load_csr(z, prefix):
+    shape = tuple(int(s) for s in z[prefix + '.shape'])
+    return sp.csr_matrix((z[prefix + '.data'], z[prefix + '.indices'],
+                          z[prefix + '.indptr']), shape=shape)
+
+
+def canonical(m):
+    m = sp.csr_matrix(m, copy=True)
+    m.sum_duplicates()
+    m.sort_indices()
+    return m
+
+
+def assert_csr_parity(got, want, rtol=1e-12, raw_nnz=None, what=''):
+    """canonical (indptr, indices) bit-exact, values
+    within rtol * max|J| entrywise."""
+    if raw_nnz is not None:
+        assert sp.csr_matrix(got).nnz == raw_nnz, \
+            '%s raw nnz %d != %d' % (what, sp.csr_matrix(got).nnz, raw_nnz)
+    g, w = canonical(got), canonical(want)
+    assert g.shape == w.shape, (what, g.shape, w.shape)
+    assert np.array_equal(g.indptr, w.indptr), what + ' indptr differs'
+    assert np.array_equal(g.indices, w.indices), what + ' indices differ'
+    scale = np.abs(w.data).max() if w.nnz else 1.0
+    err = np.abs(g.data - w.data).max() if w.nnz else 0.0
+    assert err <= rtol * (scale if scale > 0 else 1.0), \
+        '%s values differ: %g (scale %g)' % (what, err, scale)
+
+
+@pytest.fixture(scope='session')
+def golden():
+    class G:
+        def __getattr__(self, name):
+            z = np.load(os.path.join(GOLDEN, name + '.npz'))
+            setattr(self, name, z)
+            return z
+    return G()
