@@ -1,0 +1,199 @@
+/* numpad_b200 -- C-ABI of the B200 (sm_100a) engine behind numpad's hot path.
+ *
+ * The reference (qiqi/numpad) is pure Python and has no FFI of its own; the
+ * seams this library replaces are the places where all of its arithmetic
+ * funnels into scipy:
+ *
+ *   S1  adstate.py:282-297   _add_ops / _multiply_ops   -> scipy csr_plus_csr,
+ *                                                           csr_matmat, _mul_scalar
+ *   S2  adstate.py:244-272   dia_jac.tocsr / csr_jac.tocsr -> coo_tocsr
+ *   S3  adsolve.py:193-195   splinalg.spsolve(J, rhs)    -> SuperLU
+ *       adsolve.py:78,141    splinalg.factorized(...)    -> SuperLU
+ *   S4  admpisolve.py:146-188,190-453  matvec / _dot / _norm2 / _lgmres
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, < 0 = error (npb_last_error()).
+ *   - pointers are DEVICE pointers owned by the caller unless marked [host];
+ *     the library never allocates or frees device memory and keeps no state
+ *     besides an error string, a launch counter and one pinned staging buffer.
+ *   - `stream` is a cudaStream_t passed as void*; ordering is by stream only.
+ *   - CSR = indptr int32[nrows+1], indices int32[nnz], data double[nnz], rows
+ *     sorted by column and duplicate-free ("canonical").
+ *   - two-phase calls: *_symbolic fills indptr_out and writes
+ *     stats[0] = nnz of the result, stats[1] = its longest row (int64, device);
+ *     the caller reads stats, allocates, then calls *_numeric.
+ *   - `npb_scales`: chain of pending scalar factors applied (in order, one
+ *     rounding each, like the reference's repeated `number * csr`) when the
+ *     data are consumed.
+ */
+#ifndef NUMPAD_B200_H
+#define NUMPAD_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPB_OK 0
+#define NPB_ERR_CUDA (-1)
+#define NPB_ERR_ARG (-2)
+#define NPB_ERR_WORKSPACE (-3)
+#define NPB_ERR_BREAKDOWN (-4)
+#define NPB_ERR_NOCONV (-5)
+#define NPB_MAX_SCALES 6
+
+typedef struct npb_scales {
+    int n;
+    double s[NPB_MAX_SCALES];
+} npb_scales;
+
+/* ---- library ---------------------------------------------------------- */
+const char* npb_last_error(void);                 /* [host] */
+int npb_version(void);
+int npb_device_check(void);
+unsigned long long npb_launch_count(void);
+void npb_launch_count_reset(void);
+int64_t npb_scan_workspace_elems(int64_t n);      /* int64 elements of scan_ws */
+
+/* ---- S1: number * csr (scipy _mul_scalar): materialise a scale chain --- */
+int npb_csr_apply_scales(int64_t nnz, const double* in, const npb_scales* sc,
+                         double* out, void* stream);
+
+/* ---- S1: csr * dia_jac  /  dia_jac * csr (csr_matmat with a diagonal) -- */
+int npb_csr_scale_cols(int64_t nnz, const int32_t* indices, const double* in,
+                       const npb_scales* sc, const double* d, double* out,
+                       void* stream);
+int npb_csr_scale_rows(int64_t nrows, const int32_t* indptr, const double* in,
+                       const npb_scales* sc, const double* d, double* out,
+                       void* stream);
+
+/* ---- S1: csr * selection (adjoint order).  map[c] = new column of column c
+ * or -1 (dropped); w = optional weight per old column.  `_same`: map keeps
+ * every column and is increasing -> pattern shared, only indices rewritten. */
+int npb_csr_relabel_same(int64_t nnz, const int32_t* indices, const double* in,
+                         const npb_scales* sc, const int32_t* map,
+                         const double* w, int32_t* indices_out, double* out,
+                         void* stream);
+int npb_csr_relabel_symbolic(int64_t nrows, const int32_t* indptr,
+                             const int32_t* indices, const int32_t* map,
+                             int32_t* counts, int32_t* indptr_out,
+                             int64_t* scan_ws, int64_t* stats, void* stream);
+int npb_csr_relabel_numeric(int64_t nrows, const int32_t* indptr,
+                            const int32_t* indices, const double* in,
+                            const npb_scales* sc, const int32_t* map,
+                            const double* w, const int32_t* indptr_out,
+                            int32_t* indices_out, double* out, void* stream);
+
+/* ---- S1: selection * csr (tangent order): row k of the result is
+ * w[k] * B[map[k], :] (empty when map[k] < 0). */
+int npb_csr_gather_rows_symbolic(int64_t nrows_out, const int32_t* map,
+                                 const int32_t* b_indptr, int32_t* counts,
+                                 int32_t* indptr_out, int64_t* scan_ws,
+                                 int64_t* stats, void* stream);
+int npb_csr_gather_rows_numeric(int64_t nrows_out, const int32_t* map,
+                                const double* w, const int32_t* b_indptr,
+                                const int32_t* b_indices, const double* b_data,
+                                const npb_scales* sc, const int32_t* indptr_out,
+                                int32_t* indices_out, double* out, void* stream);
+
+/* ---- S1: csr + csr (scipy csr_plus_csr; prune != 0 drops exact zeros) -- */
+int npb_spadd_symbolic(int64_t nrows, const int32_t* a_indptr,
+                       const int32_t* a_indices, const double* a_data,
+                       const npb_scales* a_sc, const int32_t* b_indptr,
+                       const int32_t* b_indices, const double* b_data,
+                       const npb_scales* b_sc, int prune, int32_t* counts,
+                       int32_t* indptr_out, int64_t* scan_ws, int64_t* stats,
+                       void* stream);
+int npb_spadd_numeric(int64_t nrows, const int32_t* a_indptr,
+                      const int32_t* a_indices, const double* a_data,
+                      const npb_scales* a_sc, const int32_t* b_indptr,
+                      const int32_t* b_indices, const double* b_data,
+                      const npb_scales* b_sc, int prune,
+                      const int32_t* indptr_out, int32_t* indices_out,
+                      double* out, void* stream);
+
+/* ---- S1: general csr * csr (scipy csr_matmat), expansion to COO; finish
+ * with npb_coo_to_csr_* (prune = 0: products keep explicit zeros). */
+int npb_spgemm_expand_symbolic(int64_t a_nnz, const int32_t* a_indices,
+                               const int32_t* b_indptr, int32_t* counts,
+                               int32_t* offsets, int64_t* scan_ws,
+                               int64_t* stats, void* stream);
+int npb_spgemm_expand_numeric(int64_t a_nnz, const int32_t* a_rows,
+                              const int32_t* a_indices, const double* a_data,
+                              const npb_scales* a_sc, const int32_t* b_indptr,
+                              const int32_t* b_indices, const double* b_data,
+                              const npb_scales* b_sc, const int32_t* offsets,
+                              int32_t* out_rows, int32_t* out_cols,
+                              double* out_vals, void* stream);
+
+/* ---- S2: block -> CSR (dia_jac.tocsr, csr_jac.tocsr, sp.eye seeds) ----- */
+int npb_diag_to_csr(int64_t n, const double* d /* NULL: scale*I */, double scale,
+                    int32_t* indptr, int32_t* indices, double* data, void* stream);
+int npb_sel_to_csr_symbolic(int64_t nrows, const int32_t* map, int32_t* counts,
+                            int32_t* indptr_out, int64_t* scan_ws,
+                            int64_t* stats, void* stream);
+int npb_sel_to_csr_numeric(int64_t nrows, const int32_t* map, const double* w,
+                           const int32_t* indptr_out, int32_t* indices_out,
+                           double* out, void* stream);
+int64_t npb_coo_to_csr_workspace(int64_t nrows, int64_t nnz);   /* bytes */
+int npb_coo_to_csr_symbolic(int64_t nrows, int64_t nnz, const int32_t* rows,
+                            const int32_t* cols, const double* vals, int prune,
+                            void* ws, int64_t ws_bytes, int32_t* indptr_out,
+                            int64_t* stats, void* stream);
+int npb_coo_to_csr_numeric(int64_t nrows, int64_t nnz, void* ws,
+                           int32_t* indices_out, double* data_out, void* stream);
+int npb_csr_expand_rows(int64_t nrows, const int32_t* indptr, int32_t* rows,
+                        void* stream);
+int npb_csr_max_row(int64_t nrows, const int32_t* indptr, int64_t* stats,
+                    void* stream);
+
+/* ---- S3/S4: SpMV and Krylov vector kernels ----------------------------- */
+int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr,
+             const int32_t* indices, const double* data, const double* x,
+             double* y, void* stream);                       /* y = A x     */
+int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
+                      const int32_t* indices, const double* data,
+                      const double* x, const double* b, double* y,
+                      void* stream);                         /* y = b - A x */
+int64_t npb_reduce_scratch_bytes(void);   /* zero-initialised by the caller */
+int npb_dot_multi(int64_t n, int k, const double* V, int64_t ld,
+                  const double* w, double* out, void* scratch, void* stream);
+int npb_axpy_multi(int64_t n, int k, const double* V, int64_t ld,
+                   const double* h, double sign, double* w, double* out_norm2,
+                   void* scratch, void* stream);
+int npb_axpby(int64_t n, double a, const double* x, double b, double* y,
+              void* stream);
+
+/* ---- S3: the linear solve (replaces spsolve / factorized / _lgmres) ---- */
+typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
+typedef int (*npb_allreduce_fn)(void* ctx, double* buf, int count, void* stream);
+
+typedef struct npb_krylov_ops {          /* [host] */
+    npb_apply_fn matvec;   void* matvec_ctx;      /* y = A x                 */
+    npb_apply_fn precond;  void* precond_ctx;     /* y = M^-1 x, may be NULL */
+    npb_allreduce_fn allreduce; void* allreduce_ctx; /* NULL on one rank     */
+} npb_krylov_ops;
+
+typedef struct npb_csr_view {            /* [host] ctx of npb_csr_matvec_cb */
+    int64_t nrows, nnz;
+    const int32_t* indptr;
+    const int32_t* indices;
+    const double* data;
+} npb_csr_view;
+
+typedef struct npb_krylov_info {         /* [host] */
+    int32_t iters, restarts, status, pad;
+    double bnorm, rnorm0, rnorm;
+} npb_krylov_info;
+
+int npb_csr_matvec_cb(void* ctx, const double* x, double* y, void* stream);
+int64_t npb_fgmres_workspace_bytes(int64_t n, int restart, int flexible);
+int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
+               int restart, int maxiter, double rtol, double atol, int flexible,
+               void* work, int64_t work_bytes, npb_krylov_info* info,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUMPAD_B200_H */

@@ -1,0 +1,502 @@
+"""Device-resident Jacobian algebra: the host side of seam S1/S2.
+
+`DevCsr` is a canonical CSR matrix in HBM (int32 indptr/indices, fp64 data)
+with a chain of pending scalar factors; `DevEye` is `val * I` (what scipy keeps
+as a dia_matrix).  `mul` / `add` reproduce the semantics of the reference's
+`_multiply_ops` / `_add_ops` (adstate.py:282-297) -- including scipy's rules
+that a sum drops exact zeros while a product keeps them, and that an empty
+product collapses to the int 0 -- by dispatching to the kernels of
+csrc/assembly.cu and csrc/coo.cu through the C-ABI.  No arithmetic happens on
+the host; torch is used for allocation, streams and index plumbing only.
+"""
+import numbers
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from ._lib import make_scales, NO_SCALES, MAX_SCALES
+
+INT32_MAX = 2 ** 31 - 1
+# rows longer than this leave the row-parallel kernels for the sort-based path
+LONG_ROW = 4096
+
+_state = {'device': None}
+
+
+def device():
+    """The CUDA device of this process (cuda:LOCAL_RANK under torchrun).
+    Raises when no GPU is present: there is no CPU path."""
+    if _state['device'] is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError('numpad_b200 needs a CUDA device (B200, sm_100a); '
+                               'there is no CPU fallback')
+        import os
+        idx = int(os.environ.get('LOCAL_RANK', '0')) % torch.cuda.device_count()
+        torch.cuda.set_device(idx)
+        _state['device'] = torch.device('cuda', idx)
+    return _state['device']
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    return _lib.lib().call(name, *args, stream_ptr())
+
+
+def _empty(n, dtype):
+    return torch.empty(int(n), dtype=dtype, device=device())
+
+
+def _scan_ws(n):
+    return _empty(_lib.lib().cdll.npb_scan_workspace_elems(int(n)), torch.int64)
+
+
+def _read_stats(stats):
+    total, max_row = stats.tolist()          # the one host sync of a symbolic phase
+    if total > INT32_MAX:
+        raise OverflowError('Jacobian block with %d nonzeros exceeds the int32 '
+                            'index range of one GPU shard' % total)
+    return int(total), int(max_row)
+
+
+class DevEye:
+    """val * identity(n): the seed of a sweep and everything reached from it
+    through scalar blocks only (scipy keeps those as dia_matrix)."""
+    __slots__ = ('n', 'val')
+
+    def __init__(self, n, val=1.0):
+        self.n, self.val = int(n), float(val)
+
+    shape = property(lambda s: (s.n, s.n))
+    nnz = property(lambda s: s.n)
+
+    def scaled(self, a):
+        return DevEye(self.n, self.val * a)
+
+    def todev(self):
+        """dia.tocsr(): an all-zero diagonal converts to an EMPTY matrix"""
+        if self.val == 0.0:
+            return DevCsr.empty((self.n, self.n))
+        ptr, idx, dat = _empty(self.n + 1, torch.int32), _empty(self.n, torch.int32), \
+            _empty(self.n, torch.float64)
+        _call('npb_diag_to_csr', self.n, None, self.val, ptr, idx, dat)
+        return DevCsr((self.n, self.n), ptr, idx, dat, (), self.n, 1 if self.n else 0)
+
+    def toscipy(self):
+        return sp.dia_matrix((np.full((1, self.n), self.val), [0]),
+                             shape=(self.n, self.n))
+
+
+class DevCsr:
+    __slots__ = ('shape', 'indptr', 'indices', 'data', 'scales', 'nnz', 'max_row')
+
+    def __init__(self, shape, indptr, indices, data, scales, nnz, max_row):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.indptr, self.indices, self.data = indptr, indices, data
+        self.scales = tuple(scales)
+        self.nnz, self.max_row = int(nnz), int(max_row)
+
+    @staticmethod
+    def empty(shape):
+        return DevCsr(shape, torch.zeros(int(shape[0]) + 1, dtype=torch.int32, device=device()),
+                      _empty(0, torch.int32), _empty(0, torch.float64), (), 0, 0)
+
+    @staticmethod
+    def from_scipy(m):
+        m = sp.csr_matrix(m, copy=True)
+        m.sum_duplicates()
+        m.sort_indices()
+        if m.nnz > INT32_MAX:
+            raise OverflowError('matrix too large for int32 indices')
+        d = device()
+        lens = np.diff(m.indptr)
+        return DevCsr(m.shape, torch.from_numpy(m.indptr.astype(np.int32)).to(d),
+                      torch.from_numpy(m.indices.astype(np.int32)).to(d),
+                      torch.from_numpy(m.data.astype(np.float64)).to(d), (), m.nnz,
+                      int(lens.max()) if lens.size else 0)
+
+    def scaled(self, a):
+        if len(self.scales) >= MAX_SCALES:
+            return self.materialized().scaled(a)
+        return DevCsr(self.shape, self.indptr, self.indices, self.data,
+                      self.scales + (float(a),), self.nnz, self.max_row)
+
+    def materialized(self):
+        """apply the pending scalar chain (one pass over data)"""
+        if not self.scales:
+            return self
+        out = _empty(self.nnz, torch.float64)
+        _call('npb_csr_apply_scales', self.nnz, self.data, make_scales(self.scales), out)
+        return DevCsr(self.shape, self.indptr, self.indices, out, (), self.nnz, self.max_row)
+
+    def todev(self):
+        return self
+
+    def toscipy(self):
+        m = self.materialized()
+        return sp.csr_matrix((m.data.cpu().numpy(), m.indices.cpu().numpy(),
+                              m.indptr.cpu().numpy()), shape=self.shape)
+
+    def rows(self):
+        """COO row index of every stored entry"""
+        r = _empty(self.nnz, torch.int32)
+        _call('npb_csr_expand_rows', self.shape[0], self.indptr, r)
+        return r
+
+    def transpose(self):
+        m = self.materialized()
+        return coo_to_csr((self.shape[1], self.shape[0]), m.indices, m.rows(), m.data,
+                          prune=False)
+
+    def matvec(self, x, out=None):
+        m = self.materialized()
+        if out is None:
+            out = _empty(self.shape[0], torch.float64)
+        _call('npb_spmv', self.shape[0], self.nnz, m.indptr, m.indices, m.data, x, out)
+        return out
+
+
+# --------------------------------------------------------------------------- #
+# local Jacobian blocks emitted by the tape (public names of adstate.py:233-272)
+# --------------------------------------------------------------------------- #
+def _as_dev_f64(a):
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device(), dtype=torch.float64)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float64))).to(device())
+    return t.reshape(-1).contiguous() if not (t.dim() == 1 and t.is_contiguous()) else t
+
+
+def _as_dev_i32(a):
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device(), dtype=torch.int32)
+    else:
+        a = np.asarray(a)
+        if a.size and (a.max() > INT32_MAX or a.min() < -INT32_MAX):
+            raise OverflowError('index out of int32 range')
+        t = torch.from_numpy(np.ascontiguousarray(a.astype(np.int32))).to(device())
+    return t.reshape(-1).contiguous()
+
+
+class dia_jac:
+    """A Jacobian represented by a diagonal matrix (reference adstate.py:233-250).
+    `diag_entries` may be a numpy array or a device tensor; it lives in HBM."""
+
+    def __init__(self, diag_entries):
+        self.data = _as_dev_f64(diag_entries)
+
+    @property
+    def shape(self):
+        return (self.data.numel(), self.data.numel())
+
+    def todev(self):
+        n = self.data.numel()
+        ptr, idx, dat = _empty(n + 1, torch.int32), _empty(n, torch.int32), _empty(n, torch.float64)
+        _call('npb_diag_to_csr', n, self.data, 1.0, ptr, idx, dat)
+        return DevCsr((n, n), ptr, idx, dat, (), n, 1 if n else 0)
+
+    def tocsr(self):
+        return self.todev().toscipy()
+
+
+class csr_jac:
+    """Jacobian given as COO triplets (reference adstate.py:252-272): general
+    block, converted on the device (sort + duplicate sum) on first use."""
+
+    def __init__(self, data, i, j, shape=None):
+        self.data, self.i, self.j = data, i, j
+        self._shape = None if shape is None else (int(shape[0]), int(shape[1]))
+        self._dev = None
+
+    @property
+    def shape(self):
+        if self._shape is None:
+            i, j = _as_dev_i32(self.i), _as_dev_i32(self.j)
+            self._shape = (int(i.max()) + 1, int(j.max()) + 1)
+        return self._shape
+
+    def todev(self):
+        if self._dev is None:
+            self._dev = coo_to_csr(self.shape, _as_dev_i32(self.i), _as_dev_i32(self.j),
+                                   _as_dev_f64(self.data), prune=False)
+        return self._dev
+
+    def tocsr(self):
+        return self.todev().toscipy()
+
+
+class sel_jac:
+    """Selection block with at most one entry per row:
+    row r has the entry (r, map[r]) with value w[r] (1 if w is None), or is
+    empty when map[r] < 0.  Emitted by indexing, assignment, stacking,
+    broadcasting (what the reference builds as csr_jac with unit data,
+    adarray.py:761-796, 356-384, 593-607, 670-693).
+
+    monotone : map is strictly increasing over its non-negative entries
+               (a product with it keeps rows sorted and duplicate-free)
+    full     : no row is empty
+    """
+
+    def __init__(self, map_, n_cols, weights=None, monotone=None, full=None):
+        self.map = map_
+        self.n_rows, self.n_cols = int(map_.numel()), int(n_cols)
+        self.w = weights
+        self._monotone, self._full = monotone, full
+        self._dev = None
+
+    @property
+    def shape(self):
+        return (self.n_rows, self.n_cols)
+
+    @property
+    def full(self):
+        if self._full is None:
+            self._full = bool((self.map >= 0).all().item())
+        return self._full
+
+    @property
+    def monotone(self):
+        if self._monotone is None:
+            kept = self.map[self.map >= 0]
+            self._monotone = bool((kept[1:] > kept[:-1]).all().item()) if kept.numel() > 1 else True
+        return self._monotone
+
+    def todev(self):
+        if self._dev is None:
+            n = self.n_rows
+            cnt, ptr = _empty(n, torch.int32), _empty(n + 1, torch.int32)
+            stats = _empty(2, torch.int64)
+            _call('npb_sel_to_csr_symbolic', n, self.map, cnt, ptr, _scan_ws(n), stats)
+            nnz, _ = _read_stats(stats)
+            idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+            _call('npb_sel_to_csr_numeric', n, self.map, self.w, ptr, idx, dat)
+            self._dev = DevCsr(self.shape, ptr, idx, dat, (), nnz, 1 if nnz else 0)
+        return self._dev
+
+    def tocsr(self):
+        return self.todev().toscipy()
+
+
+def tocsr(jac):
+    """reference adstate.py:274-278 -- host (scipy) view of a block"""
+    if isinstance(jac, (dia_jac, csr_jac, sel_jac)):
+        return jac.tocsr()
+    if isinstance(jac, (DevCsr, DevEye)):
+        return jac.toscipy()
+    return jac
+
+
+# --------------------------------------------------------------------------- #
+# kernels behind the products / sums
+# --------------------------------------------------------------------------- #
+def coo_to_csr(shape, rows, cols, vals, prune):
+    nrows, nnz_in = int(shape[0]), int(rows.numel())
+    L = _lib.lib()
+    ws_bytes = L.cdll.npb_coo_to_csr_workspace(nrows, nnz_in)
+    ws = _empty(ws_bytes, torch.uint8)
+    ptr = _empty(nrows + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _lib.lib().call('npb_coo_to_csr_symbolic', nrows, nnz_in, rows, cols, vals,
+                    1 if prune else 0, ws, ws_bytes, ptr, stats, stream_ptr())
+    nnz, max_row = _read_stats(stats)
+    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    _call('npb_coo_to_csr_numeric', nrows, nnz_in, ws, idx, dat)
+    return DevCsr(shape, ptr, idx, dat, (), nnz, max_row)
+
+
+def _csr_times_diag(A, d):
+    out = _empty(A.nnz, torch.float64)
+    _call('npb_csr_scale_cols', A.nnz, A.indices, A.data, make_scales(A.scales), d.data, out)
+    return DevCsr(A.shape, A.indptr, A.indices, out, (), A.nnz, A.max_row)
+
+
+def _diag_times_csr(d, B):
+    out = _empty(B.nnz, torch.float64)
+    _call('npb_csr_scale_rows', B.shape[0], B.indptr, B.data, make_scales(B.scales), d.data, out)
+    return DevCsr(B.shape, B.indptr, B.indices, out, (), B.nnz, B.max_row)
+
+
+def _csr_times_sel(A, S):
+    """A (m x k) times a selection (k x n): column relabel."""
+    shape = (A.shape[0], S.n_cols)
+    if A.nnz == 0:
+        return DevCsr.empty(shape)
+    if S.monotone:
+        sc = make_scales(A.scales)
+        if S.full:              # per-entry kernel, any row length
+            idx = _empty(A.nnz, torch.int32)
+            if S.w is None:     # data buffer and pending scales are shared
+                _call('npb_csr_relabel_same', A.nnz, A.indices, A.data, sc, S.map, None, idx, None)
+                return DevCsr(shape, A.indptr, idx, A.data, A.scales, A.nnz, A.max_row)
+            dat = _empty(A.nnz, torch.float64)
+            _call('npb_csr_relabel_same', A.nnz, A.indices, A.data, sc, S.map, S.w, idx, dat)
+            return DevCsr(shape, A.indptr, idx, dat, (), A.nnz, A.max_row)
+        if A.max_row <= LONG_ROW:
+            m = A.shape[0]
+            cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+            stats = _empty(2, torch.int64)
+            _call('npb_csr_relabel_symbolic', m, A.indptr, A.indices, S.map, cnt, ptr,
+                  _scan_ws(m), stats)
+            nnz, max_row = _read_stats(stats)
+            idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+            _call('npb_csr_relabel_numeric', m, A.indptr, A.indices, A.data, sc, S.map, S.w,
+                  ptr, idx, dat)
+            return DevCsr(shape, ptr, idx, dat, (), nnz, max_row)
+    # general: relabel in COO form, drop, sort, merge duplicates
+    Am = A.materialized()
+    cols = S.map[Am.indices.long()]
+    vals = Am.data if S.w is None else _mul_entries(Am.data, S.w, Am.indices)
+    rows = Am.rows()
+    if not S.full:
+        keep = cols >= 0
+        rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    return coo_to_csr(shape, rows.contiguous(), cols.contiguous(), vals.contiguous(), prune=False)
+
+
+def _mul_entries(data, w, indices):
+    """data[k] * w[indices[k]] through the column-scaling kernel"""
+    out = _empty(data.numel(), torch.float64)
+    _call('npb_csr_scale_cols', data.numel(), indices, data, NO_SCALES, w, out)
+    return out
+
+
+def _sel_times_csr(S, B):
+    """selection (m x k) times B (k x n): row gather."""
+    m = S.n_rows
+    shape = (m, B.shape[1])
+    cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_csr_gather_rows_symbolic', m, S.map, B.indptr, cnt, ptr, _scan_ws(m), stats)
+    nnz, max_row = _read_stats(stats)
+    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    _call('npb_csr_gather_rows_numeric', m, S.map, S.w, B.indptr, B.indices, B.data,
+          make_scales(B.scales), ptr, idx, dat)
+    return DevCsr(shape, ptr, idx, dat, (), nnz, max_row)
+
+
+def _csr_times_csr(A, B):
+    """general product through expansion + sort (scipy csr_matmat semantics:
+    duplicates summed, explicit zeros kept)"""
+    shape = (A.shape[0], B.shape[1])
+    if A.nnz == 0 or B.nnz == 0:
+        return DevCsr.empty(shape)
+    cnt, off = _empty(A.nnz, torch.int32), _empty(A.nnz + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_spgemm_expand_symbolic', A.nnz, A.indices, B.indptr, cnt, off,
+          _scan_ws(A.nnz), stats)
+    total, _ = _read_stats(stats)
+    if total == 0:
+        return DevCsr.empty(shape)
+    r, c, v = _empty(total, torch.int32), _empty(total, torch.int32), _empty(total, torch.float64)
+    _call('npb_spgemm_expand_numeric', A.nnz, A.rows(), A.indices, A.data, make_scales(A.scales),
+          B.indptr, B.indices, B.data, make_scales(B.scales), off, r, c, v)
+    return coo_to_csr(shape, r, c, v, prune=False)
+
+
+def _csr_plus_csr(A, B):
+    assert A.shape == B.shape
+    m = A.shape[0]
+    if max(A.max_row, B.max_row) > LONG_ROW:
+        Am, Bm = A.materialized(), B.materialized()
+        return coo_to_csr(A.shape, torch.cat([Am.rows(), Bm.rows()]),
+                          torch.cat([Am.indices, Bm.indices]),
+                          torch.cat([Am.data, Bm.data]), prune=True)
+    sa, sb = make_scales(A.scales), make_scales(B.scales)
+    cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_spadd_symbolic', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
+          B.data, sb, 1, cnt, ptr, _scan_ws(m), stats)
+    nnz, max_row = _read_stats(stats)
+    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    _call('npb_spadd_numeric', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
+          B.data, sb, 1, ptr, idx, dat)
+    return DevCsr(A.shape, ptr, idx, dat, (), nnz, max_row)
+
+
+# --------------------------------------------------------------------------- #
+# _multiply_ops / _add_ops                          (reference adstate.py:282-297)
+# --------------------------------------------------------------------------- #
+def _is0(x):
+    """the reference's `x is 0`: the int literal only"""
+    return type(x) is int and x == 0
+
+
+def _as_operand(x):
+    """number | DevEye | DevCsr | dia_jac | sel_jac | csr_jac ; foreign sparse
+    matrices (user supplied scipy blocks) are uploaded once"""
+    if isinstance(x, (numbers.Number, DevEye, DevCsr, dia_jac, sel_jac, csr_jac)):
+        return x
+    if sp.issparse(x):
+        return DevCsr.from_scipy(x)
+    if hasattr(x, 'tocsr'):
+        return DevCsr.from_scipy(x.tocsr())
+    raise TypeError('unsupported Jacobian block %r' % type(x))
+
+
+def _mat(x):
+    """accumulated derivative (DevEye / DevCsr) -> DevCsr"""
+    return x.todev()
+
+
+def _collapse(c):
+    """`if op.nnz == 0: op = 0`"""
+    if isinstance(c, DevCsr) and c.nnz == 0:
+        return 0
+    return c
+
+
+def _multiply_ops(op0, op1):
+    if _is0(op0) or _is0(op1):
+        return 0
+    a, b = _as_operand(op0), _as_operand(op1)
+    an, bn = isinstance(a, numbers.Number), isinstance(b, numbers.Number)
+    if an and bn:
+        return a * b
+    if an or bn:
+        s, m = (a, b) if an else (b, a)
+        if isinstance(m, (DevEye, DevCsr)):
+            return _collapse(m.scaled(s))
+        return _collapse(m.todev().scaled(s))
+    # matrix x matrix
+    if isinstance(a, DevEye) and isinstance(b, DevEye):
+        return DevEye(a.n, a.val * b.val)
+    if isinstance(a, DevEye):           # val*I x block
+        if a.val == 0.0:                # an all-zero dia converts to an empty CSR
+            return 0
+        c = b if isinstance(b, DevCsr) else b.todev()
+        return _collapse(c if a.val == 1.0 else c.scaled(a.val))
+    if isinstance(b, DevEye):
+        if b.val == 0.0:
+            return 0
+        c = a if isinstance(a, DevCsr) else a.todev()
+        return _collapse(c if b.val == 1.0 else c.scaled(b.val))
+    if isinstance(a, DevCsr):           # adjoint order: accumulated x local block
+        if isinstance(b, dia_jac):
+            return _collapse(_csr_times_diag(a, b))
+        if isinstance(b, sel_jac):
+            return _collapse(_csr_times_sel(a, b))
+        return _collapse(_csr_times_csr(a, b.todev()))
+    if isinstance(b, DevCsr):           # tangent order: local block x accumulated
+        if isinstance(a, dia_jac):
+            return _collapse(_diag_times_csr(a, b))
+        if isinstance(a, sel_jac):
+            return _collapse(_sel_times_csr(a, b))
+        return _collapse(_csr_times_csr(a.todev(), b))
+    return _collapse(_csr_times_csr(a.todev(), b.todev()))
+
+
+def _add_ops(op0, op1):
+    if _is0(op0):
+        return op1
+    if _is0(op1):
+        return op0
+    a, b = _as_operand(op0), _as_operand(op1)
+    if isinstance(a, numbers.Number) or isinstance(b, numbers.Number):
+        raise TypeError('cannot add a number to a Jacobian')
+    if isinstance(a, DevEye) and isinstance(b, DevEye):
+        return DevEye(a.n, a.val + b.val)        # dia + dia keeps zeros
+    return _csr_plus_csr(a.todev(), b.todev())

@@ -1,0 +1,233 @@
+// Restarted flexible GMRES, right-preconditioned, host-driven.
+//
+// Seam replaced: `splinalg.spsolve(J, rhs)` in the reference Newton loop
+// (adsolve.py:193-195), `factorized(J^T)(g)` in the adjoint through a solve
+// (adsolve.py:78-82) and `_lgmres(J.matvec, ..., M=J.approx_solve)` of the
+// distributed path (admpisolve.py:190-453).  The operator, the preconditioner
+// and the cross-rank sum are callbacks so the same driver serves the
+// single-GPU CSR case (npb_csr_matvec_cb below: no Python in the loop), the
+// row-sharded multi-GPU case (matvec = halo exchange + local SpMV, allreduce =
+// NCCL) and any preconditioner written on top of the C-ABI.
+//
+// Per inner iteration: 1 preconditioner apply, 1 matvec, CGS2 = 2 multi-dots
+// + 2 multi-axpys (the second also yields ||w||), 1 scale; ONE device->host
+// copy of the (j+2)-entry Hessenberg column, Givens on the host.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                    const double* dat, const double* x, const double* b, double* y,
+                    int mode, cudaStream_t st);
+int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
+                         double* out, void* scratch, cudaStream_t st);
+int npb_axpy_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* h,
+                          double sign, double* w, double* out_norm2, void* scratch,
+                          cudaStream_t st);
+int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st);
+extern "C" int64_t npb_reduce_scratch_bytes(void);
+
+extern "C" {
+
+typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
+typedef int (*npb_allreduce_fn)(void* ctx, double* buf, int count, void* stream);
+
+struct npb_krylov_ops {
+    npb_apply_fn matvec;        // y = A x                     (required)
+    void* matvec_ctx;
+    npb_apply_fn precond;       // y = M^{-1} x                (NULL: identity)
+    void* precond_ctx;
+    npb_allreduce_fn allreduce; // in-place sum over ranks     (NULL: 1 rank)
+    void* allreduce_ctx;
+};
+
+struct npb_csr_view {           // ctx of npb_csr_matvec_cb
+    int64_t nrows, nnz;
+    const int32_t* indptr;
+    const int32_t* indices;
+    const double* data;
+};
+
+struct npb_krylov_info {
+    int32_t iters;              // inner iterations (matvecs, excluding residual checks)
+    int32_t restarts;
+    int32_t status;             // 0 converged, NPB_ERR_NOCONV, NPB_ERR_BREAKDOWN
+    int32_t pad;
+    double bnorm, rnorm0, rnorm; // ||b||, initial and final TRUE residual norms
+};
+
+int npb_csr_matvec_cb(void* ctx, const double* x, double* y, void* stream) {
+    const npb_csr_view* A = (const npb_csr_view*)ctx;
+    return npb_spmv_launch(A->nrows, A->nnz, A->indptr, A->indices, A->data, x, nullptr, y, 0,
+                           (cudaStream_t)stream);
+}
+
+int64_t npb_fgmres_workspace_bytes(int64_t n, int restart, int flexible) {
+    int64_t nv = (int64_t)(restart + 1) + (flexible ? restart : 1) + 2;  // V, Z, w, r
+    int64_t small = 4 * ((int64_t)restart + 8) * (int64_t)sizeof(double);
+    return nv * ((n * 8 + 255) / 256 * 256) + small + npb_reduce_scratch_bytes() + 1024;
+}
+
+// Solve A x = b.  x holds the initial guess on entry.  Stops when the TRUE
+// residual ||b - A x|| <= max(rtol * ||b||, atol), or after maxiter inner
+// iterations.  `work` = npb_fgmres_workspace_bytes() bytes of device memory.
+int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
+               int restart, int maxiter, double rtol, double atol, int flexible,
+               void* work, int64_t work_bytes, npb_krylov_info* info, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ops || !ops->matvec || n <= 0 || restart < 1) return NPB_ERR_ARG;
+    if (work_bytes < npb_fgmres_workspace_bytes(n, restart, flexible)) {
+        npb_set_error("fgmres: workspace too small");
+        return NPB_ERR_WORKSPACE;
+    }
+    const int m = restart;
+    const int64_t ld = (n * 8 + 255) / 256 * 256 / 8;
+    char* p = (char*)work;
+    double* V = (double*)p;                p += (size_t)(m + 1) * ld * 8;
+    double* Z = (double*)p;                p += (size_t)(flexible ? m : 1) * ld * 8;
+    double* w = (double*)p;                p += (size_t)ld * 8;
+    double* r = (double*)p;                p += (size_t)ld * 8;
+    double* dsmall = (double*)p;           p += 4 * ((size_t)m + 8) * 8;
+    void* scratch = (void*)p;
+    double* d_h1 = dsmall;                 // m+2
+    double* d_h2 = dsmall + (m + 8);       // m+2 ; [m+1] = norm^2 slot
+    double* d_y = dsmall + 2 * (m + 8);    // m
+    NPB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)npb_reduce_scratch_bytes(), st));
+
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(2 * (m + 8));
+    // pinned staging buffer, cached across calls (one Python thread per process)
+    static double* h_pin = nullptr;
+    static size_t h_pin_elems = 0;
+    if (h_pin_elems < (size_t)2 * (m + 8)) {
+        if (h_pin) cudaFreeHost(h_pin);
+        h_pin = nullptr; h_pin_elems = 0;
+        NPB_CUDA(cudaMallocHost(&h_pin, sizeof(double) * 2 * (m + 8)));
+        h_pin_elems = (size_t)2 * (m + 8);
+    }
+
+    auto allreduce = [&](double* buf, int count) -> int {
+        if (ops->allreduce) return ops->allreduce(ops->allreduce_ctx, buf, count, stream);
+        return 0;
+    };
+    auto fetch = [&](double* dst, const double* src, int count) -> int {
+        cudaError_t e = cudaMemcpyAsync(h_pin, src, sizeof(double) * count, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { npb_set_error("fgmres fetch: %s", cudaGetErrorString(e)); return NPB_ERR_CUDA; }
+        memcpy(dst, h_pin, sizeof(double) * count);
+        return 0;
+    };
+    // ||v|| with cross-rank sum
+    auto norm = [&](const double* v, double* out) -> int {
+        int rc = npb_dot_multi_launch(n, 1, v, ld, v, d_h1, scratch, st);
+        if (rc) return rc;
+        if ((rc = allreduce(d_h1, 1))) return rc;
+        double t;
+        if ((rc = fetch(&t, d_h1, 1))) return rc;
+        *out = sqrt(t);
+        return 0;
+    };
+    int rc = 0, status = NPB_ERR_NOCONV;
+    int iters = 0, restarts = 0;
+    double bnorm = 0, rnorm = 0, rnorm0 = 0;
+#define GM_TRY(expr) do { rc = (expr); if (rc) goto done; } while (0)
+
+    GM_TRY(norm(b, &bnorm));
+    {
+        const double tol = fmax(rtol * bnorm, atol);
+        // r = b - A x
+        GM_TRY(ops->matvec(ops->matvec_ctx, x, r, stream));
+        GM_TRY(npb_axpby_launch(n, 1.0, b, -1.0, r, st));
+        GM_TRY(norm(r, &rnorm));
+        rnorm0 = rnorm;
+        while (true) {
+            if (!(rnorm == rnorm)) { status = NPB_ERR_BREAKDOWN; break; }   // NaN
+            if (rnorm <= tol) { status = 0; break; }
+            if (iters >= maxiter) { status = NPB_ERR_NOCONV; break; }
+            // V0 = r / beta
+            GM_TRY(npb_axpby_launch(n, 1.0 / rnorm, r, 0.0, V, st));
+            std::fill(g.begin(), g.end(), 0.0);
+            g[0] = rnorm;
+            int j = 0;
+            bool inner_conv = false;
+            for (; j < m && iters < maxiter; ++j, ++iters) {
+                double* vj = V + (size_t)j * ld;
+                double* zj = flexible ? Z + (size_t)j * ld : Z;
+                if (ops->precond) GM_TRY(ops->precond(ops->precond_ctx, vj, zj, stream));
+                else zj = vj;
+                GM_TRY(ops->matvec(ops->matvec_ctx, zj, w, stream));
+                // CGS2: h1 = V^T w; w -= V h1; h2 = V^T w; w -= V h2 (+ ||w||^2)
+                GM_TRY(npb_dot_multi_launch(n, j + 1, V, ld, w, d_h1, scratch, st));
+                GM_TRY(allreduce(d_h1, j + 1));
+                GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h1, -1.0, w, d_h2 + m + 1, scratch, st));
+                GM_TRY(npb_dot_multi_launch(n, j + 1, V, ld, w, d_h2, scratch, st));
+                GM_TRY(allreduce(d_h2, j + 1));
+                GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h2, -1.0, w, d_h2 + m + 1, scratch, st));
+                GM_TRY(allreduce(d_h2 + m + 1, 1));
+                // one host round trip: both coefficient sets + the norm
+                GM_TRY(fetch(hcol.data(), dsmall, 2 * (m + 8)));
+                double hn = sqrt(hcol[(m + 8) + m + 1]);
+                double* Hj = &H[(size_t)j * (m + 1)];
+                for (int i = 0; i <= j; ++i) Hj[i] = hcol[i] + hcol[(m + 8) + i];
+                Hj[j + 1] = hn;
+                // Givens
+                for (int i = 0; i < j; ++i) {
+                    double t = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
+                    Hj[i + 1] = -sn[i] * Hj[i] + cs[i] * Hj[i + 1];
+                    Hj[i] = t;
+                }
+                double den = hypot(Hj[j], Hj[j + 1]);
+                if (den == 0.0 || !(den == den)) { status = NPB_ERR_BREAKDOWN; goto cycle_end; }
+                cs[j] = Hj[j] / den; sn[j] = Hj[j + 1] / den;
+                Hj[j] = den; Hj[j + 1] = 0.0;
+                g[j + 1] = -sn[j] * g[j];
+                g[j] = cs[j] * g[j];
+                if (fabs(g[j + 1]) <= tol) { inner_conv = true; ++j; ++iters; break; }
+                if (hn <= 1e-300) { inner_conv = true; ++j; ++iters; break; }   // lucky breakdown
+                GM_TRY(npb_axpby_launch(n, 1.0 / hn, w, 0.0, V + (size_t)(j + 1) * ld, st));
+            }
+        cycle_end:
+            (void)inner_conv;
+            // y = H^{-1} g (upper triangular, column-major with stride m+1)
+            for (int i = j - 1; i >= 0; --i) {
+                double s = g[i];
+                for (int k = i + 1; k < j; ++k) s -= H[(size_t)k * (m + 1) + i] * y[k];
+                y[i] = s / H[(size_t)i * (m + 1) + i];
+            }
+            if (j > 0) {
+                NPB_CUDA(cudaMemcpyAsync(d_y, y.data(), sizeof(double) * j, cudaMemcpyHostToDevice, st));
+                if (flexible || !ops->precond) {
+                    const double* basis = ops->precond ? Z : V;
+                    GM_TRY(npb_axpy_multi_launch(n, j, basis, ld, d_y, 1.0, x, d_h2 + m + 1, scratch, st));
+                } else {
+                    // x += M^{-1} (V y)
+                    NPB_CUDA(cudaMemsetAsync(w, 0, (size_t)n * 8, st));
+                    GM_TRY(npb_axpy_multi_launch(n, j, V, ld, d_y, 1.0, w, d_h2 + m + 1, scratch, st));
+                    GM_TRY(ops->precond(ops->precond_ctx, w, Z, stream));
+                    GM_TRY(npb_axpby_launch(n, 1.0, Z, 1.0, x, st));
+                }
+                NPB_CUDA(cudaStreamSynchronize(st));   // y.data() is reused next cycle
+            }
+            ++restarts;
+            if (status == NPB_ERR_BREAKDOWN) break;
+            // true residual
+            GM_TRY(ops->matvec(ops->matvec_ctx, x, r, stream));
+            GM_TRY(npb_axpby_launch(n, 1.0, b, -1.0, r, st));
+            GM_TRY(norm(r, &rnorm));
+        }
+    }
+done:
+    if (info) {
+        info->iters = iters; info->restarts = restarts;
+        info->status = rc ? rc : status;
+        info->pad = 0;
+        info->bnorm = bnorm; info->rnorm0 = rnorm0; info->rnorm = rnorm;
+    }
+    return rc ? rc : status;
+#undef GM_TRY
+}
+
+}  // extern "C"

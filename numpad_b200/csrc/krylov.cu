@@ -1,0 +1,263 @@
+// SpMV and the vector kernels of the Newton linear solve that replaces
+// scipy.sparse.linalg.spsolve (reference adsolve.py:193-195) and the
+// factorized() solves of adsolve.py:78,141: restarted (flexible) GMRES with
+// right preconditioning, CGS2 orthogonalisation done with two fused
+// multi-vector kernels, all reductions deterministic (fixed-order last-block
+// sums, no floating-point atomics).
+//
+// Every kernel is HBM-bound; algorithmic bytes per call are listed in
+// DESIGN.md:  SpMV 12*nnz + 4*(n+1) + 16*n;  multi-dot 8*n*(k+1);
+// multi-axpy 8*n*(k+2).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int RED_BLOCKS = NPB_NUM_SMS * 4;   // persistent grid of the reductions
+constexpr int KC = 16;                        // basis vectors per multi-dot pass
+
+// ---------------------------------------------------------------------- SpMV
+// G lanes cooperate on one row (G = 2..32 picked from nnz/row); lanes read
+// consecutive entries so a warp's loads of indices/data are contiguous.
+// mode 0: y = A x      mode 1: y = b - A x
+template <int G>
+__global__ void __launch_bounds__(TPB)
+k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
+       const int32_t* __restrict__ idx, const double* __restrict__ dat,
+       const double* __restrict__ x, const double* __restrict__ b,
+       double* __restrict__ y, int mode) {
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
+    double s = 0.0;
+    if (r < nrows) {
+        const int32_t e = ptr[r + 1];
+        for (int32_t k = ptr[r] + lane; k < e; k += G)
+            s = fma(dat[k], __ldg(x + idx[k]), s);
+    }
+#pragma unroll
+    for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (r < nrows && lane == 0) y[r] = mode ? b[r] - s : s;
+}
+
+// ------------------------------------------------ deterministic block reduce
+// sums `nv` per-thread values over the block into smem[0..nv)
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /*[8*NV]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        double t = v[j];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0) smem[warp * NV + j] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < TPB / 32; ++w) t += smem[w * NV + threadIdx.x];
+        smem[threadIdx.x] = t;   // safe: thread j only overwrites slot (0,j) it just read
+    }
+    __syncthreads();
+}
+
+// last block to finish adds the per-block partials in block order
+__device__ __forceinline__ bool last_block(unsigned int* ticket) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    return is_last;
+}
+
+// out[j] = V_j . w for j < kc (kc <= KC), V_j = V + j*ld
+__global__ void __launch_bounds__(TPB)
+k_dot_multi(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
+            const double* __restrict__ w, double* __restrict__ partial,
+            unsigned int* __restrict__ ticket, double* __restrict__ out) {
+    __shared__ double smem[(TPB / 32) * KC];
+    double acc[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) acc[j] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * TPB) {
+        const double wi = w[i];
+#pragma unroll
+        for (int j = 0; j < KC; ++j)
+            if (j < kc) acc[j] = fma(V[j * ld + i], wi, acc[j]);
+    }
+    block_sum<KC>(acc, smem);
+    if (threadIdx.x < kc) partial[(int64_t)blockIdx.x * KC + threadIdx.x] = smem[threadIdx.x];
+    if (last_block(ticket)) {
+        __threadfence();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int j = warp; j < kc; j += TPB / 32) {
+            double t = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += partial[(int64_t)b * KC + j];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (lane == 0) out[j] = t;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// w -= sum_j h[j] V_j (j < k), and out_norm2 = ||w_new||^2
+__global__ void __launch_bounds__(TPB)
+k_axpy_multi(int64_t n, int k, const double* __restrict__ V, int64_t ld,
+             const double* __restrict__ h, double sign, double* __restrict__ w,
+             double* __restrict__ partial, unsigned int* __restrict__ ticket,
+             double* __restrict__ out_norm2) {
+    extern __shared__ double hs[];          // k coefficients + reduce scratch
+    double* smem = hs + k;
+    for (int j = threadIdx.x; j < k; j += TPB) hs[j] = sign * h[j];
+    __syncthreads();
+    double nrm[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * TPB) {
+        double s0 = 0.0, s1 = 0.0;
+        int j = 0;
+        for (; j + 1 < k; j += 2) {
+            s0 = fma(hs[j], V[j * ld + i], s0);
+            s1 = fma(hs[j + 1], V[(j + 1) * ld + i], s1);
+        }
+        if (j < k) s0 = fma(hs[j], V[j * ld + i], s0);
+        const double wi = w[i] + (s0 + s1);
+        w[i] = wi;
+        nrm[0] = fma(wi, wi, nrm[0]);
+    }
+    block_sum<1>(nrm, smem);
+    if (threadIdx.x == 0) partial[blockIdx.x] = smem[0];
+    if (last_block(ticket)) {
+        __threadfence();
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += partial[b];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (threadIdx.x == 0) { *out_norm2 = t; *ticket = 0; }
+        }
+    }
+}
+
+// y = a*x + b*y   (b == 0 never reads y)
+__global__ void __launch_bounds__(TPB)
+k_axpby(int64_t n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * TPB)
+        y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+
+int grid_for(int64_t n) {
+    int64_t b = (n + TPB - 1) / TPB;
+    if (b > RED_BLOCKS) b = RED_BLOCKS;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+#define ST(s) ((cudaStream_t)(s))
+
+// ------------------------------------------------------------- internal API
+int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                    const double* dat, const double* x, const double* b, double* y,
+                    int mode, cudaStream_t st) {
+    if (nrows <= 0) return NPB_OK;
+    const double mean = (double)nnz / (double)nrows;
+#define NPB_SPMV(G)                                                             \
+    k_spmv<G><<<npb_blocks(nrows * G, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, \
+                                                           x, b, y, mode)
+    if (mean <= 3.0) NPB_SPMV(2);
+    else if (mean <= 6.0) NPB_SPMV(4);
+    else if (mean <= 16.0) NPB_SPMV(8);
+    else if (mean <= 48.0) NPB_SPMV(16);
+    else NPB_SPMV(32);
+#undef NPB_SPMV
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("spmv");
+    return NPB_OK;
+}
+
+// scratch: RED_BLOCKS*KC doubles of partials followed by one uint ticket
+static inline double* red_partial(void* scratch) { return (double*)scratch; }
+static inline unsigned int* red_ticket(void* scratch) {
+    return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC);
+}
+
+int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
+                         double* out, void* scratch, cudaStream_t st) {
+    for (int j0 = 0; j0 < k; j0 += KC) {
+        int kc = k - j0 < KC ? k - j0 : KC;
+        k_dot_multi<<<grid_for(n), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
+                                                 red_partial(scratch), red_ticket(scratch),
+                                                 out + j0);
+        NPB_COUNT_LAUNCH();
+    }
+    NPB_CHECK_LAUNCH("dot_multi");
+    return NPB_OK;
+}
+
+int npb_axpy_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* h,
+                          double sign, double* w, double* out_norm2, void* scratch,
+                          cudaStream_t st) {
+    size_t sh = sizeof(double) * ((size_t)k + TPB / 32);
+    k_axpy_multi<<<grid_for(n), TPB, sh, st>>>(n, k, V, ld, h, sign, w, red_partial(scratch),
+                                               red_ticket(scratch), out_norm2);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("axpy_multi");
+    return NPB_OK;
+}
+
+int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st) {
+    if (n <= 0) return NPB_OK;
+    k_axpby<<<grid_for(n), TPB, 0, st>>>(n, a, x, b, y);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("axpby");
+    return NPB_OK;
+}
+
+extern "C" {
+
+int64_t npb_reduce_scratch_bytes(void) {
+    return (int64_t)(sizeof(double) * (size_t)RED_BLOCKS * KC + 64);
+}
+
+int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+             const double* data, const double* x, double* y, void* stream) {
+    return npb_spmv_launch(nrows, nnz, indptr, indices, data, x, nullptr, y, 0, ST(stream));
+}
+
+// y = b - A x
+int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
+                      const int32_t* indices, const double* data, const double* x,
+                      const double* b, double* y, void* stream) {
+    return npb_spmv_launch(nrows, nnz, indptr, indices, data, x, b, y, 1, ST(stream));
+}
+
+// out[j] = V[j*ld : j*ld+n] . w ; scratch = npb_reduce_scratch_bytes() bytes,
+// zero-initialised once by the caller
+int npb_dot_multi(int64_t n, int k, const double* V, int64_t ld, const double* w,
+                  double* out, void* scratch, void* stream) {
+    return npb_dot_multi_launch(n, k, V, ld, w, out, scratch, ST(stream));
+}
+
+// w += sign * sum_j h[j] V_j ; *out_norm2 = ||w||^2 afterwards
+int npb_axpy_multi(int64_t n, int k, const double* V, int64_t ld, const double* h,
+                   double sign, double* w, double* out_norm2, void* scratch, void* stream) {
+    return npb_axpy_multi_launch(n, k, V, ld, h, sign, w, out_norm2, scratch, ST(stream));
+}
+
+int npb_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream) {
+    return npb_axpby_launch(n, a, x, b, y, ST(stream));
+}
+
+}  // extern "C"

