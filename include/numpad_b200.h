@@ -62,10 +62,21 @@ int npb_csr_apply_scales(int64_t nnz, const double* in, const npb_scales* sc,
 /* ---- S1: csr * dia_jac  /  dia_jac * csr (csr_matmat with a diagonal) -- */
 int npb_csr_scale_cols(int64_t nnz, const int32_t* indices, const double* in,
                        const npb_scales* sc, const double* d, double* out,
-                       void* stream);
+                       int64_t* zero_count, void* stream);
 int npb_csr_scale_rows(int64_t nrows, const int32_t* indptr, const double* in,
                        const npb_scales* sc, const double* d, double* out,
-                       void* stream);
+                       int64_t* zero_count, void* stream);
+
+/* ---- csr_matmat drops entries whose value is exactly 0.0: every product
+ * that can create zeros reports in *zero_count (int64, device, may be NULL)
+ * how many it wrote; npb_csr_prune_* compacts them away when that is > 0. */
+int npb_csr_prune_symbolic(int64_t nrows, const int32_t* indptr, const double* data,
+                           const npb_scales* sc, int32_t* counts, int32_t* indptr_out,
+                           int64_t* scan_ws, int64_t* stats, void* stream);
+int npb_csr_prune_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                          const double* data, const npb_scales* sc,
+                          const int32_t* indptr_out, int32_t* indices_out, double* out,
+                          void* stream);
 
 /* ---- S1: csr * selection (adjoint order).  map[c] = new column of column c
  * or -1 (dropped); w = optional weight per old column.  `_same`: map keeps
@@ -73,7 +84,7 @@ int npb_csr_scale_rows(int64_t nrows, const int32_t* indptr, const double* in,
 int npb_csr_relabel_same(int64_t nnz, const int32_t* indices, const double* in,
                          const npb_scales* sc, const int32_t* map,
                          const double* w, int32_t* indices_out, double* out,
-                         void* stream);
+                         int64_t* zero_count, void* stream);
 int npb_csr_relabel_symbolic(int64_t nrows, const int32_t* indptr,
                              const int32_t* indices, const int32_t* map,
                              int32_t* counts, int32_t* indptr_out,
@@ -82,7 +93,8 @@ int npb_csr_relabel_numeric(int64_t nrows, const int32_t* indptr,
                             const int32_t* indices, const double* in,
                             const npb_scales* sc, const int32_t* map,
                             const double* w, const int32_t* indptr_out,
-                            int32_t* indices_out, double* out, void* stream);
+                            int32_t* indices_out, double* out,
+                            int64_t* zero_count, void* stream);
 
 /* ---- S1: selection * csr (tangent order): row k of the result is
  * w[k] * B[map[k], :] (empty when map[k] < 0). */
@@ -94,7 +106,8 @@ int npb_csr_gather_rows_numeric(int64_t nrows_out, const int32_t* map,
                                 const double* w, const int32_t* b_indptr,
                                 const int32_t* b_indices, const double* b_data,
                                 const npb_scales* sc, const int32_t* indptr_out,
-                                int32_t* indices_out, double* out, void* stream);
+                                int32_t* indices_out, double* out,
+                                int64_t* zero_count, void* stream);
 
 /* ---- S1: csr + csr (scipy csr_plus_csr; prune != 0 drops exact zeros) -- */
 int npb_spadd_symbolic(int64_t nrows, const int32_t* a_indptr,
@@ -113,7 +126,7 @@ int npb_spadd_numeric(int64_t nrows, const int32_t* a_indptr,
                       double* out, void* stream);
 
 /* ---- S1: general csr * csr (scipy csr_matmat), expansion to COO; finish
- * with npb_coo_to_csr_* (prune = 0: products keep explicit zeros). */
+ * with npb_coo_to_csr_* (prune = 1: csr_matmat never stores a zero). */
 int npb_spgemm_expand_symbolic(int64_t a_nnz, const int32_t* a_indices,
                                const int32_t* b_indptr, int32_t* counts,
                                int32_t* offsets, int64_t* scan_ws,
@@ -163,6 +176,19 @@ int npb_axpy_multi(int64_t n, int k, const double* V, int64_t ld,
                    void* scratch, void* stream);
 int npb_axpby(int64_t n, double a, const double* x, double b, double* y,
               void* stream);
+
+/* ---- S3: banded LU with partial pivoting (robust direct solve for small
+ * systems, stands where the reference calls SuperLU) + host RCM ordering -- */
+int npb_rcm_host(int64_t n, const int32_t* indptr /*[host]*/,
+                 const int32_t* indices /*[host]*/, int32_t* perm /*[host]*/,
+                 int32_t* bw /*[host] lower, upper*/);
+int npb_band_fill(int64_t n, const int32_t* indptr, const int32_t* indices,
+                  const double* data, const int32_t* inv, int kl, int ku, double* AB,
+                  int ldab, void* stream);
+int npb_band_lu_factor(int n, int kl, int ku, double* AB, int ldab, int32_t* ipiv,
+                       int32_t* info, void* stream);
+int npb_band_lu_solve(int n, int kl, int ku, const double* AB, int ldab,
+                      const int32_t* ipiv, double* b, void* stream);
 
 /* ---- S3: the linear solve (replaces spsolve / factorized / _lgmres) ---- */
 typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);

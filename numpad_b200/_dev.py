@@ -4,7 +4,8 @@
 with a chain of pending scalar factors; `DevEye` is `val * I` (what scipy keeps
 as a dia_matrix).  `mul` / `add` reproduce the semantics of the reference's
 `_multiply_ops` / `_add_ops` (adstate.py:282-297) -- including scipy's rules
-that a sum drops exact zeros while a product keeps them, and that an empty
+that sums AND products drop exactly-zero results (csr_plus_csr, csr_matmat in
+scipy 1.18) while `number * csr` keeps them, and that an empty
 product collapses to the int 0 -- by dispatching to the kernels of
 csrc/assembly.cu and csrc/coo.cu through the C-ABI.  No arithmetic happens on
 the host; torch is used for allocation, streams and index plumbing only.
@@ -92,18 +93,21 @@ class DevEye:
 
 
 class DevCsr:
-    __slots__ = ('shape', 'indptr', 'indices', 'data', 'scales', 'nnz', 'max_row')
+    """`clean` = known to hold no explicit zero: true for every sum / product
+    result (scipy prunes both), unknown for uploaded or converted blocks."""
+    __slots__ = ('shape', 'indptr', 'indices', 'data', 'scales', 'nnz', 'max_row', 'clean')
 
-    def __init__(self, shape, indptr, indices, data, scales, nnz, max_row):
+    def __init__(self, shape, indptr, indices, data, scales, nnz, max_row, clean=False):
         self.shape = (int(shape[0]), int(shape[1]))
         self.indptr, self.indices, self.data = indptr, indices, data
         self.scales = tuple(scales)
         self.nnz, self.max_row = int(nnz), int(max_row)
+        self.clean = bool(clean) and all(v != 0.0 for v in self.scales)
 
     @staticmethod
     def empty(shape):
         return DevCsr(shape, torch.zeros(int(shape[0]) + 1, dtype=torch.int32, device=device()),
-                      _empty(0, torch.int32), _empty(0, torch.float64), (), 0, 0)
+                      _empty(0, torch.int32), _empty(0, torch.float64), (), 0, 0, True)
 
     @staticmethod
     def from_scipy(m):
@@ -117,13 +121,14 @@ class DevCsr:
         return DevCsr(m.shape, torch.from_numpy(m.indptr.astype(np.int32)).to(d),
                       torch.from_numpy(m.indices.astype(np.int32)).to(d),
                       torch.from_numpy(m.data.astype(np.float64)).to(d), (), m.nnz,
-                      int(lens.max()) if lens.size else 0)
+                      int(lens.max()) if lens.size else 0,
+                      clean=bool(np.count_nonzero(m.data) == m.nnz))
 
     def scaled(self, a):
         if len(self.scales) >= MAX_SCALES:
             return self.materialized().scaled(a)
         return DevCsr(self.shape, self.indptr, self.indices, self.data,
-                      self.scales + (float(a),), self.nnz, self.max_row)
+                      self.scales + (float(a),), self.nnz, self.max_row, self.clean)
 
     def materialized(self):
         """apply the pending scalar chain (one pass over data)"""
@@ -131,7 +136,27 @@ class DevCsr:
             return self
         out = _empty(self.nnz, torch.float64)
         _call('npb_csr_apply_scales', self.nnz, self.data, make_scales(self.scales), out)
-        return DevCsr(self.shape, self.indptr, self.indices, out, (), self.nnz, self.max_row)
+        return DevCsr(self.shape, self.indptr, self.indices, out, (), self.nnz, self.max_row,
+                      self.clean)
+
+    def pruned(self):
+        """without its exactly-zero entries (what scipy's product / sum emit)"""
+        if self.clean or self.nnz == 0:
+            return self
+        if any(v == 0.0 for v in self.scales):
+            return DevCsr.empty(self.shape)
+        m = self.shape[0]
+        sc = make_scales(self.scales)
+        cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+        stats = _empty(2, torch.int64)
+        _call('npb_csr_prune_symbolic', m, self.indptr, self.data, sc, cnt, ptr, _scan_ws(m), stats)
+        nnz, max_row = _read_stats(stats)
+        if nnz == self.nnz:
+            self.clean = True
+            return self
+        idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+        _call('npb_csr_prune_numeric', m, self.indptr, self.indices, self.data, sc, ptr, idx, dat)
+        return DevCsr(self.shape, ptr, idx, dat, (), nnz, max_row, True)
 
     def todev(self):
         return self
@@ -149,8 +174,10 @@ class DevCsr:
 
     def transpose(self):
         m = self.materialized()
-        return coo_to_csr((self.shape[1], self.shape[0]), m.indices, m.rows(), m.data,
-                          prune=False)
+        t = coo_to_csr((self.shape[1], self.shape[0]), m.indices, m.rows(), m.data,
+                       prune=False)
+        t.clean = self.clean
+        return t
 
     def matvec(self, x, out=None):
         m = self.materialized()
@@ -305,19 +332,34 @@ def coo_to_csr(shape, rows, cols, vals, prune):
     nnz, max_row = _read_stats(stats)
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
     _call('npb_coo_to_csr_numeric', nrows, nnz_in, ws, idx, dat)
-    return DevCsr(shape, ptr, idx, dat, (), nnz, max_row)
+    return DevCsr(shape, ptr, idx, dat, (), nnz, max_row, clean=bool(prune))
+
+
+def _zero_cell():
+    return _empty(1, torch.int64)
+
+
+def _finish(C, zc):
+    """C was written by a product kernel that counted the zeros it produced in
+    `zc`; compact them away if there are any (csr_matmat never stores a zero)"""
+    if zc is not None and int(zc.item()) > 0:
+        C.clean = False
+        return C.pruned()
+    C.clean = True
+    return C
 
 
 def _csr_times_diag(A, d):
-    out = _empty(A.nnz, torch.float64)
-    _call('npb_csr_scale_cols', A.nnz, A.indices, A.data, make_scales(A.scales), d.data, out)
-    return DevCsr(A.shape, A.indptr, A.indices, out, (), A.nnz, A.max_row)
+    out, zc = _empty(A.nnz, torch.float64), _zero_cell()
+    _call('npb_csr_scale_cols', A.nnz, A.indices, A.data, make_scales(A.scales), d.data, out, zc)
+    return _finish(DevCsr(A.shape, A.indptr, A.indices, out, (), A.nnz, A.max_row), zc)
 
 
 def _diag_times_csr(d, B):
-    out = _empty(B.nnz, torch.float64)
-    _call('npb_csr_scale_rows', B.shape[0], B.indptr, B.data, make_scales(B.scales), d.data, out)
-    return DevCsr(B.shape, B.indptr, B.indices, out, (), B.nnz, B.max_row)
+    out, zc = _empty(B.nnz, torch.float64), _zero_cell()
+    _call('npb_csr_scale_rows', B.shape[0], B.indptr, B.data, make_scales(B.scales), d.data,
+          out, zc)
+    return _finish(DevCsr(B.shape, B.indptr, B.indices, out, (), B.nnz, B.max_row), zc)
 
 
 def _csr_times_sel(A, S):
@@ -330,11 +372,12 @@ def _csr_times_sel(A, S):
         if S.full:              # per-entry kernel, any row length
             idx = _empty(A.nnz, torch.int32)
             if S.w is None:     # data buffer and pending scales are shared
-                _call('npb_csr_relabel_same', A.nnz, A.indices, A.data, sc, S.map, None, idx, None)
-                return DevCsr(shape, A.indptr, idx, A.data, A.scales, A.nnz, A.max_row)
-            dat = _empty(A.nnz, torch.float64)
-            _call('npb_csr_relabel_same', A.nnz, A.indices, A.data, sc, S.map, S.w, idx, dat)
-            return DevCsr(shape, A.indptr, idx, dat, (), A.nnz, A.max_row)
+                _call('npb_csr_relabel_same', A.nnz, A.indices, A.data, sc, S.map, None, idx,
+                      None, None)
+                return DevCsr(shape, A.indptr, idx, A.data, A.scales, A.nnz, A.max_row, True)
+            dat, zc = _empty(A.nnz, torch.float64), _zero_cell()
+            _call('npb_csr_relabel_same', A.nnz, A.indices, A.data, sc, S.map, S.w, idx, dat, zc)
+            return _finish(DevCsr(shape, A.indptr, idx, dat, (), A.nnz, A.max_row), zc)
         if A.max_row <= LONG_ROW:
             m = A.shape[0]
             cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
@@ -343,10 +386,11 @@ def _csr_times_sel(A, S):
                   _scan_ws(m), stats)
             nnz, max_row = _read_stats(stats)
             idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+            zc = _zero_cell() if S.w is not None else None
             _call('npb_csr_relabel_numeric', m, A.indptr, A.indices, A.data, sc, S.map, S.w,
-                  ptr, idx, dat)
-            return DevCsr(shape, ptr, idx, dat, (), nnz, max_row)
-    # general: relabel in COO form, drop, sort, merge duplicates
+                  ptr, idx, dat, zc)
+            return _finish(DevCsr(shape, ptr, idx, dat, (), nnz, max_row), zc)
+    # general: relabel in COO form, drop, sort, merge duplicates, prune
     Am = A.materialized()
     cols = S.map[Am.indices.long()]
     vals = Am.data if S.w is None else _mul_entries(Am.data, S.w, Am.indices)
@@ -354,13 +398,13 @@ def _csr_times_sel(A, S):
     if not S.full:
         keep = cols >= 0
         rows, cols, vals = rows[keep], cols[keep], vals[keep]
-    return coo_to_csr(shape, rows.contiguous(), cols.contiguous(), vals.contiguous(), prune=False)
+    return coo_to_csr(shape, rows.contiguous(), cols.contiguous(), vals.contiguous(), prune=True)
 
 
 def _mul_entries(data, w, indices):
     """data[k] * w[indices[k]] through the column-scaling kernel"""
     out = _empty(data.numel(), torch.float64)
-    _call('npb_csr_scale_cols', data.numel(), indices, data, NO_SCALES, w, out)
+    _call('npb_csr_scale_cols', data.numel(), indices, data, NO_SCALES, w, out, None)
     return out
 
 
@@ -373,14 +417,15 @@ def _sel_times_csr(S, B):
     _call('npb_csr_gather_rows_symbolic', m, S.map, B.indptr, cnt, ptr, _scan_ws(m), stats)
     nnz, max_row = _read_stats(stats)
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    zc = _zero_cell() if S.w is not None else None
     _call('npb_csr_gather_rows_numeric', m, S.map, S.w, B.indptr, B.indices, B.data,
-          make_scales(B.scales), ptr, idx, dat)
-    return DevCsr(shape, ptr, idx, dat, (), nnz, max_row)
+          make_scales(B.scales), ptr, idx, dat, zc)
+    return _finish(DevCsr(shape, ptr, idx, dat, (), nnz, max_row), zc)
 
 
 def _csr_times_csr(A, B):
     """general product through expansion + sort (scipy csr_matmat semantics:
-    duplicates summed, explicit zeros kept)"""
+    duplicates summed, exact-zero sums dropped)"""
     shape = (A.shape[0], B.shape[1])
     if A.nnz == 0 or B.nnz == 0:
         return DevCsr.empty(shape)
@@ -394,7 +439,7 @@ def _csr_times_csr(A, B):
     r, c, v = _empty(total, torch.int32), _empty(total, torch.int32), _empty(total, torch.float64)
     _call('npb_spgemm_expand_numeric', A.nnz, A.rows(), A.indices, A.data, make_scales(A.scales),
           B.indptr, B.indices, B.data, make_scales(B.scales), off, r, c, v)
-    return coo_to_csr(shape, r, c, v, prune=False)
+    return coo_to_csr(shape, r, c, v, prune=True)
 
 
 def _csr_plus_csr(A, B):
@@ -414,7 +459,7 @@ def _csr_plus_csr(A, B):
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
     _call('npb_spadd_numeric', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
           B.data, sb, 1, ptr, idx, dat)
-    return DevCsr(A.shape, ptr, idx, dat, (), nnz, max_row)
+    return DevCsr(A.shape, ptr, idx, dat, (), nnz, max_row, True)
 
 
 # --------------------------------------------------------------------------- #
@@ -461,26 +506,33 @@ def _multiply_ops(op0, op1):
         if isinstance(m, (DevEye, DevCsr)):
             return _collapse(m.scaled(s))
         return _collapse(m.todev().scaled(s))
-    # matrix x matrix
+    # matrix x matrix: csr_matmat semantics -- operands' explicit zeros never
+    # reach the result, so accumulated operands are cleaned first
     if isinstance(a, DevEye) and isinstance(b, DevEye):
         return DevEye(a.n, a.val * b.val)
     if isinstance(a, DevEye):           # val*I x block
         if a.val == 0.0:                # an all-zero dia converts to an empty CSR
             return 0
-        c = b if isinstance(b, DevCsr) else b.todev()
+        c = (b if isinstance(b, DevCsr) else b.todev()).pruned()
         return _collapse(c if a.val == 1.0 else c.scaled(a.val))
     if isinstance(b, DevEye):
         if b.val == 0.0:
             return 0
-        c = a if isinstance(a, DevCsr) else a.todev()
+        c = (a if isinstance(a, DevCsr) else a.todev()).pruned()
         return _collapse(c if b.val == 1.0 else c.scaled(b.val))
     if isinstance(a, DevCsr):           # adjoint order: accumulated x local block
+        a = a.pruned()
+        if a.nnz == 0:
+            return 0
         if isinstance(b, dia_jac):
             return _collapse(_csr_times_diag(a, b))
         if isinstance(b, sel_jac):
             return _collapse(_csr_times_sel(a, b))
         return _collapse(_csr_times_csr(a, b.todev()))
     if isinstance(b, DevCsr):           # tangent order: local block x accumulated
+        b = b.pruned()
+        if b.nnz == 0:
+            return 0
         if isinstance(a, dia_jac):
             return _collapse(_diag_times_csr(a, b))
         if isinstance(a, sel_jac):

@@ -19,6 +19,16 @@ namespace {
 
 constexpr int TPB = 256;
 
+// scipy's csr_matmat drops entries whose value is exactly 0.0 (scipy >= 1.1x:
+// `if (sums[head] != 0)`), so every product that can create zeros reports how
+// many it produced; the host compacts the result only when that count is > 0
+// (it almost never is).  Must be reached by all 32 lanes of a warp.
+__device__ __forceinline__ void count_zeros(bool is_zero, int64_t* zero_count) {
+    const unsigned m = __ballot_sync(0xffffffffu, is_zero);
+    if (m && (threadIdx.x & 31) == 0 && zero_count)
+        atomicAdd((unsigned long long*)zero_count, (unsigned long long)__popc(m));
+}
+
 // ---------------------------------------------------------------- elementwise
 __global__ void __launch_bounds__(TPB)
 k_apply_scales(int64_t nnz, const double* __restrict__ in, npb_scales sc,
@@ -31,9 +41,16 @@ k_apply_scales(int64_t nnz, const double* __restrict__ in, npb_scales sc,
 __global__ void __launch_bounds__(TPB)
 k_scale_cols(int64_t nnz, const int32_t* __restrict__ idx,
              const double* __restrict__ in, npb_scales sc,
-             const double* __restrict__ d, double* __restrict__ out) {
+             const double* __restrict__ d, double* __restrict__ out,
+             int64_t* __restrict__ zero_count) {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (k < nnz) out[k] = __dmul_rn(npb_apply(sc, in[k]), __ldg(d + idx[k]));
+    bool z = false;
+    if (k < nnz) {
+        const double v = __dmul_rn(npb_apply(sc, in[k]), __ldg(d + idx[k]));
+        out[k] = v;
+        z = (v == 0.0);
+    }
+    count_zeros(z, zero_count);
 }
 
 // C = diag(d) * A: data_out[k] = d[row(k)] * chain(data[k])   (dia_jac x csr)
@@ -41,13 +58,22 @@ k_scale_cols(int64_t nnz, const int32_t* __restrict__ idx,
 __global__ void __launch_bounds__(TPB)
 k_scale_rows(int64_t nrows, const int32_t* __restrict__ ptr,
              const double* __restrict__ in, npb_scales sc,
-             const double* __restrict__ d, double* __restrict__ out) {
+             const double* __restrict__ d, double* __restrict__ out,
+             int64_t* __restrict__ zero_count) {
     const int lane = threadIdx.x & 7;
     int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) >> 3;
-    if (r >= nrows) return;
-    const double dr = d[r];
-    for (int32_t k = ptr[r] + lane, e = ptr[r + 1]; k < e; k += 8)
-        out[k] = __dmul_rn(dr, npb_apply(sc, in[k]));
+    int nz = 0;
+    if (r < nrows) {
+        const double dr = d[r];
+        for (int32_t k = ptr[r] + lane, e = ptr[r + 1]; k < e; k += 8) {
+            const double v = __dmul_rn(dr, npb_apply(sc, in[k]));
+            out[k] = v;
+            nz += (v == 0.0);
+        }
+    }
+    for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
+    if (nz && (threadIdx.x & 31) == 0 && zero_count)
+        atomicAdd((unsigned long long*)zero_count, (unsigned long long)nz);
 }
 
 // C = A * S with S a selection whose map is strictly increasing on the kept
@@ -56,12 +82,20 @@ __global__ void __launch_bounds__(TPB)
 k_relabel_same(int64_t nnz, const int32_t* __restrict__ idx,
                const double* __restrict__ in, npb_scales sc,
                const int32_t* __restrict__ map, const double* __restrict__ w,
-               int32_t* __restrict__ idx_out, double* __restrict__ out) {
+               int32_t* __restrict__ idx_out, double* __restrict__ out,
+               int64_t* __restrict__ zero_count) {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (k >= nnz) return;
-    const int32_t c = idx[k];
-    idx_out[k] = __ldg(map + c);
-    if (w) out[k] = __dmul_rn(npb_apply(sc, in[k]), __ldg(w + c));
+    bool z = false;
+    if (k < nnz) {
+        const int32_t c = idx[k];
+        idx_out[k] = __ldg(map + c);
+        if (w) {
+            const double v = __dmul_rn(npb_apply(sc, in[k]), __ldg(w + c));
+            out[k] = v;
+            z = (v == 0.0);
+        }
+    }
+    if (w) count_zeros(z, zero_count);
 }
 
 // ------------------------------------------------------ relabel with dropping
@@ -87,21 +121,28 @@ k_relabel_fill(int64_t nrows, const int32_t* __restrict__ ptr,
                const int32_t* __restrict__ idx, const double* __restrict__ in,
                npb_scales sc, const int32_t* __restrict__ map,
                const double* __restrict__ w, const int32_t* __restrict__ optr,
-               int32_t* __restrict__ oidx, double* __restrict__ out) {
+               int32_t* __restrict__ oidx, double* __restrict__ out,
+               int64_t* __restrict__ zero_count) {
     int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (r >= nrows) return;
-    int32_t o = optr[r];
-    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
-        const int32_t c = idx[k];
-        const int32_t m = __ldg(map + c);
-        if (m >= 0) {
-            double v = npb_apply(sc, in[k]);
-            if (w) v = __dmul_rn(v, __ldg(w + c));
-            oidx[o] = m;
-            out[o] = v;
-            ++o;
+    int nz = 0;
+    if (r < nrows) {
+        int32_t o = optr[r];
+        for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
+            const int32_t c = idx[k];
+            const int32_t m = __ldg(map + c);
+            if (m >= 0) {
+                double v = npb_apply(sc, in[k]);
+                if (w) v = __dmul_rn(v, __ldg(w + c));
+                oidx[o] = m;
+                out[o] = v;
+                nz += (v == 0.0);
+                ++o;
+            }
         }
     }
+    for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
+    if (nz && (threadIdx.x & 31) == 0 && zero_count)
+        atomicAdd((unsigned long long*)zero_count, (unsigned long long)nz);
 }
 
 // ------------------------------------------------- row gather (tangent order)
@@ -126,18 +167,55 @@ k_gather_fill(int64_t nrows, const int32_t* __restrict__ map,
               const double* __restrict__ w, const int32_t* __restrict__ bptr,
               const int32_t* __restrict__ bidx, const double* __restrict__ bdat,
               npb_scales sc, const int32_t* __restrict__ optr,
-              int32_t* __restrict__ oidx, double* __restrict__ out) {
+              int32_t* __restrict__ oidx, double* __restrict__ out,
+              int64_t* __restrict__ zero_count) {
     const int lane = threadIdx.x & 7;
     int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) >> 3;
+    int nz = 0;
+    const int32_t m = (r < nrows) ? map[r] : -1;
+    if (m >= 0) {
+        const int32_t b0 = bptr[m], len = bptr[m + 1] - b0, o = optr[r];
+        const double wr = w ? w[r] : 1.0;
+        for (int32_t k = lane; k < len; k += 8) {
+            oidx[o + k] = bidx[b0 + k];
+            double v = npb_apply(sc, bdat[b0 + k]);
+            if (w) v = __dmul_rn(wr, v);
+            out[o + k] = v;
+            nz += (v == 0.0);
+        }
+    }
+    for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
+    if (nz && (threadIdx.x & 31) == 0 && zero_count)
+        atomicAdd((unsigned long long*)zero_count, (unsigned long long)nz);
+}
+
+// ------------------------------------------------- drop explicit zero entries
+__global__ void __launch_bounds__(TPB)
+k_prune_count(int64_t nrows, const int32_t* __restrict__ ptr,
+              const double* __restrict__ dat, npb_scales sc,
+              int32_t* __restrict__ cnt, int64_t* __restrict__ stats) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    int32_t c = 0;
+    if (r < nrows) {
+        for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) c += (npb_apply(sc, dat[k]) != 0.0);
+        cnt[r] = c;
+    }
+    for (int d = 16; d; d >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, d));
+    if ((threadIdx.x & 31) == 0 && c > 0)
+        atomicMax((unsigned long long*)(stats + 1), (unsigned long long)c);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_prune_fill(int64_t nrows, const int32_t* __restrict__ ptr,
+             const int32_t* __restrict__ idx, const double* __restrict__ dat,
+             npb_scales sc, const int32_t* __restrict__ optr,
+             int32_t* __restrict__ oidx, double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r >= nrows) return;
-    const int32_t m = map[r];
-    if (m < 0) return;
-    const int32_t b0 = bptr[m], len = bptr[m + 1] - b0, o = optr[r];
-    const double wr = w ? w[r] : 1.0;
-    for (int32_t k = lane; k < len; k += 8) {
-        oidx[o + k] = bidx[b0 + k];
-        double v = npb_apply(sc, bdat[b0 + k]);
-        out[o + k] = w ? __dmul_rn(wr, v) : v;
+    int32_t o = optr[r];
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
+        const double v = npb_apply(sc, dat[k]);
+        if (v != 0.0) { oidx[o] = idx[k]; out[o] = v; ++o; }
     }
 }
 
@@ -294,9 +372,10 @@ int npb_csr_apply_scales(int64_t nnz, const double* in, const npb_scales* sc,
 
 int npb_csr_scale_cols(int64_t nnz, const int32_t* indices, const double* in,
                        const npb_scales* sc, const double* d, double* out,
-                       void* stream) {
+                       int64_t* zero_count, void* stream) {
+    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
     if (nnz <= 0) return NPB_OK;
-    k_scale_cols<<<npb_blocks(nnz, TPB), TPB, 0, ST(stream)>>>(nnz, indices, in, *sc, d, out);
+    k_scale_cols<<<npb_blocks(nnz, TPB), TPB, 0, ST(stream)>>>(nnz, indices, in, *sc, d, out, zero_count);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_scale_cols");
     return NPB_OK;
@@ -304,9 +383,10 @@ int npb_csr_scale_cols(int64_t nnz, const int32_t* indices, const double* in,
 
 int npb_csr_scale_rows(int64_t nrows, const int32_t* indptr, const double* in,
                        const npb_scales* sc, const double* d, double* out,
-                       void* stream) {
+                       int64_t* zero_count, void* stream) {
+    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
     if (nrows <= 0) return NPB_OK;
-    k_scale_rows<<<npb_blocks(nrows * 8, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, in, *sc, d, out);
+    k_scale_rows<<<npb_blocks(nrows * 8, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, in, *sc, d, out, zero_count);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_scale_rows");
     return NPB_OK;
@@ -315,10 +395,11 @@ int npb_csr_scale_rows(int64_t nrows, const int32_t* indptr, const double* in,
 int npb_csr_relabel_same(int64_t nnz, const int32_t* indices, const double* in,
                          const npb_scales* sc, const int32_t* map,
                          const double* w, int32_t* indices_out, double* out,
-                         void* stream) {
+                         int64_t* zero_count, void* stream) {
+    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
     if (nnz <= 0) return NPB_OK;
     if (w && !out) return NPB_ERR_ARG;
-    k_relabel_same<<<npb_blocks(nnz, TPB), TPB, 0, ST(stream)>>>(nnz, indices, in, *sc, map, w, indices_out, out);
+    k_relabel_same<<<npb_blocks(nnz, TPB), TPB, 0, ST(stream)>>>(nnz, indices, in, *sc, map, w, indices_out, out, zero_count);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_relabel_same");
     return NPB_OK;
@@ -340,9 +421,11 @@ int npb_csr_relabel_numeric(int64_t nrows, const int32_t* indptr,
                             const int32_t* indices, const double* in,
                             const npb_scales* sc, const int32_t* map,
                             const double* w, const int32_t* indptr_out,
-                            int32_t* indices_out, double* out, void* stream) {
+                            int32_t* indices_out, double* out,
+                            int64_t* zero_count, void* stream) {
+    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
     if (nrows <= 0) return NPB_OK;
-    k_relabel_fill<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, in, *sc, map, w, indptr_out, indices_out, out);
+    k_relabel_fill<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, in, *sc, map, w, indptr_out, indices_out, out, zero_count);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_relabel_fill");
     return NPB_OK;
@@ -363,11 +446,35 @@ int npb_csr_gather_rows_numeric(int64_t nrows_out, const int32_t* map,
                                 const double* w, const int32_t* b_indptr,
                                 const int32_t* b_indices, const double* b_data,
                                 const npb_scales* sc, const int32_t* indptr_out,
-                                int32_t* indices_out, double* out, void* stream) {
+                                int32_t* indices_out, double* out,
+                                int64_t* zero_count, void* stream) {
+    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
     if (nrows_out <= 0) return NPB_OK;
-    k_gather_fill<<<npb_blocks(nrows_out * 8, TPB), TPB, 0, ST(stream)>>>(nrows_out, map, w, b_indptr, b_indices, b_data, *sc, indptr_out, indices_out, out);
+    k_gather_fill<<<npb_blocks(nrows_out * 8, TPB), TPB, 0, ST(stream)>>>(nrows_out, map, w, b_indptr, b_indices, b_data, *sc, indptr_out, indices_out, out, zero_count);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_gather_fill");
+    return NPB_OK;
+}
+
+// drop the entries whose (scaled) value is exactly 0.0
+int npb_csr_prune_symbolic(int64_t nrows, const int32_t* indptr, const double* data,
+                           const npb_scales* sc, int32_t* counts, int32_t* indptr_out,
+                           int64_t* scan_ws, int64_t* stats, void* stream) {
+    NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), ST(stream)));
+    k_prune_count<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, data, *sc, counts, stats);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_prune_count");
+    return npb_scan_launch(counts, indptr_out, nrows, scan_ws, stats, ST(stream));
+}
+
+int npb_csr_prune_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                          const double* data, const npb_scales* sc,
+                          const int32_t* indptr_out, int32_t* indices_out, double* out,
+                          void* stream) {
+    if (nrows <= 0) return NPB_OK;
+    k_prune_fill<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, *sc, indptr_out, indices_out, out);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_prune_fill");
     return NPB_OK;
 }
 

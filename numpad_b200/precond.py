@@ -1,21 +1,110 @@
-"""Preconditioner selection for the Newton linear solve (seam S3).
+"""Preconditioner / direct-solver selection for the Newton linear solve (S3).
 
 build(A, kind) -> (M, method):
-  'none'   : M is None -- plain restarted GMRES (full GMRES when n is tiny)
-  'direct' : M.solve(b) is a device banded LU (csrc/bandlu.cu), for systems
-             small enough that n * bandwidth^2 is cheap
+  'none'   : M is None -- plain restarted GMRES
+  'direct' : M.solve(b) is a device banded LU with partial pivoting
+             (csrc/bandlu.cu) after a host RCM ordering; for systems small
+             enough that n * bandwidth^2 is cheap (the reference's own config 1)
   'lsc'    : block preconditioner for saddle-point Jacobians (rows with a
              zero diagonal = constraints): least-squares-commutator Schur
-             complement, multigrid sub-solves (csrc/amg.cu)
-  'auto'   : picks from the structure of A
+             complement with multigrid sub-solves
+  'auto'   : picks from the size and structure of A
 """
-from . import _dev
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._dev import device, stream_ptr, _empty, _call
+
+# direct solve when  n * kl * (kl + ku) <= DIRECT_WORK  and the band fits
+DIRECT_WORK = 2.5e9
+DIRECT_BYTES = 8e9
+
+_rcm_cache = {}
+
+
+def _pattern_key(A):
+    n, nnz = A.shape[0], A.nnz
+    if nnz == 0:
+        return (n, 0, 0)
+    w = torch.arange(1, nnz + 1, dtype=torch.int64, device=device())
+    return (n, nnz, int((A.indices.to(torch.int64) * (w % 8191)).sum().item()))
+
+
+def rcm(A):
+    """(perm, inv, kl, ku) on the device for the pattern of A (cached)"""
+    key = _pattern_key(A)
+    hit = _rcm_cache.get(key)
+    if hit is not None:
+        return hit
+    n = A.shape[0]
+    ptr = np.ascontiguousarray(A.indptr.cpu().numpy())
+    idx = np.ascontiguousarray(A.indices.cpu().numpy())
+    perm = np.empty(n, np.int32)
+    bw = np.zeros(2, np.int32)
+    rc = _lib.lib().cdll.npb_rcm_host(n, ptr.ctypes.data, idx.ctypes.data, perm.ctypes.data,
+                                      bw.ctypes.data)
+    if rc != 0:
+        raise RuntimeError('npb_rcm_host failed')
+    inv = np.empty(n, np.int32)
+    inv[perm] = np.arange(n, dtype=np.int32)
+    out = (torch.from_numpy(perm).to(device()), torch.from_numpy(inv).to(device()),
+           int(bw[0]), int(bw[1]))
+    if len(_rcm_cache) > 8:
+        _rcm_cache.clear()
+    _rcm_cache[key] = out
+    return out
+
+
+class BandLU:
+    """P A P^T = L U in LAPACK band storage on the device."""
+
+    def __init__(self, A, ordering=None):
+        A = A.materialized()
+        self.n = n = A.shape[0]
+        self.perm, self.inv, self.kl, self.ku = ordering or rcm(A)
+        self.ldab = 2 * self.kl + self.ku + 1
+        self.AB = torch.zeros(self.ldab * n, dtype=torch.float64, device=device())
+        _call('npb_band_fill', n, A.indptr, A.indices, A.data, self.inv, self.kl, self.ku,
+              self.AB, self.ldab)
+        self.ipiv = _empty(n, torch.int32)
+        info = _empty(1, torch.int32)
+        _call('npb_band_lu_factor', n, self.kl, self.ku, self.AB, self.ldab, self.ipiv, info)
+        self.info = int(info.item())
+        if self.info != 0:
+            raise np.linalg.LinAlgError('banded LU: matrix is exactly singular '
+                                        '(zero pivot in column %d)' % (self.info - 1))
+
+    @staticmethod
+    def cost(A):
+        _, _, kl, ku = rcm(A)
+        n = A.shape[0]
+        return n * kl * (kl + ku), 8.0 * n * (2 * kl + ku + 1)
+
+    def solve(self, b):
+        y = b.reshape(-1)[self.perm.long()].contiguous()
+        _call('npb_band_lu_solve', self.n, self.kl, self.ku, self.AB, self.ldab, self.ipiv, y)
+        x = torch.empty_like(y)
+        x[self.perm.long()] = y
+        return x
+
+    def apply(self, r, z):
+        z.copy_(self.solve(r))
 
 
 def build(A, kind='auto'):
     n = A.shape[0]
     if kind == 'auto':
-        kind = 'none'
+        if n <= 200000:
+            work, nbytes = BandLU.cost(A)
+            if work <= DIRECT_WORK and nbytes <= DIRECT_BYTES:
+                kind = 'direct'
+        if kind == 'auto':
+            kind = 'none'
     if kind == 'none':
         return None, 'gmres'
+    if kind == 'direct':
+        return BandLU(A), 'direct'
     raise ValueError('unknown preconditioner %r' % kind)

@@ -16,8 +16,9 @@ All arithmetic of the reference on this path lives in third-party code that is
 not vendored in /root/reference (no version pinned there): scipy.sparse
 ``_sparsetools`` (csr_matmat, csr_plus_csr, coo_tocsr) and SuperLU via
 ``scipy.sparse.linalg``; this oracle calls the very same routines (the image
-has numpy 2.3 / scipy 1.18), so its sparsity rules (sum prunes exact zeros,
-product keeps them) are the reference's by construction.
+has numpy 2.3 / scipy 1.18), so its sparsity rules (sums and products drop
+exactly-zero results, `number * csr` keeps them) are the reference's by
+construction.
 
 Parity pinning: ``tests/golden/make_golden.py`` imports the UNMODIFIED
 reference from /root/reference (through a 3-line numpy-2 shim) and stores its

@@ -323,7 +323,8 @@ def c_cancel(xp, rng):
 
 
 def c_zero_diag(xp, rng):
-    """products keep explicit zeros, sums drop them."""
+    """zero diagonal entries: the blocks carry explicit zeros, scipy's product
+    and sum both drop them (value-dependent pattern)."""
     u = xp.array(np.array([0.0, 1.0, 0.0, 2.0]))
     w = u * u
     return w + w[::-1] * u, u

@@ -48,3 +48,29 @@ def test_no_cpu_fallback():
     import numpad_b200 as npd
     with pytest.raises(RuntimeError):
         npd.zeros(4)
+
+
+def test_rcm_host():
+    """npb_rcm_host is host code: a valid permutation whose bandwidth matches
+    scipy's reverse Cuthill-McKee on a 2-D grid operator"""
+    import numpy as np
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    n1 = 30
+    T = sp.diags([-1, 2, -1], [-1, 0, 1], shape=(n1, n1))
+    A = sp.csr_matrix(sp.kron(sp.identity(n1), T) + sp.kron(T, sp.identity(n1)))
+    rng = np.random.RandomState(0)
+    p0 = rng.permutation(n1 * n1)
+    A = A[p0][:, p0].tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    ptr, idx = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    perm, bw = np.empty(n, np.int32), np.zeros(2, np.int32)
+    rc = _lib.lib().cdll.npb_rcm_host(n, ptr.ctypes.data, idx.ctypes.data,
+                                      perm.ctypes.data, bw.ctypes.data)
+    assert rc == 0 and sorted(perm) == list(range(n))
+    B = A[perm][:, perm].tocoo()
+    assert (B.row - B.col).max() == bw[0] and (B.col - B.row).max() == bw[1]
+    q = reverse_cuthill_mckee(A, symmetric_mode=True)
+    C = A[q][:, q].tocoo()
+    assert bw[0] <= 1.5 * (C.row - C.col).max()

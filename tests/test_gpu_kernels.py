@@ -82,8 +82,10 @@ def test_diag_products(dev):
     A = dev.DevCsr.from_scipy(a).scaled(1.7)
     dc = rng.standard_normal(500); dc[::7] = 0.0
     dr = rng.standard_normal(600)
-    check(dev._multiply_ops(A, dev.dia_jac(dc)), (a * 1.7) * sp.diags(dc).tocsr(), 0.0)
-    check(dev._multiply_ops(dev.dia_jac(dr), A), sp.diags(dr).tocsr() * (a * 1.7), 0.0)
+    # dia_jac.tocsr keeps explicit zeros (reference adstate.py:244-250)
+    dia = lambda d: sp.csr_matrix((d, np.arange(d.size), np.arange(d.size + 1)))
+    check(dev._multiply_ops(A, dev.dia_jac(dc)), (a * 1.7) * dia(dc), 0.0)
+    check(dev._multiply_ops(dev.dia_jac(dr), A), dia(dr) * (a * 1.7), 0.0)
 
 
 def sel_scipy(map_, ncols, w=None):
@@ -173,3 +175,36 @@ def test_fgmres_poisson(dev):
     got3, info3 = linsolve.fgmres(None, b, matvec=lambda v, y: A.matvec(v, out=y), rtol=1e-12,
                                   restart=80, maxiter=4000)
     assert info3['status'] == 0 and info3['iters'] == info['iters']
+
+
+@pytest.mark.parametrize('n,density', [(1, 1.0), (40, 0.2), (700, 0.01), (3000, 0.002)])
+def test_band_lu(dev, n, density):
+    """pivoted banded LU after RCM vs scipy spsolve, incl. zero diagonals"""
+    import torch
+    import scipy.sparse.linalg as spla
+    from numpad_b200 import precond, linsolve
+    rng = np.random.RandomState(7)
+    a = rand_csr(rng, n, n, density) + sp.diags(rng.standard_normal(n) * 3).tocsr()
+    a = a.tolil()
+    if n > 10:                      # saddle-like: some zero diagonals, needs pivoting
+        for i in range(0, n - 1, 7):
+            a[i, i] = 0.0
+            a[i, i + 1] = 1.5
+            a[i + 1, i] = -2.0
+    a = sp.csr_matrix(a)
+    a.eliminate_zeros()
+    x = rng.standard_normal(n)
+    b = a @ x
+    A = dev.DevCsr.from_scipy(a)
+    lu = precond.BandLU(A)
+    got = lu.solve(torch.from_numpy(b).to(dev.device())).cpu().numpy()
+    ref = spla.spsolve(a.tocsc(), b) if n > 1 else b / a.toarray()[0, 0]
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9 * scale)
+    # through the front door (direct + refinement), and the transposed system
+    got2 = linsolve.solve(A, torch.from_numpy(b).to(dev.device()), precond='direct').cpu().numpy()
+    np.testing.assert_allclose(got2, ref, rtol=0, atol=1e-10 * scale)
+    bt = a.T @ x
+    got3 = linsolve.solve(A, torch.from_numpy(bt).to(dev.device()), transpose=True,
+                          precond='direct').cpu().numpy()
+    np.testing.assert_allclose(got3, x, rtol=0, atol=1e-8 * np.abs(x).max())
