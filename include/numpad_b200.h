@@ -219,6 +219,66 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
                void* work, int64_t work_bytes, npb_krylov_info* info,
                void* stream);
 
+/* ---- S3: algebraic multigrid + least-squares-commutator preconditioner --
+ * Setup pieces (device): diagonal extraction, MIS aggregation, dense inverse
+ * of the coarsest operator.  Solve phase: npb_amg_vcycle, and the two
+ * npb_apply_fn callbacks usable as `precond` of npb_fgmres. */
+typedef struct npb_csr_mat {
+    int64_t nrows, ncols, nnz;
+    const int32_t* indptr;
+    const int32_t* indices;
+    const double* data;
+} npb_csr_mat;
+
+typedef struct npb_amg_level {      /* [host] */
+    npb_csr_mat A, P, R;            /* operator, prolongation, restriction */
+    const double* dinv;             /* 1 / diag(A) */
+    double *x, *x2, *b, *r;         /* work vectors of the level's size */
+} npb_amg_level;
+
+typedef struct npb_amg {            /* [host] */
+    int32_t nlevels, nu_pre, nu_post, coarse_n;
+    double omega;
+    const double* coarse_inv;       /* dense inverse of the coarsest operator */
+    npb_amg_level* levels;
+} npb_amg;
+
+typedef struct npb_amg_precond {    /* [host] ctx of npb_amg_apply_cb */
+    const npb_amg* amg;
+    npb_csr_mat A;
+    int32_t cycles, pad;
+    double *r, *dx;
+} npb_amg_precond;
+
+typedef struct npb_lsc {            /* [host] ctx of npb_lsc_apply_cb */
+    int64_t n, nv, np;
+    const int32_t* vset;            /* rows with a diagonal entry  */
+    const int32_t* pset;            /* rows with a zero diagonal   */
+    npb_csr_mat A, G, D, Lm;        /* J[V,V], J[V,P], J[P,V], -D G */
+    const double* a_dinv;
+    const npb_amg* amg_a;
+    const npb_amg* amg_l;
+    int32_t cycles_a, cycles_l;
+    double* wv[5];
+    double* wp[5];
+} npb_lsc;
+
+int npb_csr_diagonal(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                     const double* data, double* diag, void* stream);
+int npb_amg_aggregate(int64_t n, const int32_t* indptr, const int32_t* indices,
+                      const double* data, double theta, int max_rounds, int8_t* state,
+                      int8_t* state2, int32_t* flag, int32_t* root_id, int32_t* agg,
+                      int32_t* undecided, int64_t* scan_ws, int64_t* stats,
+                      void* stream);
+int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices,
+                      const double* data, double* W, double* Minv, int32_t* info,
+                      void* stream);
+int npb_gather(int64_t n, const int32_t* idx, const double* src, double* dst,
+               void* stream);
+int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream);
+int npb_amg_apply_cb(void* ctx, const double* x, double* y, void* stream);
+int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,248 @@
+"""Setup of the multigrid hierarchies and of the least-squares-commutator block
+preconditioner whose solve phase lives in csrc/amg.cu.
+
+Everything numeric runs on the device through the C-ABI: the strength graph /
+MIS aggregation (npb_amg_aggregate), the prolongation smoothing and the
+Galerkin products R A P (the same SpGEMM / SpAdd kernels that accumulate
+Jacobians), the dense inverse of the coarsest operator (npb_dense_inverse).
+Python only owns the buffers and fills the descriptor structs.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._dev import (DevCsr, sel_jac, dia_jac, device, stream_ptr, _empty, _call, _scan_ws,
+                   _read_stats, _csr_times_sel, _csr_times_csr, _diag_times_csr,
+                   _csr_plus_csr, _sel_times_csr)
+
+
+class CsrMat(ctypes.Structure):
+    _fields_ = [('nrows', ctypes.c_int64), ('ncols', ctypes.c_int64), ('nnz', ctypes.c_int64),
+                ('indptr', ctypes.c_void_p), ('indices', ctypes.c_void_p),
+                ('data', ctypes.c_void_p)]
+
+
+class AmgLevel(ctypes.Structure):
+    _fields_ = [('A', CsrMat), ('P', CsrMat), ('R', CsrMat), ('dinv', ctypes.c_void_p),
+                ('x', ctypes.c_void_p), ('x2', ctypes.c_void_p), ('b', ctypes.c_void_p),
+                ('r', ctypes.c_void_p)]
+
+
+class AmgStruct(ctypes.Structure):
+    _fields_ = [('nlevels', ctypes.c_int32), ('nu_pre', ctypes.c_int32),
+                ('nu_post', ctypes.c_int32), ('coarse_n', ctypes.c_int32),
+                ('omega', ctypes.c_double), ('coarse_inv', ctypes.c_void_p),
+                ('levels', ctypes.POINTER(AmgLevel))]
+
+
+class AmgPrecondStruct(ctypes.Structure):
+    _fields_ = [('amg', ctypes.c_void_p), ('A', CsrMat), ('cycles', ctypes.c_int32),
+                ('pad', ctypes.c_int32), ('r', ctypes.c_void_p), ('dx', ctypes.c_void_p)]
+
+
+class LscStruct(ctypes.Structure):
+    _fields_ = [('n', ctypes.c_int64), ('nv', ctypes.c_int64), ('np', ctypes.c_int64),
+                ('vset', ctypes.c_void_p), ('pset', ctypes.c_void_p),
+                ('A', CsrMat), ('G', CsrMat), ('D', CsrMat), ('Lm', CsrMat),
+                ('a_dinv', ctypes.c_void_p), ('amg_a', ctypes.c_void_p),
+                ('amg_l', ctypes.c_void_p), ('cycles_a', ctypes.c_int32),
+                ('cycles_l', ctypes.c_int32), ('wv', ctypes.c_void_p * 5),
+                ('wp', ctypes.c_void_p * 5)]
+
+
+def csr_mat(A):
+    m = CsrMat()
+    m.nrows, m.ncols, m.nnz = A.shape[0], A.shape[1], A.nnz
+    m.indptr, m.indices, m.data = A.indptr.data_ptr(), A.indices.data_ptr(), A.data.data_ptr()
+    return m
+
+
+def diagonal(A):
+    d = _empty(A.shape[0], torch.float64)
+    _call('npb_csr_diagonal', A.shape[0], A.indptr, A.indices, A.data, d)
+    return d
+
+
+def aggregate(A, theta, max_rounds=12):
+    """-> (agg int32[n], n_agg)"""
+    n = A.shape[0]
+    state, state2 = _empty(n, torch.int8), _empty(n, torch.int8)
+    flag, root_id, agg = _empty(n, torch.int32), _empty(n + 1, torch.int32), _empty(n, torch.int32)
+    und = _empty(2, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_amg_aggregate', n, A.indptr, A.indices, A.data, float(theta), int(max_rounds),
+          state, state2, flag, root_id, agg, und, _scan_ws(n), stats)
+    n_agg, _ = _read_stats(stats)
+    return agg, n_agg
+
+
+class Hierarchy:
+    """Smoothed-aggregation AMG for one operator."""
+
+    def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
+                 coarse_max=512, max_levels=24):
+        A = A.materialized()
+        self.mats, self.keep = [], []
+        levels = []
+        cur = A
+        while True:
+            n = cur.shape[0]
+            d = diagonal(cur)
+            dinv = torch.where(d != 0, 1.0 / d, torch.ones_like(d))
+            lev = dict(A=cur, dinv=dinv)
+            levels.append(lev)
+            if n <= coarse_max or len(levels) >= max_levels:
+                break
+            agg, n_agg = aggregate(cur, theta)
+            if n_agg >= 0.9 * n or n_agg == 0:
+                break
+            T = sel_jac(agg, n_agg, full=True, monotone=False)
+            if smooth:
+                AT = _csr_times_sel(cur, T)
+                P = _csr_plus_csr(T.todev(), _diag_times_csr(dia_jac(-omega_p * dinv), AT))
+            else:
+                P = T.todev()
+            R = P.transpose()
+            Ac = _csr_times_csr(R, _csr_times_csr(cur, P))
+            lev['P'], lev['R'] = P.materialized(), R.materialized()
+            cur = Ac.materialized()
+        self.levels = levels
+        nl = len(levels)
+        self.arr = (AmgLevel * nl)()
+        for l, lev in enumerate(levels):
+            n = lev['A'].shape[0]
+            L = self.arr[l]
+            L.A = csr_mat(lev['A'])
+            if 'P' in lev:
+                L.P, L.R = csr_mat(lev['P']), csr_mat(lev['R'])
+            L.dinv = lev['dinv'].data_ptr()
+            lev['work'] = [torch.zeros(n, dtype=torch.float64, device=device()) for _ in range(4)]
+            L.x, L.x2, L.b, L.r = [w.data_ptr() for w in lev['work']]
+        self.struct = AmgStruct()
+        self.struct.nlevels = nl
+        self.struct.nu_pre = self.struct.nu_post = int(nu)
+        self.struct.omega = float(omega)
+        self.struct.levels = ctypes.cast(self.arr, ctypes.POINTER(AmgLevel))
+        last = levels[-1]['A']
+        nc = last.shape[0]
+        if nc <= 2048:
+            W = _empty(2 * nc * nc, torch.float64)
+            self.coarse_inv = _empty(nc * nc, torch.float64)
+            info = _empty(1, torch.int32)
+            _call('npb_dense_inverse', nc, last.indptr, last.indices, last.data, W,
+                  self.coarse_inv, info)
+            if int(info.item()) == 0:
+                self.struct.coarse_n = nc
+                self.struct.coarse_inv = self.coarse_inv.data_ptr()
+            else:
+                self.struct.coarse_n = 0
+        else:
+            self.struct.coarse_n = 0
+        self.sizes = [lev['A'].shape[0] for lev in levels]
+        self.nnzs = [lev['A'].nnz for lev in levels]
+
+    @property
+    def addr(self):
+        return ctypes.addressof(self.struct)
+
+    def vcycle(self, b, x=None):
+        if x is None:
+            x = torch.empty_like(b)
+        _lib.lib().call('npb_amg_vcycle', self.addr, b, x, stream_ptr())
+        return x
+
+    def describe(self):
+        return 'levels %s, operator complexity %.2f' % (
+            self.sizes, sum(self.nnzs) / max(self.nnzs[0], 1))
+
+
+class AmgPreconditioner:
+    """k V-cycles as an npb_apply_fn (C callback, no Python in the loop)."""
+
+    def __init__(self, A, cycles=1, **kw):
+        self.A = A.materialized()
+        self.h = Hierarchy(self.A, **kw)
+        n = A.shape[0]
+        self.work = [torch.zeros(n, dtype=torch.float64, device=device()) for _ in range(2)]
+        self.struct = AmgPrecondStruct()
+        self.struct.amg = self.h.addr
+        self.struct.A = csr_mat(self.A)
+        self.struct.cycles = int(cycles)
+        self.struct.r, self.struct.dx = [w.data_ptr() for w in self.work]
+        self.c_apply = ctypes.cast(_lib.lib().cdll.npb_amg_apply_cb, ctypes.c_void_p).value
+        self.c_ctx = ctypes.addressof(self.struct)
+
+    def apply(self, r, z):
+        rc = _lib.lib().cdll.npb_amg_apply_cb(self.c_ctx, r.data_ptr(), z.data_ptr(), stream_ptr())
+        if rc:
+            raise RuntimeError('npb_amg_apply_cb failed: %s' % _lib.lib().last_error())
+
+
+def _submatrix(J, rows, colmap, ncols):
+    """J[rows][:, cols] with cols given as a map old column -> new column / -1"""
+    Jr = _sel_times_csr(sel_jac(rows, J.shape[1], full=True, monotone=True), J)
+    return _csr_times_sel(Jr, sel_jac(colmap, ncols, monotone=True, full=False)).materialized()
+
+
+class LscPreconditioner:
+    """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
+
+    def __init__(self, J, cycles_a=1, cycles_l=2, theta_a=0.25, nu_a=2, nu_l=1, reuse=None):
+        J = J.materialized()
+        n = J.shape[0]
+        d = diagonal(J)
+        has = d != 0
+        vset = torch.nonzero(has).reshape(-1).to(torch.int32)
+        pset = torch.nonzero(~has).reshape(-1).to(torch.int32)
+        nv, np_ = int(vset.numel()), int(pset.numel())
+        self.n, self.nv, self.np = n, nv, np_
+        ar_v = torch.arange(nv, dtype=torch.int32, device=device())
+        ar_p = torch.arange(np_, dtype=torch.int32, device=device())
+        vmap = torch.full((n,), -1, dtype=torch.int32, device=device())
+        vmap[vset.long()] = ar_v
+        pmap = torch.full((n,), -1, dtype=torch.int32, device=device())
+        pmap[pset.long()] = ar_p
+        self.vset, self.pset = vset, pset
+        self.A = _submatrix(J, vset, vmap, nv)
+        self.G = _submatrix(J, vset, pmap, np_)
+        self.D = _submatrix(J, pset, vmap, nv)
+        # L = -D G: constant across Newton iterations when the constraint
+        # blocks are (they are the linear div / grad operators); reuse its
+        # hierarchy when the caller hands back an LscPreconditioner whose D, G
+        # are bit-identical
+        if (reuse is not None and reuse.np == np_ and reuse.nv == nv and
+                reuse.D.nnz == self.D.nnz and reuse.G.nnz == self.G.nnz and
+                torch.equal(reuse.D.indices, self.D.indices) and
+                torch.equal(reuse.D.data, self.D.data) and
+                torch.equal(reuse.G.indices, self.G.indices) and
+                torch.equal(reuse.G.data, self.G.data)):
+            self.Lm, self.amg_l = reuse.Lm, reuse.amg_l
+        else:
+            self.Lm = _csr_times_csr(self.D, self.G).scaled(-1.0).materialized()
+            self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l)
+        self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a)
+        self.a_dinv = self.amg_a.levels[0]['dinv']
+        self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]
+        self.wp = [torch.zeros(max(np_, 1), dtype=torch.float64, device=device()) for _ in range(5)]
+        s = self.struct = LscStruct()
+        s.n, s.nv, s.np = n, nv, np_
+        s.vset, s.pset = vset.data_ptr(), pset.data_ptr()
+        s.A, s.G, s.D, s.Lm = csr_mat(self.A), csr_mat(self.G), csr_mat(self.D), csr_mat(self.Lm)
+        s.a_dinv = self.a_dinv.data_ptr()
+        s.amg_a, s.amg_l = self.amg_a.addr, self.amg_l.addr
+        s.cycles_a, s.cycles_l = int(cycles_a), int(cycles_l)
+        for k in range(5):
+            s.wv[k] = self.wv[k].data_ptr()
+            s.wp[k] = self.wp[k].data_ptr()
+        self.c_apply = ctypes.cast(_lib.lib().cdll.npb_lsc_apply_cb, ctypes.c_void_p).value
+        self.c_ctx = ctypes.addressof(s)
+
+    def apply(self, r, z):
+        rc = _lib.lib().cdll.npb_lsc_apply_cb(self.c_ctx, r.data_ptr(), z.data_ptr(), stream_ptr())
+        if rc:
+            raise RuntimeError('npb_lsc_apply_cb failed: %s' % _lib.lib().last_error())
+
+    def describe(self):
+        return 'LSC: nv=%d np=%d | A-AMG %s | L-AMG %s' % (
+            self.nv, self.np, self.amg_a.describe(), self.amg_l.describe())

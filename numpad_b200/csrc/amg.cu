@@ -1,0 +1,529 @@
+// Algebraic multigrid (smoothed aggregation, V-cycle, damped-Jacobi smoother)
+// and the least-squares-commutator block preconditioner built on it.
+//
+// Role (seam S3): the preconditioner of the FGMRES that replaces SuperLU
+// `spsolve` in the reference Newton loop (adsolve.py:193-195).  The cavity
+// Jacobian is a saddle-point matrix (N^2-1 zero diagonals):
+// with V = rows with a diagonal entry, P = rows without,
+//      J = [ A  G ]  (V rows)        S = -D A^-1 G  ~  -(DG) (D A G)^-1 (DG)
+//          [ D  0 ]  (P rows)
+// M^-1 r:  u* = A~^-1 r_V ;  q = r_P - D u* ;  p = -L~^-1 (D A G) L~^-1 q with
+// L = -D G ;  u = u* - diag(A)^-1 G p.   A~^-1, L~^-1 = k V-cycles.
+// The setup (aggregation, Galerkin products) runs once per matrix through the
+// chain-rule kernels of assembly.cu/coo.cu; everything below is the solve
+// phase: SpMV-shaped, HBM-bound kernels launched from C++ (no Python in the
+// Krylov loop).
+#include <math.h>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                    const double* dat, const double* x, const double* b, double* y,
+                    int mode, cudaStream_t st);
+int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st);
+
+namespace {
+
+constexpr int TPB = 256;
+
+// xout = xin + omega * dinv .* (b - A xin)   (xout must not alias xin)
+template <int G>
+__global__ void __launch_bounds__(TPB)
+k_jacobi(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+         const double* __restrict__ dat, const double* __restrict__ dinv, double omega,
+         const double* __restrict__ b, const double* __restrict__ xin,
+         double* __restrict__ xout) {
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
+    double s = 0.0;
+    if (r < nrows) {
+        const int32_t e = ptr[r + 1];
+        for (int32_t k = ptr[r] + lane; k < e; k += G) s = fma(dat[k], __ldg(xin + idx[k]), s);
+    }
+#pragma unroll
+    for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (r < nrows && lane == 0) xout[r] = xin[r] + omega * dinv[r] * (b[r] - s);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_jacobi0(int64_t n, const double* __restrict__ dinv, double omega,
+          const double* __restrict__ b, double* __restrict__ x) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) x[i] = omega * dinv[i] * b[i];
+}
+
+// y = Ainv b (dense row-major n x n), one warp per row
+__global__ void __launch_bounds__(TPB)
+k_dense_mv(int n, const double* __restrict__ M, const double* __restrict__ b,
+           double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * TPB + threadIdx.x) >> 5;
+    double s = 0.0;
+    if (r < n)
+        for (int c = lane; c < n; c += 32) s = fma(M[(int64_t)r * n + c], b[c], s);
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (r < n && lane == 0) y[r] = s;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_gather(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ src,
+         double* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+__global__ void __launch_bounds__(TPB)
+k_scatter(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ src,
+          double* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) dst[idx[i]] = src[i];
+}
+
+// u = a - dinv .* g
+__global__ void __launch_bounds__(TPB)
+k_sub_scaled(int64_t n, const double* a, const double* __restrict__ dinv,
+             const double* __restrict__ g, double* u) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) u[i] = a[i] - dinv[i] * g[i];
+}
+
+// ------------------------------------------------------------------ setup
+// diag[r] = A(r, r) (0 when absent)
+__global__ void __launch_bounds__(TPB)
+k_csr_diag(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+           const double* __restrict__ dat, double* __restrict__ diag) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (r >= nrows) return;
+    double d = 0.0;
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k)
+        if (idx[k] == r) d = dat[k];
+    diag[r] = d;
+}
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// One Luby round on the strength graph (|a_ij| >= theta * max_k |a_ik|):
+// state 0 undecided, 1 root, 2 covered.  Reads `state`, writes `next`.
+__global__ void __launch_bounds__(TPB)
+k_mis_select(int64_t n, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+             const double* __restrict__ dat, double theta, const int8_t* __restrict__ state,
+             int8_t* __restrict__ next) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    int8_t s = state[i];
+    if (s == 0) {
+        double mx = 0.0;
+        for (int32_t k = ptr[i], e = ptr[i + 1]; k < e; ++k)
+            if (idx[k] != i) mx = fmax(mx, fabs(dat[k]));
+        const double thr = theta * mx;
+        const uint32_t pi = hash32((uint32_t)i);
+        bool root = true;
+        for (int32_t k = ptr[i], e = ptr[i + 1]; k < e && root; ++k) {
+            const int32_t j = idx[k];
+            if (j == i || fabs(dat[k]) < thr || dat[k] == 0.0 || state[j] != 0) continue;
+            const uint32_t pj = hash32((uint32_t)j);
+            if (pj > pi || (pj == pi && j > i)) root = false;
+        }
+        if (root) s = 1;
+    }
+    next[i] = s;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_mis_cover(int64_t n, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+            const double* __restrict__ dat, double theta, int8_t* __restrict__ state,
+            int32_t* __restrict__ undecided) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    bool und = false;
+    if (i < n && state[i] == 0) {
+        double mx = 0.0;
+        for (int32_t k = ptr[i], e = ptr[i + 1]; k < e; ++k)
+            if (idx[k] != i) mx = fmax(mx, fabs(dat[k]));
+        const double thr = theta * mx;
+        bool cov = false;
+        for (int32_t k = ptr[i], e = ptr[i + 1]; k < e; ++k) {
+            const int32_t j = idx[k];
+            if (j != i && dat[k] != 0.0 && fabs(dat[k]) >= thr && state[j] == 1) { cov = true; break; }
+        }
+        // benign race: neighbours only move 0 -> 2 here, roots are already final
+        if (cov) state[i] = 2; else und = true;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, und);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(undecided, __popc(m));
+}
+
+__global__ void __launch_bounds__(TPB)
+k_mis_flags(int64_t n, const int8_t* __restrict__ state, int force_roots, int32_t* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) flag[i] = (state[i] == 1) || (force_roots && state[i] == 0);
+}
+
+// agg[i] = id of own aggregate (roots) or of the most strongly connected root
+__global__ void __launch_bounds__(TPB)
+k_mis_join(int64_t n, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+           const double* __restrict__ dat, const int32_t* __restrict__ flag,
+           const int32_t* __restrict__ root_id, int32_t* __restrict__ agg) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) { agg[i] = root_id[i]; return; }
+    double best = -1.0;
+    int32_t bj = -1;
+    for (int32_t k = ptr[i], e = ptr[i + 1]; k < e; ++k) {
+        const int32_t j = idx[k];
+        if (j != i && flag[j] && fabs(dat[k]) > best) { best = fabs(dat[k]); bj = j; }
+    }
+    agg[i] = bj >= 0 ? root_id[bj] : -1;    // -1 cannot happen for covered nodes
+}
+
+__global__ void __launch_bounds__(TPB)
+k_csr_to_dense(int64_t n, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+               const double* __restrict__ dat, double* __restrict__ M, int ld) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (r >= n) return;
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) M[r * ld + idx[k]] = dat[k];
+}
+
+// Gauss-Jordan inverse with partial pivoting, one CTA, W = [A | I] (n x 2n,
+// row-major, in global memory / L2); on exit the right half is A^-1.
+__global__ void __launch_bounds__(1024)
+k_gauss_jordan(int n, double* __restrict__ W, int32_t* __restrict__ info) {
+    __shared__ double rv[32];
+    __shared__ int ri[32];
+    __shared__ int s_p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = 2 * n;
+    for (int k = 0; k < n; ++k) {
+        double best = -1.0;
+        int bi = k;
+        for (int r = k + tid; r < n; r += 1024) {
+            double v = fabs(W[(int64_t)r * ld + k]);
+            if (v > best) { best = v; bi = r; }
+        }
+        for (int d = 16; d; d >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, d);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { rv[warp] = best; ri[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            best = rv[lane]; bi = ri[lane];
+            for (int d = 16; d; d >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, best, d);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { s_p = bi; if (best == 0.0 && *info == 0) *info = k + 1; }
+        }
+        __syncthreads();
+        const int p = s_p;
+        double* rk = W + (int64_t)k * ld;
+        if (p != k) {
+            double* rp = W + (int64_t)p * ld;
+            for (int c = tid; c < ld; c += 1024) { double t = rk[c]; rk[c] = rp[c]; rp[c] = t; }
+            __syncthreads();
+        }
+        const double piv = rk[k];
+        if (piv != 0.0) {
+            const double rinv = 1.0 / piv;
+            __syncthreads();
+            for (int c = tid; c < ld; c += 1024) rk[c] *= rinv;
+            __syncthreads();
+            // eliminate column k from every other row; columns <= k of the left
+            // half are already unit vectors except column k itself
+            for (int64_t t = tid; t < (int64_t)n * ld; t += 1024) {
+                const int r = (int)(t / ld), c = (int)(t % ld);
+                if (r == k || c == k) continue;
+                const double f = W[(int64_t)r * ld + k];
+                if (f != 0.0) W[(int64_t)r * ld + c] = fma(-f, rk[c], W[(int64_t)r * ld + c]);
+            }
+            __syncthreads();
+            for (int r = tid; r < n; r += 1024)
+                if (r != k) W[(int64_t)r * ld + k] = 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_copy_right_half(int n, const double* __restrict__ W, double* __restrict__ Minv) {
+    int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (t < (int64_t)n * n) {
+        const int r = (int)(t / n), c = (int)(t % n);
+        Minv[t] = W[(int64_t)r * 2 * n + n + c];
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_set_identity_right(int n, double* __restrict__ W) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (r < n) W[r * 2 * n + n + r] = 1.0;
+}
+
+template <int G>
+void launch_jacobi(int64_t n, const int32_t* ptr, const int32_t* idx, const double* dat,
+                   const double* dinv, double omega, const double* b, const double* xin,
+                   double* xout, cudaStream_t st) {
+    k_jacobi<G><<<npb_blocks(n * G, TPB), TPB, 0, st>>>(n, ptr, idx, dat, dinv, omega, b, xin, xout);
+}
+
+}  // namespace
+
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+struct npb_csr_mat {
+    int64_t nrows, ncols, nnz;
+    const int32_t* indptr;
+    const int32_t* indices;
+    const double* data;
+};
+
+struct npb_amg_level {
+    npb_csr_mat A;         // level operator
+    npb_csr_mat P;         // prolongation  (n x n_coarse)   [unused on the coarsest level]
+    npb_csr_mat R;         // restriction   (n_coarse x n)
+    const double* dinv;    // 1 / diag(A)
+    double* x;             // work vectors of length n (x, x2 ping-pong, b, r)
+    double* x2;
+    double* b;
+    double* r;
+};
+
+struct npb_amg {
+    int32_t nlevels;       // >= 1
+    int32_t nu_pre, nu_post;
+    int32_t coarse_n;      // size of the dense coarse inverse (0: smooth only)
+    double omega;
+    const double* coarse_inv;   // dense row-major inverse of the coarsest operator
+    npb_amg_level* levels;      // [host] array of nlevels descriptors
+};
+
+static int jacobi_sweep(const npb_amg_level& L, double omega, const double* b, const double* xin,
+                        double* xout, cudaStream_t st) {
+    const double mean = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
+    if (mean <= 3.0) launch_jacobi<2>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
+    else if (mean <= 6.0) launch_jacobi<4>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
+    else if (mean <= 16.0) launch_jacobi<8>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
+    else launch_jacobi<16>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
+    NPB_COUNT_LAUNCH();
+    return NPB_OK;
+}
+
+// x <- V-cycle(b) from a zero initial guess.  b and x have the fine size and
+// must not alias the hierarchy's work vectors.
+int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
+    cudaStream_t st = ST(stream);
+    const int nl = h->nlevels;
+    // downward
+    for (int l = 0; l < nl; ++l) {
+        npb_amg_level& L = h->levels[l];
+        const int64_t n = L.A.nrows;
+        const double* bl = (l == 0) ? b : L.b;
+        if (l == nl - 1 && h->coarse_n > 0) {
+            double* xl = (l == 0) ? x : L.x;
+            k_dense_mv<<<npb_blocks((int64_t)h->coarse_n * 32, TPB), TPB, 0, st>>>(h->coarse_n, h->coarse_inv, bl, xl);
+            NPB_COUNT_LAUNCH();
+            break;
+        }
+        // pre-smoothing from zero: x = omega dinv b, then nu_pre-1 sweeps
+        double* cur = L.x;
+        double* oth = L.x2;
+        k_jacobi0<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, L.dinv, h->omega, bl, cur);
+        NPB_COUNT_LAUNCH();
+        const int extra = (l == nl - 1) ? (h->nu_pre + h->nu_post + 6) : (h->nu_pre - 1);
+        for (int s = 0; s < extra; ++s) {
+            jacobi_sweep(L, h->omega, bl, cur, oth, st);
+            double* t = cur; cur = oth; oth = t;
+        }
+        if (cur != L.x) { double* t = L.x; L.x = L.x2; L.x2 = t; }   // keep the iterate in L.x
+        if (l == nl - 1) {
+            if (l == 0) NPB_CUDA(cudaMemcpyAsync(x, L.x, n * 8, cudaMemcpyDeviceToDevice, st));
+            break;
+        }
+        // r = b - A x ; b_{l+1} = R r
+        int rc = npb_spmv_launch(n, L.A.nnz, L.A.indptr, L.A.indices, L.A.data, L.x, bl, L.r, 1, st);
+        if (rc) return rc;
+        npb_amg_level& C = h->levels[l + 1];
+        rc = npb_spmv_launch(L.R.nrows, L.R.nnz, L.R.indptr, L.R.indices, L.R.data, L.r, nullptr, C.b, 0, st);
+        if (rc) return rc;
+    }
+    // upward
+    for (int l = nl - 2; l >= 0; --l) {
+        npb_amg_level& L = h->levels[l];
+        npb_amg_level& C = h->levels[l + 1];
+        const int64_t n = L.A.nrows;
+        const double* bl = (l == 0) ? b : L.b;
+        // x += P x_{l+1}
+        int rc = npb_spmv_launch(n, L.P.nnz, L.P.indptr, L.P.indices, L.P.data, C.x, L.x, L.x, 2, st);
+        if (rc) return rc;
+        double* cur = L.x;
+        double* oth = L.x2;
+        for (int s = 0; s < h->nu_post; ++s) {
+            double* out = (l == 0 && s == h->nu_post - 1) ? x : oth;
+            jacobi_sweep(L, h->omega, bl, cur, out, st);
+            if (out == x) { cur = x; break; }
+            double* t = cur; cur = oth; oth = t;
+        }
+        if (l == 0) {
+            if (cur != x) NPB_CUDA(cudaMemcpyAsync(x, cur, n * 8, cudaMemcpyDeviceToDevice, st));
+        } else if (cur != L.x) {
+            double* t = L.x; L.x = L.x2; L.x2 = t;
+        }
+    }
+    NPB_CHECK_LAUNCH("amg_vcycle");
+    return NPB_OK;
+}
+
+// x <- k V-cycles on A x = b (stationary iteration, zero start); r = scratch (fine size)
+static int amg_solve(const npb_amg* h, const npb_csr_mat& A, int k, const double* b, double* x,
+                     double* r, double* dx, cudaStream_t st) {
+    int rc = npb_amg_vcycle(h, b, x, (void*)st);
+    for (int it = 1; it < k && !rc; ++it) {
+        rc = npb_spmv_launch(A.nrows, A.nnz, A.indptr, A.indices, A.data, x, b, r, 1, st);
+        if (!rc) rc = npb_amg_vcycle(h, r, dx, (void*)st);
+        if (!rc) rc = npb_axpby_launch(A.nrows, 1.0, dx, 1.0, x, st);
+    }
+    return rc;
+}
+
+// y = k V-cycles applied to x: usable directly as an npb_apply_fn
+struct npb_amg_precond {
+    const npb_amg* amg;
+    npb_csr_mat A;
+    int32_t cycles, pad;
+    double* r;     // 2 work vectors of the fine size
+    double* dx;
+};
+
+int npb_amg_apply_cb(void* ctx, const double* x, double* y, void* stream) {
+    const npb_amg_precond* p = (const npb_amg_precond*)ctx;
+    return amg_solve(p->amg, p->A, p->cycles, x, y, p->r, p->dx, ST(stream));
+}
+
+// least-squares-commutator block preconditioner (see file header)
+struct npb_lsc {
+    int64_t n, nv, np;
+    const int32_t* vset;       // rows with a diagonal (size nv), increasing
+    const int32_t* pset;       // rows without        (size np), increasing
+    npb_csr_mat A, G, D;       // J[V,V], J[V,P], J[P,V]
+    npb_csr_mat Lm;            // -D G
+    const double* a_dinv;      // 1 / diag(A)
+    const npb_amg* amg_a;
+    const npb_amg* amg_l;
+    int32_t cycles_a, cycles_l;
+    double* wv[5];             // work vectors of size nv
+    double* wp[5];             // work vectors of size np
+};
+
+int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
+    const npb_lsc* c = (const npb_lsc*)ctx;
+    cudaStream_t st = ST(stream);
+    const int64_t nv = c->nv, np = c->np;
+    double *rv = c->wv[0], *us = c->wv[1], *t1 = c->wv[2], *t2 = c->wv[3], *t3 = c->wv[4];
+    double *rp = c->wp[0], *q = c->wp[1], *p1 = c->wp[2], *s1 = c->wp[3], *s2 = c->wp[4];
+    int rc;
+    k_gather<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, r, rv);
+    NPB_COUNT_LAUNCH();
+    if (np > 0) { k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, rp); NPB_COUNT_LAUNCH(); }
+    // u* = A~^-1 r_V
+    if ((rc = amg_solve(c->amg_a, c->A, c->cycles_a, rv, us, t1, t2, st))) return rc;
+    if (np > 0) {
+        // q = r_P - D u*
+        if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, us, rp, q, 1, st))) return rc;
+        // p1 = L^-1 q            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
+        if ((rc = amg_solve(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, st))) return rc;
+        // s1 = D A G p1
+        if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t1, 0, st))) return rc;
+        if ((rc = npb_spmv_launch(nv, c->A.nnz, c->A.indptr, c->A.indices, c->A.data, t1, nullptr, t2, 0, st))) return rc;
+        if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, t2, nullptr, q, 0, st))) return rc;
+        // p = -L^-1 s1
+        if ((rc = amg_solve(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, st))) return rc;
+        if ((rc = npb_axpby_launch(np, 0.0, p1, -1.0, p1, st))) return rc;
+        // u = u* - diag(A)^-1 G p
+        if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t3, 0, st))) return rc;
+        k_sub_scaled<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, us, c->a_dinv, t3, us);
+        NPB_COUNT_LAUNCH();
+        k_scatter<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, p1, z);
+        NPB_COUNT_LAUNCH();
+    }
+    k_scatter<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, us, z);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("lsc_apply");
+    return NPB_OK;
+}
+
+// ------------------------------------------------------------- setup pieces
+int npb_csr_diagonal(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                     const double* data, double* diag, void* stream) {
+    if (nrows <= 0) return NPB_OK;
+    k_csr_diag<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, diag);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_diagonal");
+    return NPB_OK;
+}
+
+// Aggregation by a maximal independent set of the strength graph.
+// state, state2: int8[n] scratch; flag, root_id(n+1), agg: int32; counters:
+// int32[2] device.  On return agg[i] in [0, *n_agg) and stats[0] = n_agg.
+int npb_amg_aggregate(int64_t n, const int32_t* indptr, const int32_t* indices,
+                      const double* data, double theta, int max_rounds, int8_t* state,
+                      int8_t* state2, int32_t* flag, int32_t* root_id, int32_t* agg,
+                      int32_t* undecided /*device int32*/, int64_t* scan_ws, int64_t* stats,
+                      void* stream) {
+    cudaStream_t st = ST(stream);
+    NPB_CUDA(cudaMemsetAsync(state, 0, n, st));
+    int8_t* cur = state;
+    int8_t* nxt = state2;
+    for (int round = 0; round < max_rounds; ++round) {
+        k_mis_select<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, indptr, indices, data, theta, cur, nxt);
+        NPB_COUNT_LAUNCH();
+        NPB_CUDA(cudaMemsetAsync(undecided, 0, sizeof(int32_t), st));
+        k_mis_cover<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, indptr, indices, data, theta, nxt, undecided);
+        NPB_COUNT_LAUNCH();
+        int8_t* t = cur; cur = nxt; nxt = t;
+        int32_t und = 0;
+        NPB_CUDA(cudaMemcpyAsync(&und, undecided, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        NPB_CUDA(cudaStreamSynchronize(st));
+        if (und == 0) break;
+    }
+    k_mis_flags<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, cur, 1, flag);
+    NPB_COUNT_LAUNCH();
+    int rc = npb_scan_launch(flag, root_id, n, scan_ws, stats, st);
+    if (rc) return rc;
+    k_mis_join<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, indptr, indices, data, flag, root_id, agg);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("amg_aggregate");
+    return NPB_OK;
+}
+
+// dense inverse of a small CSR matrix: W = scratch n x 2n, Minv = n x n out
+int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices, const double* data,
+                      double* W, double* Minv, int32_t* info, void* stream) {
+    cudaStream_t st = ST(stream);
+    if (n <= 0) return NPB_OK;
+    NPB_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * 2 * (size_t)n * n, st));
+    NPB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    k_csr_to_dense<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, indptr, indices, data, W, 2 * n);
+    k_set_identity_right<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, W);
+    k_gauss_jordan<<<1, 1024, 0, st>>>(n, W, info);
+    k_copy_right_half<<<npb_blocks((int64_t)n * n, TPB), TPB, 0, st>>>(n, W, Minv);
+    NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("dense_inverse");
+    return NPB_OK;
+}
+
+int npb_gather(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream) {
+    if (n <= 0) return NPB_OK;
+    k_gather<<<npb_blocks(n, TPB), TPB, 0, ST(stream)>>>(n, idx, src, dst);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("gather");
+    return NPB_OK;
+}
+
+}  // extern "C"

@@ -24,13 +24,13 @@ constexpr int KC = 16;                        // basis vectors per multi-dot pas
 // ---------------------------------------------------------------------- SpMV
 // G lanes cooperate on one row (G = 2..32 picked from nnz/row); lanes read
 // consecutive entries so a warp's loads of indices/data are contiguous.
-// mode 0: y = A x      mode 1: y = b - A x
+// mode 0: y = A x      mode 1: y = b - A x      mode 2: y = b + A x
+// (b may alias y: each row reads b[r] before it writes y[r])
 template <int G>
 __global__ void __launch_bounds__(TPB)
 k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
        const int32_t* __restrict__ idx, const double* __restrict__ dat,
-       const double* __restrict__ x, const double* __restrict__ b,
-       double* __restrict__ y, int mode) {
+       const double* __restrict__ x, const double* b, double* y, int mode) {
     const int lane = threadIdx.x & (G - 1);
     const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
     double s = 0.0;
@@ -41,7 +41,7 @@ k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
     }
 #pragma unroll
     for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (r < nrows && lane == 0) y[r] = mode ? b[r] - s : s;
+    if (r < nrows && lane == 0) y[r] = mode == 0 ? s : (mode == 1 ? b[r] - s : b[r] + s);
 }
 
 // ------------------------------------------------ deterministic block reduce

@@ -57,7 +57,10 @@ def fgmres(A, b, x0=None, precond=None, rtol=1e-12, atol=0.0, restart=60, maxite
         cb = _lib.APPLY_FN(_wrap_apply(matvec, n))
         keep.append(cb)
         ops.matvec = ctypes.cast(cb, ctypes.c_void_p).value
-    if precond is not None:
+    if precond is not None and hasattr(precond, 'c_apply'):
+        keep.append(precond)             # C callback + ctx: no Python in the loop
+        ops.precond, ops.precond_ctx = precond.c_apply, precond.c_ctx
+    elif precond is not None:
         cb = _lib.APPLY_FN(_wrap_apply(precond, n))
         keep.append(cb)
         ops.precond = ctypes.cast(cb, ctypes.c_void_p).value
@@ -129,7 +132,8 @@ def solve(A, b, transpose=False, **opts):
         last_info.clear()
         last_info.update(res)
         return x
-    x, res = fgmres(A, b, precond=(M.apply if M is not None else None), rtol=o['rtol'],
+    pc = None if M is None else (M if hasattr(M, 'c_apply') else M.apply)
+    x, res = fgmres(A, b, precond=pc, rtol=o['rtol'],
                     atol=o['atol'], restart=min(o['restart'], n), maxiter=o['maxiter'])
     res['method'] = method
     last_info.clear()
@@ -141,6 +145,9 @@ def solve(A, b, transpose=False, **opts):
     if o['verbose']:
         print('    linear solve [%s]: %d its, |r|/|b| = %.2e' %
               (method, res['iters'], res['rnorm'] / max(res['bnorm'], 1e-300)))
+    if res['status'] != 0 and method != 'direct' and _pc.direct_feasible(A):
+        # robust fallback: pivoted banded LU (+ refinement through the front door)
+        return solve(A, b, **dict(o, precond='direct'))
     if res['status'] != 0:
         raise LinearSolveError('linear solve (%s) did not converge: %d iterations, '
                                '|r|/|b| = %.3e' % (method, res['iters'],

@@ -94,17 +94,35 @@ class BandLU:
         z.copy_(self.solve(r))
 
 
+def direct_feasible(A):
+    if A.shape[0] > 200000:
+        return False
+    work, nbytes = BandLU.cost(A)
+    return work <= DIRECT_WORK and nbytes <= DIRECT_BYTES
+
+
+_last = {'lsc': None}
+
+
 def build(A, kind='auto'):
-    n = A.shape[0]
+    """-> (preconditioner object or None, method name)"""
     if kind == 'auto':
-        if n <= 200000:
-            work, nbytes = BandLU.cost(A)
-            if work <= DIRECT_WORK and nbytes <= DIRECT_BYTES:
-                kind = 'direct'
-        if kind == 'auto':
-            kind = 'none'
+        if direct_feasible(A):
+            kind = 'direct'
+        else:
+            from . import amg
+            d = amg.diagonal(A)
+            kind = 'lsc' if bool((d == 0).any()) else 'amg'
     if kind == 'none':
         return None, 'gmres'
     if kind == 'direct':
         return BandLU(A), 'direct'
+    if kind == 'lsc':
+        from . import amg
+        M = amg.LscPreconditioner(A, reuse=_last['lsc'])
+        _last['lsc'] = M
+        return M, 'fgmres+lsc'
+    if kind == 'amg':
+        from . import amg
+        return amg.AmgPreconditioner(A, theta=0.25, nu=2), 'fgmres+amg'
     raise ValueError('unknown preconditioner %r' % kind)

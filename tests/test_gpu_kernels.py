@@ -208,3 +208,46 @@ def test_band_lu(dev, n, density):
     got3 = linsolve.solve(A, torch.from_numpy(bt).to(dev.device()), transpose=True,
                           precond='direct').cpu().numpy()
     np.testing.assert_allclose(got3, x, rtol=0, atol=1e-8 * np.abs(x).max())
+
+
+def poisson2d(n1):
+    T = sp.diags([-1, 2, -1], [-1, 0, 1], shape=(n1, n1))
+    return sp.csr_matrix(sp.kron(sp.identity(n1), T) + sp.kron(T, sp.identity(n1)))
+
+
+def test_amg_poisson(dev):
+    """smoothed-aggregation V-cycle as FGMRES preconditioner: mesh-independent"""
+    import torch
+    from numpad_b200 import amg, linsolve
+    its = []
+    for n1 in (48, 96, 192):
+        a = poisson2d(n1)
+        A = dev.DevCsr.from_scipy(a)
+        M = amg.AmgPreconditioner(A, theta=0.0, nu=1)
+        rng = np.random.RandomState(8)
+        x = rng.standard_normal(a.shape[0])
+        b = torch.from_numpy(a @ x).to(dev.device())
+        got, info = linsolve.fgmres(A, b, precond=M, rtol=1e-10, restart=50, maxiter=200)
+        assert info['status'] == 0, (n1, info, M.h.describe())
+        np.testing.assert_allclose(got.cpu().numpy(), x, rtol=0, atol=1e-6 * np.abs(x).max())
+        its.append(info['iters'])
+        assert M.h.struct.coarse_n > 0 and len(M.h.sizes) >= 2
+    print('amg poisson its', its)
+    assert its[-1] <= 40 and its[-1] <= its[0] + 15
+
+
+def test_dense_inverse(dev):
+    import torch
+    rng = np.random.RandomState(9)
+    n = 150
+    a = rand_csr(rng, n, n, 0.1) + sp.identity(n, format='csr') * 0.05
+    a = sp.csr_matrix(a); a.sort_indices()
+    A = dev.DevCsr.from_scipy(a)
+    W = torch.empty(2 * n * n, dtype=torch.float64, device=dev.device())
+    Minv = torch.empty(n * n, dtype=torch.float64, device=dev.device())
+    info = torch.zeros(1, dtype=torch.int32, device=dev.device())
+    dev._call('npb_dense_inverse', n, A.indptr, A.indices, A.data, W, Minv, info)
+    assert int(info.item()) == 0
+    got = Minv.cpu().numpy().reshape(n, n)
+    ref = np.linalg.inv(a.toarray())
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9 * np.abs(ref).max())

@@ -168,3 +168,25 @@ def test_cavity_march_small_vs_reference_golden(npd, golden):
     adj = ke.diff(force).toarray().ravel()
     np.testing.assert_allclose(adj, z['adjoint'], rtol=0,
                                atol=1e-8 * np.abs(z['adjoint']).max())
+
+
+@pytest.mark.parametrize('N', [64, 128])
+def test_cavity_newton_step_lsc_vs_oracle(npd, orc, N):
+    """one Newton linear system of the benchmark state solved by FGMRES + LSC/AMG
+    against SuperLU on the oracle's Jacobian"""
+    import scipy.sparse.linalg as spla
+    from numpad_b200 import linsolve
+    from numpad_b200.workloads.cavity import CavityProblem
+    Pg, Po = CavityProblem(npd, N), CavityProblem(orc, N)
+    u0 = Pg.fixed_state()
+    ug = npd.array(u0.copy())
+    rg = Pg.residual(ug, npd.array(u0), 1.0, 0)
+    J = npd.diff_dev(rg, ug)
+    du = linsolve.solve(J, rg._dev.reshape(-1).contiguous(), precond='lsc')
+    info = dict(linsolve.last_info)
+    uo = orc.array(u0.copy())
+    ro = Po.residual(uo, orc.array(u0), 1.0, 0)
+    ref = spla.spsolve(orc.canonical(ro.diff(uo)).tocsc(), ro._value)
+    print('N=%d lsc: %s' % (N, info))
+    assert info['iters'] <= 80
+    np.testing.assert_allclose(du.cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
