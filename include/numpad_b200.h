@@ -164,6 +164,9 @@ int npb_csr_max_row(int64_t nrows, const int32_t* indptr, int64_t* stats,
 int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr,
              const int32_t* indices, const double* data, const double* x,
              double* y, void* stream);                       /* y = A x     */
+int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
+                     const int32_t* indices, const double* data, const double* x,
+                     double* y, int variant /* 1 stream, 2 vector */, void* stream);
 int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
                       const int32_t* indices, const double* data,
                       const double* x, const double* b, double* y,
@@ -258,13 +261,22 @@ typedef struct npb_lsc {            /* [host] ctx of npb_lsc_apply_cb */
     const double* a_dinv;
     const npb_amg* amg_a;
     const npb_amg* amg_l;
-    int32_t cycles_a, cycles_l;
+    int32_t cycles_a, cycles_l;     /* A: stationary V-cycles; L: V-cycle-preconditioned CG steps */
     double* wv[5];
-    double* wp[5];
+    double* wp[8];
+    double* scal;                   /* 4 device doubles */
+    void* red;                      /* npb_reduce_scratch_bytes(), zeroed */
 } npb_lsc;
 
 int npb_csr_diagonal(int64_t nrows, const int32_t* indptr, const int32_t* indices,
                      const double* data, double* diag, void* stream);
+int npb_csr_filter_symbolic(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                            const double* data, double theta, int32_t* counts,
+                            int32_t* indptr_out, int64_t* scan_ws, int64_t* stats,
+                            void* stream);
+int npb_csr_filter_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                           const double* data, double theta, const int32_t* indptr_out,
+                           int32_t* indices_out, double* out, void* stream);
 int npb_amg_aggregate(int64_t n, const int32_t* indptr, const int32_t* indices,
                       const double* data, double theta, int max_rounds, int8_t* state,
                       int8_t* state2, int32_t* flag, int32_t* root_id, int32_t* agg,

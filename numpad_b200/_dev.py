@@ -423,6 +423,30 @@ def _sel_times_csr(S, B):
     return _finish(DevCsr(shape, ptr, idx, dat, (), nnz, max_row), zc)
 
 
+# expansion buffers of the general product are capped at this many triplets;
+# larger products are done by row blocks of A and stacked
+SPGEMM_CHUNK = 1 << 29
+
+
+def _row_block(A, r0, r1):
+    """rows r0..r1 of a CSR matrix as its own DevCsr (views + rebased indptr)"""
+    k0, k1 = int(A.indptr[r0].item()), int(A.indptr[r1].item())
+    ptr = (A.indptr[r0:r1 + 1] - k0).contiguous()
+    return DevCsr((r1 - r0, A.shape[1]), ptr, A.indices[k0:k1], A.data[k0:k1], A.scales,
+                  k1 - k0, A.max_row, A.clean)
+
+
+def _vstack(blocks, shape):
+    ptrs, off = [], 0
+    for b in blocks:
+        ptrs.append(b.indptr[:-1] + off)
+        off += b.nnz
+    ptrs.append(torch.tensor([off], dtype=torch.int32, device=device()))
+    bm = [b.materialized() for b in blocks]
+    return DevCsr(shape, torch.cat(ptrs).to(torch.int32), torch.cat([b.indices for b in bm]),
+                  torch.cat([b.data for b in bm]), (), off, max(b.max_row for b in blocks), True)
+
+
 def _csr_times_csr(A, B):
     """general product through expansion + sort (scipy csr_matmat semantics:
     duplicates summed, exact-zero sums dropped)"""
@@ -433,9 +457,16 @@ def _csr_times_csr(A, B):
     stats = _empty(2, torch.int64)
     _call('npb_spgemm_expand_symbolic', A.nnz, A.indices, B.indptr, cnt, off,
           _scan_ws(A.nnz), stats)
-    total, _ = _read_stats(stats)
+    total = int(stats[0].item())
     if total == 0:
         return DevCsr.empty(shape)
+    if total > SPGEMM_CHUNK and A.shape[0] > 1:
+        nblk = min(A.shape[0], -(-total // (SPGEMM_CHUNK // 2)))
+        cuts = [int(round(i * A.shape[0] / nblk)) for i in range(nblk + 1)]
+        return _vstack([_csr_times_csr(_row_block(A, cuts[i], cuts[i + 1]), B)
+                        for i in range(nblk) if cuts[i + 1] > cuts[i]], shape)
+    if total > INT32_MAX:
+        raise OverflowError('sparse product with %d partial products in one row block' % total)
     r, c, v = _empty(total, torch.int32), _empty(total, torch.int32), _empty(total, torch.float64)
     _call('npb_spgemm_expand_numeric', A.nnz, A.rows(), A.indices, A.data, make_scales(A.scales),
           B.indptr, B.indices, B.data, make_scales(B.scales), off, r, c, v)

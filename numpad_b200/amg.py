@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._dev import (DevCsr, sel_jac, dia_jac, device, stream_ptr, _empty, _call, _scan_ws,
                    _read_stats, _csr_times_sel, _csr_times_csr, _diag_times_csr,
-                   _csr_plus_csr, _sel_times_csr)
+                   _csr_plus_csr, _sel_times_csr, coo_to_csr)
 
 
 class CsrMat(ctypes.Structure):
@@ -48,7 +48,8 @@ class LscStruct(ctypes.Structure):
                 ('a_dinv', ctypes.c_void_p), ('amg_a', ctypes.c_void_p),
                 ('amg_l', ctypes.c_void_p), ('cycles_a', ctypes.c_int32),
                 ('cycles_l', ctypes.c_int32), ('wv', ctypes.c_void_p * 5),
-                ('wp', ctypes.c_void_p * 5)]
+                ('wp', ctypes.c_void_p * 8), ('scal', ctypes.c_void_p),
+                ('red', ctypes.c_void_p)]
 
 
 def csr_mat(A):
@@ -77,11 +78,24 @@ def aggregate(A, theta, max_rounds=12):
     return agg, n_agg
 
 
+def filtered(A, theta):
+    """A with its weak off-diagonal entries lumped onto the diagonal"""
+    m = A.shape[0]
+    cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_csr_filter_symbolic', m, A.indptr, A.indices, A.data, float(theta), cnt, ptr,
+          _scan_ws(m), stats)
+    nnz = int(stats[0].item())
+    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    _call('npb_csr_filter_numeric', m, A.indptr, A.indices, A.data, float(theta), ptr, idx, dat)
+    return DevCsr(A.shape, ptr, idx, dat, (), nnz, A.max_row, False)
+
+
 class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=512, max_levels=24):
+                 coarse_max=256, max_levels=24):
         A = A.materialized()
         self.mats, self.keep = [], []
         levels = []
@@ -95,16 +109,29 @@ class Hierarchy:
             if n <= coarse_max or len(levels) >= max_levels:
                 break
             agg, n_agg = aggregate(cur, theta)
+            if n_agg > 0.6 * n and theta > 0:      # filtered graph too sparse down here
+                agg, n_agg = aggregate(cur, 0.0)
             if n_agg >= 0.9 * n or n_agg == 0:
                 break
             T = sel_jac(agg, n_agg, full=True, monotone=False)
             if smooth:
-                AT = _csr_times_sel(cur, T)
-                P = _csr_plus_csr(T.todev(), _diag_times_csr(dia_jac(-omega_p * dinv), AT))
+                # P = (I - omega D_F^-1 A_F) T with the strength-filtered A_F
+                AF = filtered(cur, theta) if theta > 0 else cur
+                dF = diagonal(AF) if theta > 0 else d
+                dFinv = torch.where(dF != 0, 1.0 / dF, torch.ones_like(dF))
+                AT = _csr_times_sel(AF, T)
+                P = _csr_plus_csr(T.todev(), _diag_times_csr(dia_jac(-omega_p * dFinv), AT))
+                R = P.transpose()
+                Ac = _csr_times_csr(R, _csr_times_csr(cur, P))
             else:
+                # piecewise-constant P: the Galerkin product is a relabel of
+                # rows and columns by aggregate id + duplicate sum (one sort)
                 P = T.todev()
-            R = P.transpose()
-            Ac = _csr_times_csr(R, _csr_times_csr(cur, P))
+                R = P.transpose()
+                rows = agg[cur.rows().long()]
+                cols = agg[cur.indices.long()]
+                Ac = coo_to_csr((n_agg, n_agg), rows.contiguous(), cols.contiguous(),
+                                cur.data, prune=False)
             lev['P'], lev['R'] = P.materialized(), R.materialized()
             cur = Ac.materialized()
         self.levels = levels
@@ -188,7 +215,8 @@ def _submatrix(J, rows, colmap, ncols):
 class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
-    def __init__(self, J, cycles_a=1, cycles_l=2, theta_a=0.25, nu_a=2, nu_l=1, reuse=None):
+    def __init__(self, J, cycles_a=2, cycles_l=3, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
+                 reuse=None):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -221,10 +249,16 @@ class LscPreconditioner:
         else:
             self.Lm = _csr_times_csr(self.D, self.G).scaled(-1.0).materialized()
             self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l)
-        self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a)
+        # momentum block: aggregation on the strength graph, prolongator smoothed
+        # with the strength-filtered operator (keeps the two velocity components
+        # apart, operator complexity ~2.5 instead of ~4)
+        self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a)
         self.a_dinv = self.amg_a.levels[0]['dinv']
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]
-        self.wp = [torch.zeros(max(np_, 1), dtype=torch.float64, device=device()) for _ in range(5)]
+        self.wp = [torch.zeros(max(np_, 1), dtype=torch.float64, device=device()) for _ in range(8)]
+        self.scal = torch.zeros(4, dtype=torch.float64, device=device())
+        self.red = torch.zeros(_lib.lib().cdll.npb_reduce_scratch_bytes(), dtype=torch.uint8,
+                               device=device())
         s = self.struct = LscStruct()
         s.n, s.nv, s.np = n, nv, np_
         s.vset, s.pset = vset.data_ptr(), pset.data_ptr()
@@ -234,7 +268,9 @@ class LscPreconditioner:
         s.cycles_a, s.cycles_l = int(cycles_a), int(cycles_l)
         for k in range(5):
             s.wv[k] = self.wv[k].data_ptr()
+        for k in range(8):
             s.wp[k] = self.wp[k].data_ptr()
+        s.scal, s.red = self.scal.data_ptr(), self.red.data_ptr()
         self.c_apply = ctypes.cast(_lib.lib().cdll.npb_lsc_apply_cb, ctypes.c_void_p).value
         self.c_ctx = ctypes.addressof(s)
 

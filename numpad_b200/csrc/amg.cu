@@ -22,29 +22,15 @@ int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_
                     const double* dat, const double* x, const double* b, double* y,
                     int mode, cudaStream_t st);
 int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st);
+int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                const double* dat, const double* x, int mode, const double* b,
+                const double* dinv, double omega, double* y, int variant, cudaStream_t st);
+int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
+                         double* out, void* scratch, cudaStream_t st);
 
 namespace {
 
 constexpr int TPB = 256;
-
-// xout = xin + omega * dinv .* (b - A xin)   (xout must not alias xin)
-template <int G>
-__global__ void __launch_bounds__(TPB)
-k_jacobi(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-         const double* __restrict__ dat, const double* __restrict__ dinv, double omega,
-         const double* __restrict__ b, const double* __restrict__ xin,
-         double* __restrict__ xout) {
-    const int lane = threadIdx.x & (G - 1);
-    const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
-    double s = 0.0;
-    if (r < nrows) {
-        const int32_t e = ptr[r + 1];
-        for (int32_t k = ptr[r] + lane; k < e; k += G) s = fma(dat[k], __ldg(xin + idx[k]), s);
-    }
-#pragma unroll
-    for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (r < nrows && lane == 0) xout[r] = xin[r] + omega * dinv[r] * (b[r] - s);
-}
 
 __global__ void __launch_bounds__(TPB)
 k_jacobi0(int64_t n, const double* __restrict__ dinv, double omega,
@@ -80,6 +66,32 @@ k_scatter(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__
     if (i < n) dst[idx[i]] = src[i];
 }
 
+// CG with every scalar on the device (no host round trip inside the
+// preconditioner):  p = z + (rz_new / rz_old) p   (first = 1: p = z)
+__global__ void __launch_bounds__(TPB)
+k_cg_dir(int64_t n, const double* __restrict__ rz_new, const double* __restrict__ rz_old,
+         int first, const double* __restrict__ z, double* __restrict__ p) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    if (first) { p[i] = z[i]; return; }
+    const double den = *rz_old;
+    const double beta = den != 0.0 ? *rz_new / den : 0.0;
+    p[i] = fma(beta, p[i], z[i]);
+}
+
+// alpha = rz / pq ;  x += alpha p ;  r -= alpha q
+__global__ void __launch_bounds__(TPB)
+k_cg_update(int64_t n, const double* __restrict__ rz, const double* __restrict__ pq,
+            const double* __restrict__ p, const double* __restrict__ q,
+            double* __restrict__ x, double* __restrict__ r, int first) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const double den = *pq;
+    const double alpha = den != 0.0 ? *rz / den : 0.0;
+    x[i] = first ? alpha * p[i] : fma(alpha, p[i], x[i]);
+    r[i] = fma(-alpha, q[i], r[i]);
+}
+
 // u = a - dinv .* g
 __global__ void __launch_bounds__(TPB)
 k_sub_scaled(int64_t n, const double* a, const double* __restrict__ dinv,
@@ -99,6 +111,35 @@ k_csr_diag(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __rest
     for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k)
         if (idx[k] == r) d = dat[k];
     diag[r] = d;
+}
+
+// Strength-filtered copy of A for prolongator smoothing: off-diagonal entries
+// with |a_ij| < theta * max_k |a_ik| are dropped and lumped onto the diagonal
+// (row sums preserved).  FILL = false counts, FILL = true writes.
+template <bool FILL>
+__global__ void __launch_bounds__(TPB)
+k_filter(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+         const double* __restrict__ dat, double theta, int32_t* __restrict__ cnt,
+         const int32_t* __restrict__ optr, int32_t* __restrict__ oidx, double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (r >= nrows) return;
+    double mx = 0.0;
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k)
+        if (idx[k] != r) mx = fmax(mx, fabs(dat[k]));
+    const double thr = theta * mx;
+    int32_t c = 0, o = FILL ? optr[r] : 0, dpos = -1;
+    double lump = 0.0;
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
+        const bool diag = idx[k] == r;
+        if (diag || fabs(dat[k]) >= thr) {
+            if (FILL) { oidx[o] = idx[k]; out[o] = dat[k]; if (diag) dpos = o; ++o; }
+            ++c;
+        } else {
+            lump += dat[k];
+        }
+    }
+    if (FILL) { if (dpos >= 0) out[dpos] += lump; }
+    else cnt[r] = c;
 }
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
@@ -189,8 +230,14 @@ k_csr_to_dense(int64_t n, const int32_t* __restrict__ ptr, const int32_t* __rest
 
 // Gauss-Jordan inverse with partial pivoting, one CTA, W = [A | I] (n x 2n,
 // row-major, in global memory / L2); on exit the right half is A^-1.
+// Per column: block arg-max, row swap, pivot row scaled and staged in shared
+// memory, then one warp per row eliminates with coalesced accesses.  Only the
+// columns that can be non-trivial are touched: k+1..n-1 of the left half and
+// 0..n-1 of the right half restricted to what earlier steps filled is not
+// tracked -- the right half is swept fully (n <= 2048).
 __global__ void __launch_bounds__(1024)
 k_gauss_jordan(int n, double* __restrict__ W, int32_t* __restrict__ info) {
+    extern __shared__ double prow[];      // 2n doubles: the scaled pivot row
     __shared__ double rv[32];
     __shared__ int ri[32];
     __shared__ int s_p;
@@ -222,28 +269,29 @@ k_gauss_jordan(int n, double* __restrict__ W, int32_t* __restrict__ info) {
         __syncthreads();
         const int p = s_p;
         double* rk = W + (int64_t)k * ld;
-        if (p != k) {
-            double* rp = W + (int64_t)p * ld;
-            for (int c = tid; c < ld; c += 1024) { double t = rk[c]; rk[c] = rp[c]; rp[c] = t; }
-            __syncthreads();
+        double* rp = W + (int64_t)p * ld;
+        const double piv = rp[k];
+        __syncthreads();                  // everyone holds the pivot before row p is rewritten
+        if (piv == 0.0) continue;
+        const double rinv = 1.0 / piv;
+        // swap rows k and p (columns >= k of the left half, all of the right
+        // half), scale the new pivot row, stage it in shared memory
+        for (int c = k + tid; c < ld; c += 1024) {
+            const double top = rk[c], bot = rp[c];
+            const double v = bot * rinv;
+            if (p != k) rp[c] = top;
+            rk[c] = v;
+            prow[c] = v;
         }
-        const double piv = rk[k];
-        if (piv != 0.0) {
-            const double rinv = 1.0 / piv;
-            __syncthreads();
-            for (int c = tid; c < ld; c += 1024) rk[c] *= rinv;
-            __syncthreads();
-            // eliminate column k from every other row; columns <= k of the left
-            // half are already unit vectors except column k itself
-            for (int64_t t = tid; t < (int64_t)n * ld; t += 1024) {
-                const int r = (int)(t / ld), c = (int)(t % ld);
-                if (r == k || c == k) continue;
-                const double f = W[(int64_t)r * ld + k];
-                if (f != 0.0) W[(int64_t)r * ld + c] = fma(-f, rk[c], W[(int64_t)r * ld + c]);
-            }
-            __syncthreads();
-            for (int r = tid; r < n; r += 1024)
-                if (r != k) W[(int64_t)r * ld + k] = 0.0;
+        __syncthreads();
+        // eliminate column k from every other row: one warp per row
+        for (int r = warp; r < n; r += 32) {
+            if (r == k) continue;
+            double* rr = W + (int64_t)r * ld;
+            const double f = rr[k];
+            if (f == 0.0) continue;
+            for (int c = k + 1 + lane; c < ld; c += 32) rr[c] = fma(-f, prow[c], rr[c]);
+            if (lane == 0) rr[k] = 0.0;
         }
         __syncthreads();
     }
@@ -262,13 +310,6 @@ __global__ void __launch_bounds__(TPB)
 k_set_identity_right(int n, double* __restrict__ W) {
     int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r < n) W[r * 2 * n + n + r] = 1.0;
-}
-
-template <int G>
-void launch_jacobi(int64_t n, const int32_t* ptr, const int32_t* idx, const double* dat,
-                   const double* dinv, double omega, const double* b, const double* xin,
-                   double* xout, cudaStream_t st) {
-    k_jacobi<G><<<npb_blocks(n * G, TPB), TPB, 0, st>>>(n, ptr, idx, dat, dinv, omega, b, xin, xout);
 }
 
 }  // namespace
@@ -306,13 +347,9 @@ struct npb_amg {
 
 static int jacobi_sweep(const npb_amg_level& L, double omega, const double* b, const double* xin,
                         double* xout, cudaStream_t st) {
-    const double mean = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
-    if (mean <= 3.0) launch_jacobi<2>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
-    else if (mean <= 6.0) launch_jacobi<4>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
-    else if (mean <= 16.0) launch_jacobi<8>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
-    else launch_jacobi<16>(L.A.nrows, L.A.indptr, L.A.indices, L.A.data, L.dinv, omega, b, xin, xout, st);
-    NPB_COUNT_LAUNCH();
-    return NPB_OK;
+    // xout = xin + omega dinv (b - A xin): the SpMV kernel with the Jacobi epilogue
+    return npb_spmv_ex(L.A.nrows, L.A.nnz, L.A.indptr, L.A.indices, L.A.data, xin, 3, b, L.dinv,
+                       omega, xout, 0, st);
 }
 
 // x <- V-cycle(b) from a zero initial guess.  b and x have the fine size and
@@ -392,6 +429,30 @@ static int amg_solve(const npb_amg* h, const npb_csr_mat& A, int k, const double
     return rc;
 }
 
+// x <- k steps of CG on A x = b preconditioned by one V-cycle (A SPD), zero
+// start.  r, z, p, q: work vectors; scal: 4 device doubles; red: zeroed
+// reduction scratch (npb_reduce_scratch_bytes).  b is not modified.
+static int amg_pcg(const npb_amg* h, const npb_csr_mat& A, int k, const double* b, double* x,
+                   double* r, double* z, double* p, double* q, double* scal, void* red,
+                   cudaStream_t st) {
+    const int64_t n = A.nrows;
+    int rc;
+    NPB_CUDA(cudaMemcpyAsync(r, b, n * 8, cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < k; ++i) {
+        double* rz_new = scal + (i & 1);
+        double* rz_old = scal + ((i + 1) & 1);
+        if ((rc = npb_amg_vcycle(h, r, z, (void*)st))) return rc;
+        if ((rc = npb_dot_multi_launch(n, 1, r, n, z, rz_new, red, st))) return rc;
+        k_cg_dir<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, rz_old, i == 0, z, p);
+        NPB_COUNT_LAUNCH();
+        if ((rc = npb_spmv_launch(n, A.nnz, A.indptr, A.indices, A.data, p, nullptr, q, 0, st))) return rc;
+        if ((rc = npb_dot_multi_launch(n, 1, p, n, q, scal + 2, red, st))) return rc;
+        k_cg_update<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, scal + 2, p, q, x, r, i == 0);
+        NPB_COUNT_LAUNCH();
+    }
+    return NPB_OK;
+}
+
 // y = k V-cycles applied to x: usable directly as an npb_apply_fn
 struct npb_amg_precond {
     const npb_amg* amg;
@@ -418,7 +479,9 @@ struct npb_lsc {
     const npb_amg* amg_l;
     int32_t cycles_a, cycles_l;
     double* wv[5];             // work vectors of size nv
-    double* wp[5];             // work vectors of size np
+    double* wp[8];             // work vectors of size np
+    double* scal;              // 4 device doubles (CG scalars)
+    void* red;                 // zeroed reduction scratch
 };
 
 int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
@@ -427,6 +490,7 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
     const int64_t nv = c->nv, np = c->np;
     double *rv = c->wv[0], *us = c->wv[1], *t1 = c->wv[2], *t2 = c->wv[3], *t3 = c->wv[4];
     double *rp = c->wp[0], *q = c->wp[1], *p1 = c->wp[2], *s1 = c->wp[3], *s2 = c->wp[4];
+    double *s3 = c->wp[5], *s4 = c->wp[6];
     int rc;
     k_gather<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, r, rv);
     NPB_COUNT_LAUNCH();
@@ -437,13 +501,13 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
         // q = r_P - D u*
         if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, us, rp, q, 1, st))) return rc;
         // p1 = L^-1 q            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
-        if ((rc = amg_solve(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, st))) return rc;
+        if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         // s1 = D A G p1
         if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t1, 0, st))) return rc;
         if ((rc = npb_spmv_launch(nv, c->A.nnz, c->A.indptr, c->A.indices, c->A.data, t1, nullptr, t2, 0, st))) return rc;
         if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, t2, nullptr, q, 0, st))) return rc;
         // p = -L^-1 s1
-        if ((rc = amg_solve(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, st))) return rc;
+        if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         if ((rc = npb_axpby_launch(np, 0.0, p1, -1.0, p1, st))) return rc;
         // u = u* - diag(A)^-1 G p
         if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t3, 0, st))) return rc;
@@ -502,6 +566,26 @@ int npb_amg_aggregate(int64_t n, const int32_t* indptr, const int32_t* indices,
     return NPB_OK;
 }
 
+int npb_csr_filter_symbolic(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                            const double* data, double theta, int32_t* counts,
+                            int32_t* indptr_out, int64_t* scan_ws, int64_t* stats, void* stream) {
+    NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), ST(stream)));
+    k_filter<false><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, theta, counts, nullptr, nullptr, nullptr);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_filter_count");
+    return npb_scan_launch(counts, indptr_out, nrows, scan_ws, stats, ST(stream));
+}
+
+int npb_csr_filter_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                           const double* data, double theta, const int32_t* indptr_out,
+                           int32_t* indices_out, double* out, void* stream) {
+    if (nrows <= 0) return NPB_OK;
+    k_filter<true><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, theta, nullptr, indptr_out, indices_out, out);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_filter_fill");
+    return NPB_OK;
+}
+
 // dense inverse of a small CSR matrix: W = scratch n x 2n, Minv = n x n out
 int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices, const double* data,
                       double* W, double* Minv, int32_t* info, void* stream) {
@@ -511,7 +595,12 @@ int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices, cons
     NPB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     k_csr_to_dense<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, indptr, indices, data, W, 2 * n);
     k_set_identity_right<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, W);
-    k_gauss_jordan<<<1, 1024, 0, st>>>(n, W, info);
+    {
+        size_t sh = sizeof(double) * 2 * (size_t)n;
+        if (sh > 48 * 1024)
+            NPB_CUDA(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        k_gauss_jordan<<<1, 1024, sh, st>>>(n, W, info);
+    }
     k_copy_right_half<<<npb_blocks((int64_t)n * n, TPB), TPB, 0, st>>>(n, W, Minv);
     NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("dense_inverse");

@@ -22,15 +22,70 @@ constexpr int RED_BLOCKS = NPB_NUM_SMS * 4;   // persistent grid of the reductio
 constexpr int KC = 16;                        // basis vectors per multi-dot pass
 
 // ---------------------------------------------------------------------- SpMV
-// G lanes cooperate on one row (G = 2..32 picked from nnz/row); lanes read
-// consecutive entries so a warp's loads of indices/data are contiguous.
-// mode 0: y = A x      mode 1: y = b - A x      mode 2: y = b + A x
-// (b may alias y: each row reads b[r] before it writes y[r])
+// Epilogues shared by both SpMV kernels (s = (A x)[r]):
+//   0: y = s     1: y = b - s     2: y = b + s
+//   3: y = x + omega * dinv .* (b - s)      (damped-Jacobi sweep; y != x)
+struct spmv_epi {
+    int mode;
+    const double* b;
+    const double* dinv;
+    double omega;
+};
+
+__device__ __forceinline__ double spmv_finish(const spmv_epi& e, int64_t r, double s,
+                                              const double* x) {
+    switch (e.mode) {
+        case 0: return s;
+        case 1: return e.b[r] - s;
+        case 2: return e.b[r] + s;
+        default: return x[r] + e.omega * e.dinv[r] * (e.b[r] - s);
+    }
+}
+
+// (a) "stream" kernel for short rows (the Jacobians here have 4..36 nnz/row):
+// a CTA owns 256 consecutive rows; it streams their CONTIGUOUS range of
+// (index, value) pairs with fully coalesced, mutually independent loads -- no
+// load depends on a row pointer, so memory-level parallelism is limited only
+// by occupancy -- stages the products in shared memory, then thread t sums row
+// t from shared memory in CSR order (deterministic, same order as a sequential
+// CPU SpMV).  Rows longer than the tile are handled by looping over tiles.
+constexpr int SP_ROWS = 256;
+constexpr int SP_TILE = 3072;       // 24 KB of products -> 8 CTAs / SM
+
+__global__ void __launch_bounds__(SP_ROWS)
+k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
+              const int32_t* __restrict__ idx, const double* __restrict__ dat,
+              const double* x, spmv_epi epi, double* y) {
+    __shared__ int32_t sptr[SP_ROWS + 1];
+    __shared__ double sprod[SP_TILE];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * SP_ROWS;
+    const int nr = (int)min((int64_t)SP_ROWS, nrows - r0);
+    if (tid <= nr) sptr[tid] = ptr[r0 + tid];
+    if (tid == 0 && nr == SP_ROWS) sptr[SP_ROWS] = ptr[r0 + SP_ROWS];
+    __syncthreads();
+    const int32_t k0 = sptr[0], k1 = sptr[nr];
+    const int32_t rs = (tid < nr) ? sptr[tid] : k1, re = (tid < nr) ? sptr[tid + 1] : k1;
+    double acc = 0.0;
+    for (int32_t base = k0; base < k1; base += SP_TILE) {
+        const int32_t lim = min(base + SP_TILE, k1);
+#pragma unroll 4
+        for (int32_t k = base + tid; k < lim; k += SP_ROWS)
+            sprod[k - base] = dat[k] * __ldg(x + idx[k]);
+        __syncthreads();
+        const int32_t s = max(rs, base), e = min(re, lim);
+        for (int32_t k = s; k < e; ++k) acc += sprod[k - base];
+        __syncthreads();
+    }
+    if (tid < nr) y[r0 + tid] = spmv_finish(epi, r0 + tid, acc, x);
+}
+
+// (b) "vector" kernel for long rows: G lanes cooperate on one row.
 template <int G>
 __global__ void __launch_bounds__(TPB)
 k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
        const int32_t* __restrict__ idx, const double* __restrict__ dat,
-       const double* __restrict__ x, const double* b, double* y, int mode) {
+       const double* x, spmv_epi epi, double* y) {
     const int lane = threadIdx.x & (G - 1);
     const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
     double s = 0.0;
@@ -41,7 +96,7 @@ k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
     }
 #pragma unroll
     for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (r < nrows && lane == 0) y[r] = mode == 0 ? s : (mode == 1 ? b[r] - s : b[r] + s);
+    if (r < nrows && lane == 0) y[r] = spmv_finish(epi, r, s, x);
 }
 
 // ------------------------------------------------ deterministic block reduce
@@ -168,23 +223,29 @@ int grid_for(int64_t n) {
 #define ST(s) ((cudaStream_t)(s))
 
 // ------------------------------------------------------------- internal API
-int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
-                    const double* dat, const double* x, const double* b, double* y,
-                    int mode, cudaStream_t st) {
+// y = epilogue(A x); see spmv_epi.  `variant`: 0 auto, 1 stream, 2 vector
+int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                const double* dat, const double* x, int mode, const double* b,
+                const double* dinv, double omega, double* y, int variant, cudaStream_t st) {
     if (nrows <= 0) return NPB_OK;
+    spmv_epi e{mode, b, dinv, omega};
     const double mean = (double)nnz / (double)nrows;
-#define NPB_SPMV(G)                                                             \
-    k_spmv<G><<<npb_blocks(nrows * G, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, \
-                                                           x, b, y, mode)
-    if (mean <= 3.0) NPB_SPMV(2);
-    else if (mean <= 6.0) NPB_SPMV(4);
-    else if (mean <= 16.0) NPB_SPMV(8);
-    else if (mean <= 48.0) NPB_SPMV(16);
-    else NPB_SPMV(32);
-#undef NPB_SPMV
+    if (variant == 1 || (variant == 0 && mean <= 64.0)) {
+        k_spmv_stream<<<npb_blocks(nrows, SP_ROWS), SP_ROWS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    } else if (mean <= 48.0) {
+        k_spmv<16><<<npb_blocks(nrows * 16, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    } else {
+        k_spmv<32><<<npb_blocks(nrows * 32, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    }
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("spmv");
     return NPB_OK;
+}
+
+int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                    const double* dat, const double* x, const double* b, double* y,
+                    int mode, cudaStream_t st) {
+    return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st);
 }
 
 // scratch: RED_BLOCKS*KC doubles of partials followed by one uint ticket
@@ -192,6 +253,10 @@ static inline double* red_partial(void* scratch) { return (double*)scratch; }
 static inline unsigned int* red_ticket(void* scratch) {
     return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC);
 }
+
+int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                const double* dat, const double* x, int mode, const double* b,
+                const double* dinv, double omega, double* y, int variant, cudaStream_t st);
 
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st) {
@@ -234,6 +299,13 @@ int64_t npb_reduce_scratch_bytes(void) {
 int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
              const double* data, const double* x, double* y, void* stream) {
     return npb_spmv_launch(nrows, nnz, indptr, indices, data, x, nullptr, y, 0, ST(stream));
+}
+
+// same, forcing a kernel variant (1 = stream, 2 = vector); for tests / tuning
+int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                     const double* data, const double* x, double* y, int variant, void* stream) {
+    return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, 0, nullptr, nullptr, 0.0, y, variant,
+                       ST(stream));
 }
 
 // y = b - A x

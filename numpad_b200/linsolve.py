@@ -109,6 +109,12 @@ def _tensor_from_ptr(ptr, n):
     return torch.as_tensor(h, device=device())
 
 
+def _now():
+    import time
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
 def solve(A, b, transpose=False, **opts):
     """x = A^{-1} b (or A^{-T} b) for a DevCsr A and a device vector b."""
     o = dict(DEFAULTS)
@@ -119,7 +125,9 @@ def solve(A, b, transpose=False, **opts):
     n = A.shape[0]
     b = b.reshape(-1).contiguous()
     from . import precond as _pc
+    t0 = _now()
     M, method = _pc.build(A, o['precond'])
+    t_setup = _now() - t0
     if method == 'direct':
         x = M.solve(b)
         r = b - A.matvec(x)
@@ -129,13 +137,19 @@ def solve(A, b, transpose=False, **opts):
             x = x + M.solve(r)
             res['rnorm'] = float((b - A.matvec(x)).norm())
         res['method'] = method
+        res['setup_ms'] = 1e3 * t_setup
         last_info.clear()
         last_info.update(res)
         return x
+    t0 = _now()
     pc = None if M is None else (M if hasattr(M, 'c_apply') else M.apply)
     x, res = fgmres(A, b, precond=pc, rtol=o['rtol'],
                     atol=o['atol'], restart=min(o['restart'], n), maxiter=o['maxiter'])
     res['method'] = method
+    res['setup_ms'] = 1e3 * t_setup
+    res['krylov_ms'] = 1e3 * (_now() - t0)
+    if hasattr(M, 'describe'):
+        res['precond'] = M.describe()
     last_info.clear()
     last_info.update(res)
     if _cb_error:

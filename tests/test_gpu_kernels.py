@@ -251,3 +251,21 @@ def test_dense_inverse(dev):
     got = Minv.cpu().numpy().reshape(n, n)
     ref = np.linalg.inv(a.toarray())
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize('shape,density', [((1, 1), 1.0), ((257, 300), 0.03), ((5000, 5000), 0.002),
+                                           ((3, 20000), 0.5), ((70000, 70000), 0.00013)])
+def test_spmv_variants_agree(dev, shape, density):
+    """stream (short rows) and vector (long rows) SpMV kernels vs scipy"""
+    import torch
+    rng = np.random.RandomState(10)
+    a = rand_csr(rng, shape[0], shape[1], density)
+    A = dev.DevCsr.from_scipy(a)
+    x = rng.standard_normal(shape[1])
+    xd = torch.from_numpy(x).to(dev.device())
+    want = a @ x
+    for variant in (1, 2):
+        y = torch.full((shape[0],), np.nan, dtype=torch.float64, device=dev.device())
+        dev._call('npb_spmv_variant', shape[0], A.nnz, A.indptr, A.indices, A.data, xd, y, variant)
+        np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-13,
+                                   atol=1e-13 * (np.abs(want).max() if a.nnz else 1))

@@ -1,0 +1,22 @@
+"""Sweep LSC/AMG parameters on one cavity Jacobian (GPU): iterations and times."""
+import argparse, os, sys, time, itertools
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import numpad_b200 as npd
+from numpad_b200 import linsolve, amg
+from numpad_b200.workloads.cavity import CavityProblem
+ap = argparse.ArgumentParser(); ap.add_argument('--grid', type=int, default=512)
+ap.add_argument('--configs', default='2,3,1,1;2,3,1,0;2,2,1,1;3,3,1,1;1,3,1,1')
+a = ap.parse_args()
+P = CavityProblem(npd, a.grid); u0 = P.fixed_state()
+u = npd.array(u0.copy()); res = P.residual(u, npd.array(u0), 1.0, 0)
+J = npd.diff_dev(res, u).materialized(); b = res._dev.reshape(-1).contiguous()
+for cfg in a.configs.split(';'):
+    ca, cl, nul, sm = [int(v) for v in cfg.split(',')]
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    M = amg.LscPreconditioner(J, cycles_a=ca, cycles_l=cl, nu_l=nul, smooth_a=bool(sm))
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    x, info = linsolve.fgmres(J, b, precond=M, rtol=1e-10, restart=60, maxiter=600)
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print('grid %d cycles_a=%d pcg_l=%d nu_l=%d smooth_a=%d: its %d status %d setup %.0f ms krylov %.0f ms | %s'
+          % (a.grid, ca, cl, nul, sm, info['iters'], info['status'], 1e3*(t1-t0), 1e3*(t2-t1), M.describe()), flush=True)
