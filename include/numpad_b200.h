@@ -166,7 +166,8 @@ int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr,
              double* y, void* stream);                       /* y = A x     */
 int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      const int32_t* indices, const double* data, const double* x,
-                     double* y, int variant /* 1 stream, 2 vector */, void* stream);
+                     double* y, int variant /* 1 stream, 2 vector, 3 stream+cp.async */,
+                     void* stream);
 int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
                       const int32_t* indices, const double* data,
                       const double* x, const double* b, double* y,

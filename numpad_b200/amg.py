@@ -95,7 +95,7 @@ class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=256, max_levels=24):
+                 coarse_max=600, max_levels=24):
         A = A.materialized()
         self.mats, self.keep = [], []
         levels = []

@@ -7,8 +7,9 @@
 // with V = rows with a diagonal entry, P = rows without,
 //      J = [ A  G ]  (V rows)        S = -D A^-1 G  ~  -(DG) (D A G)^-1 (DG)
 //          [ D  0 ]  (P rows)
-// M^-1 r:  u* = A~^-1 r_V ;  q = r_P - D u* ;  p = -L~^-1 (D A G) L~^-1 q with
-// L = -D G ;  u = u* - diag(A)^-1 G p.   A~^-1, L~^-1 = k V-cycles.
+// M^-1 r (block upper triangular):  p = -L~^-1 (D A G) L~^-1 r_P  with L = -D G ;
+// u = A~^-1 (r_V - G p).   L~^-1 = k CG steps preconditioned by a V-cycle,
+// A~^-1 = k stationary V-cycles.
 // The setup (aggregation, Galerkin products) runs once per matrix through the
 // chain-rule kernels of assembly.cu/coo.cu; everything below is the solve
 // phase: SpMV-shaped, HBM-bound kernels launched from C++ (no Python in the
@@ -485,37 +486,35 @@ struct npb_lsc {
 };
 
 int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
+    // block upper-triangular form:  p = S~^-1 r_P ;  u = A~^-1 (r_V - G p)
     const npb_lsc* c = (const npb_lsc*)ctx;
     cudaStream_t st = ST(stream);
     const int64_t nv = c->nv, np = c->np;
-    double *rv = c->wv[0], *us = c->wv[1], *t1 = c->wv[2], *t2 = c->wv[3], *t3 = c->wv[4];
+    double *rv = c->wv[0], *us = c->wv[1], *t1 = c->wv[2], *t2 = c->wv[3];
     double *rp = c->wp[0], *q = c->wp[1], *p1 = c->wp[2], *s1 = c->wp[3], *s2 = c->wp[4];
     double *s3 = c->wp[5], *s4 = c->wp[6];
     int rc;
     k_gather<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, r, rv);
     NPB_COUNT_LAUNCH();
-    if (np > 0) { k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, rp); NPB_COUNT_LAUNCH(); }
-    // u* = A~^-1 r_V
-    if ((rc = amg_solve(c->amg_a, c->A, c->cycles_a, rv, us, t1, t2, st))) return rc;
     if (np > 0) {
-        // q = r_P - D u*
-        if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, us, rp, q, 1, st))) return rc;
-        // p1 = L^-1 q            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
-        if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
-        // s1 = D A G p1
+        k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, rp);
+        NPB_COUNT_LAUNCH();
+        // p1 = L^-1 r_P            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
+        if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, rp, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
+        // q = D A G p1
         if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t1, 0, st))) return rc;
         if ((rc = npb_spmv_launch(nv, c->A.nnz, c->A.indptr, c->A.indices, c->A.data, t1, nullptr, t2, 0, st))) return rc;
         if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, t2, nullptr, q, 0, st))) return rc;
-        // p = -L^-1 s1
+        // p = -L^-1 q
         if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         if ((rc = npb_axpby_launch(np, 0.0, p1, -1.0, p1, st))) return rc;
-        // u = u* - diag(A)^-1 G p
-        if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t3, 0, st))) return rc;
-        k_sub_scaled<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, us, c->a_dinv, t3, us);
-        NPB_COUNT_LAUNCH();
+        // r_V <- r_V - G p
+        if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, rv, rv, 1, st))) return rc;
         k_scatter<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, p1, z);
         NPB_COUNT_LAUNCH();
     }
+    // u = A~^-1 (r_V - G p)
+    if ((rc = amg_solve(c->amg_a, c->A, c->cycles_a, rv, us, t1, t2, st))) return rc;
     k_scatter<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, us, z);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("lsc_apply");

@@ -49,35 +49,174 @@ __device__ __forceinline__ double spmv_finish(const spmv_epi& e, int64_t r, doub
 // by occupancy -- stages the products in shared memory, then thread t sums row
 // t from shared memory in CSR order (deterministic, same order as a sequential
 // CPU SpMV).  Rows longer than the tile are handled by looping over tiles.
-constexpr int SP_ROWS = 256;
+constexpr int SP_THREADS = 256;
 constexpr int SP_TILE = 3072;       // 24 KB of products -> 8 CTAs / SM
 
-__global__ void __launch_bounds__(SP_ROWS)
+// ROWS rows per CTA, TPR = 256 / ROWS threads cooperate on the sum of one row.
+// ROWS = 256 for the big operators (least overhead per row); 64 / 32 for the
+// small multigrid levels so that their grids still cover the 148 SMs.
+template <int ROWS>
+__global__ void __launch_bounds__(SP_THREADS)
 k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
               const int32_t* __restrict__ idx, const double* __restrict__ dat,
               const double* x, spmv_epi epi, double* y) {
-    __shared__ int32_t sptr[SP_ROWS + 1];
+    constexpr int TPR = SP_THREADS / ROWS;
+    __shared__ int32_t sptr[ROWS + 1];
     __shared__ double sprod[SP_TILE];
     const int tid = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * SP_ROWS;
-    const int nr = (int)min((int64_t)SP_ROWS, nrows - r0);
+    const int64_t r0 = (int64_t)blockIdx.x * ROWS;
+    const int nr = (int)min((int64_t)ROWS, nrows - r0);
     if (tid <= nr) sptr[tid] = ptr[r0 + tid];
-    if (tid == 0 && nr == SP_ROWS) sptr[SP_ROWS] = ptr[r0 + SP_ROWS];
+    if (ROWS == SP_THREADS && tid == 0 && nr == ROWS) sptr[ROWS] = ptr[r0 + ROWS];
     __syncthreads();
     const int32_t k0 = sptr[0], k1 = sptr[nr];
-    const int32_t rs = (tid < nr) ? sptr[tid] : k1, re = (tid < nr) ? sptr[tid + 1] : k1;
+    const int row = tid / TPR, sub = tid % TPR;
+    const int32_t rs = (row < nr) ? sptr[row] : k1, re = (row < nr) ? sptr[row + 1] : k1;
     double acc = 0.0;
     for (int32_t base = k0; base < k1; base += SP_TILE) {
         const int32_t lim = min(base + SP_TILE, k1);
 #pragma unroll 4
-        for (int32_t k = base + tid; k < lim; k += SP_ROWS)
+        for (int32_t k = base + tid; k < lim; k += SP_THREADS)
             sprod[k - base] = dat[k] * __ldg(x + idx[k]);
         __syncthreads();
         const int32_t s = max(rs, base), e = min(re, lim);
-        for (int32_t k = s; k < e; ++k) acc += sprod[k - base];
+        for (int32_t k = s + sub; k < e; k += TPR) acc += sprod[k - base];
         __syncthreads();
     }
-    if (tid < nr) y[r0 + tid] = spmv_finish(epi, r0 + tid, acc, x);
+    if (TPR > 1) {
+#pragma unroll
+        for (int d = TPR >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    }
+    if (row < nr && sub == 0) y[r0 + row] = spmv_finish(epi, r0 + row, acc, x);
+}
+
+// (a') same decomposition, but the (index, value) range is brought into shared
+// memory with 16-byte cp.async (LDGSTS): no registers are tied up by loads in
+// flight, so every CTA keeps its whole tile (36 KB) outstanding at once.  Needs
+// 16-byte aligned idx / dat base pointers (checked by the launcher).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(SP_THREADS)
+k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
+                    const int32_t* __restrict__ idx, const double* __restrict__ dat,
+                    const double* x, spmv_epi epi, double* y) {
+    constexpr int TPR = SP_THREADS / ROWS;
+    __shared__ int32_t sptr[ROWS + 1];
+    __shared__ __align__(16) int32_t sidx[SP_TILE];
+    __shared__ __align__(16) double sdat[SP_TILE];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * ROWS;
+    const int nr = (int)min((int64_t)ROWS, nrows - r0);
+    if (tid <= nr) sptr[tid] = ptr[r0 + tid];
+    if (ROWS == SP_THREADS && tid == 0 && nr == ROWS) sptr[ROWS] = ptr[r0 + ROWS];
+    __syncthreads();
+    const int32_t k0 = sptr[0], k1 = sptr[nr];
+    const int row = tid / TPR, sub = tid % TPR;
+    const int32_t rs = (row < nr) ? sptr[row] : k1, re = (row < nr) ? sptr[row + 1] : k1;
+    double acc = 0.0;
+    for (int32_t base = k0 & ~3; base < k1; base += SP_TILE) {
+        const int32_t lim = min(base + SP_TILE, k1);            // exclusive, unaligned
+        const int32_t full = (int32_t)min((int64_t)((lim - base + 3) & ~3), (nnz - base) & ~(int64_t)3);
+        // whole 16-byte chunks inside the arrays
+        for (int32_t c = tid * 4; c < full; c += SP_THREADS * 4) cp_async16(sidx + c, idx + base + c);
+        for (int32_t c = tid * 2; c < full; c += SP_THREADS * 2) cp_async16(sdat + c, dat + base + c);
+        // ragged tail at the very end of the arrays
+        for (int32_t k = base + full + tid; k < lim; k += SP_THREADS) {
+            sidx[k - base] = idx[k];
+            sdat[k - base] = dat[k];
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        const int32_t lo = max(base, k0);
+#pragma unroll 4
+        for (int32_t k = lo + tid; k < lim; k += SP_THREADS)
+            sdat[k - base] *= __ldg(x + sidx[k - base]);
+        __syncthreads();
+        const int32_t s = max(rs, base), e = min(re, lim);
+        for (int32_t k = s + sub; k < e; k += TPR) acc += sdat[k - base];
+        __syncthreads();
+    }
+    if (TPR > 1) {
+#pragma unroll
+        for (int d = TPR >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    }
+    if (row < nr && sub == 0) y[r0 + row] = spmv_finish(epi, r0 + row, acc, x);
+}
+
+// (a'') same decomposition with 128-bit loads: the tile starts at the 4-entry
+// boundary below the CTA's first entry, every thread fetches 4 indices (int4)
+// and 4 values (2 x double2) per round and three rounds are in flight at once
+// (144 B per thread outstanding instead of 48).  Needs 16-byte aligned idx /
+// dat base pointers (checked by the launcher).
+template <int ROWS>
+__global__ void __launch_bounds__(SP_THREADS)
+k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
+                 const int32_t* __restrict__ idx, const double* __restrict__ dat,
+                 const double* x, spmv_epi epi, double* y) {
+    constexpr int TPR = SP_THREADS / ROWS;
+    constexpr int ROUNDS = SP_TILE / (SP_THREADS * 4);
+    __shared__ int32_t sptr[ROWS + 1];
+    __shared__ __align__(16) double sprod[SP_TILE];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * ROWS;
+    const int nr = (int)min((int64_t)ROWS, nrows - r0);
+    if (tid <= nr) sptr[tid] = ptr[r0 + tid];
+    if (ROWS == SP_THREADS && tid == 0 && nr == ROWS) sptr[ROWS] = ptr[r0 + ROWS];
+    __syncthreads();
+    const int32_t k0 = sptr[0], k1 = sptr[nr];
+    const int row = tid / TPR, sub = tid % TPR;
+    const int32_t rs = (row < nr) ? sptr[row] : k1, re = (row < nr) ? sptr[row + 1] : k1;
+    double acc = 0.0;
+    for (int32_t base = k0 & ~3; base < k1; base += SP_TILE) {
+        const int32_t lim = min(base + SP_TILE, k1);
+        int4 iv[ROUNDS];
+        double2 da[ROUNDS], db[ROUNDS];
+#pragma unroll
+        for (int j = 0; j < ROUNDS; ++j) {
+            const int32_t k = base + (j * SP_THREADS + tid) * 4;
+            iv[j] = make_int4(0, 0, 0, 0);
+            da[j] = make_double2(0.0, 0.0);
+            db[j] = make_double2(0.0, 0.0);
+            if (k < lim) {
+                if ((int64_t)k + 3 < nnz) {
+                    iv[j] = *reinterpret_cast<const int4*>(idx + k);
+                    da[j] = *reinterpret_cast<const double2*>(dat + k);
+                    db[j] = *reinterpret_cast<const double2*>(dat + k + 2);
+                } else {                      // last 1..3 entries of the arrays
+                    iv[j].x = idx[k]; da[j].x = dat[k];
+                    if ((int64_t)k + 1 < nnz) { iv[j].y = idx[k + 1]; da[j].y = dat[k + 1]; }
+                    if ((int64_t)k + 2 < nnz) { iv[j].z = idx[k + 2]; db[j].x = dat[k + 2]; }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ROUNDS; ++j) {
+            const int32_t k = base + (j * SP_THREADS + tid) * 4;
+            if (k < lim) {
+                double2 p0, p1;
+                p0.x = da[j].x * __ldg(x + iv[j].x);
+                p0.y = da[j].y * __ldg(x + iv[j].y);
+                p1.x = db[j].x * __ldg(x + iv[j].z);
+                p1.y = db[j].y * __ldg(x + iv[j].w);
+                *reinterpret_cast<double2*>(sprod + (k - base)) = p0;
+                *reinterpret_cast<double2*>(sprod + (k - base) + 2) = p1;
+            }
+        }
+        __syncthreads();
+        const int32_t s = max(rs, base), e = min(re, lim);
+        for (int32_t k = s + sub; k < e; k += TPR) acc += sprod[k - base];
+        __syncthreads();
+    }
+    if (TPR > 1) {
+#pragma unroll
+        for (int d = TPR >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    }
+    if (row < nr && sub == 0) y[r0 + row] = spmv_finish(epi, r0 + row, acc, x);
 }
 
 // (b) "vector" kernel for long rows: G lanes cooperate on one row.
@@ -223,15 +362,27 @@ int grid_for(int64_t n) {
 #define ST(s) ((cudaStream_t)(s))
 
 // ------------------------------------------------------------- internal API
-// y = epilogue(A x); see spmv_epi.  `variant`: 0 auto, 1 stream, 2 vector
+// y = epilogue(A x); see spmv_epi.  `variant`: 0 auto, 1 stream, 2 vector, 3 stream + cp.async
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                 const double* dat, const double* x, int mode, const double* b,
                 const double* dinv, double omega, double* y, int variant, cudaStream_t st) {
     if (nrows <= 0) return NPB_OK;
     spmv_epi e{mode, b, dinv, omega};
     const double mean = (double)nnz / (double)nrows;
-    if (variant == 1 || (variant == 0 && mean <= 64.0)) {
-        k_spmv_stream<<<npb_blocks(nrows, SP_ROWS), SP_ROWS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    const bool aligned = (((uintptr_t)idx | (uintptr_t)dat) & 15) == 0;
+    if ((variant == 4 || (variant == 0 && nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)) && aligned) {
+        k_spmv_stream_v4<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
+    } else if (variant == 3 && aligned) {
+        k_spmv_stream_async<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
+    } else if (variant == 1 || variant == 3 || variant == 4 || (variant == 0 && mean <= 96.0)) {
+        // rows per CTA: as many as keep >= ~4 CTAs per SM in flight and the
+        // row block inside a few shared-memory tiles
+        if (nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)
+            k_spmv_stream<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+        else if (nrows >= 64 * NPB_NUM_SMS * 4 && mean <= 64.0)
+            k_spmv_stream<64><<<npb_blocks(nrows, 64), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+        else
+            k_spmv_stream<32><<<npb_blocks(nrows, 32), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
     } else if (mean <= 48.0) {
         k_spmv<16><<<npb_blocks(nrows * 16, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
     } else {

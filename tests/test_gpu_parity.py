@@ -190,3 +190,31 @@ def test_cavity_newton_step_lsc_vs_oracle(npd, orc, N):
     print('N=%d lsc: %s' % (N, info))
     assert info['iters'] <= 80
     np.testing.assert_allclose(du.cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
+def test_cavity_script_config1_vs_reference_golden(npd, golden):
+    """BASELINE.json configs[0]: test/cavity.py verbatim (N=50, 29 time steps,
+    71 Newton linear solves, dt doubling to 8192) and test/cavity_adjoint.py:6-8,
+    against the unmodified reference's results."""
+    import numpad_b200.adsolve as ads
+    z = golden.cavity_march_script
+    N = int(z['N'])
+    count = []
+    ads.newton_trace = lambda it, u, J, b, du: count.append(it)
+    try:
+        P, q, force, states, newton, t, dt = cavity_march(npd, N)
+    finally:
+        ads.newton_trace = None
+    assert len(count) == int(z['n_linear_solves']) == 71
+    np.testing.assert_array_equal(newton, z['n_newton'])
+    assert len(states) == 29 and t == float(z['final_t']) == 16476.0 and dt == 8192.0
+    scale = np.abs(z['states']).max()
+    np.testing.assert_allclose(states[[0, 1, -1]], z['states'], rtol=0, atol=1e-10 * scale)
+    np.testing.assert_allclose(np.linalg.norm(states, axis=1), z['state_norms'], rtol=1e-10)
+    assert abs(np.linalg.norm(states[-1]) - 6.015146088185117) < 1e-9
+    assert abs(q._res_norm - float(z['final_res_norm'])) < 1e-6 * float(z['final_res_norm']) + 1e-12
+    ke = 0.5 * npd.sum(q[N * N:] ** 2)
+    assert abs(float(ke._value) - float(z['kinetic_energy'])) < 1e-10 * abs(float(z['kinetic_energy']))
+    adj = ke.diff(force).toarray().ravel()
+    np.testing.assert_allclose(adj, z['adjoint'], rtol=0, atol=1e-8 * np.abs(z['adjoint']).max())
+    assert abs(np.linalg.norm(adj) - 7.079873951678084e+02) < 1e-5
