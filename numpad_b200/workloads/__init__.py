@@ -5,3 +5,4 @@ CPU oracle, or the unmodified reference) so that the very same operation
 sequence -- hence the same tape -- is recorded on all three.
 """
 from .cavity import CavityProblem  # noqa: F401
+from .kec import KecProblem  # noqa: F401

@@ -185,10 +185,64 @@ def gen_poisson_solve(numpad):
     print('poisson solve done')
 
 
+def kec_namespace(numpad, script, Ni, Nj):
+    """exec the part of test/euler_kec.py / test/navierstokes.py above the time
+    integration with a stub `pylab` (numpy names, no plotting) and bind the
+    module globals the residual reads"""
+    import types
+    stub = types.ModuleType('pylab')
+    stub.__dict__.update({k: getattr(np, k) for k in ('pi', 'sin', 'cos', 'sqrt', 'linspace',
+                                                       'arange', 'meshgrid', 'vstack')})
+    sys.modules['pylab'] = stub
+    src = open(os.path.join(REF, 'test', script)).read()
+    src = src.split('# ---------------------- time integration')[0]
+    src = src.replace("sys.path.append('../..')", '')
+    g = {}
+    exec(src, g)
+    sys.path.insert(0, ROOT)
+    from numpad_b200.workloads.kec import synthetic_mesh
+    x, y = synthetic_mesh(Ni, Nj)
+    g.update(Ni=Ni, Nj=Nj, p_out=1E5, mu=1.0,
+             pt_in=1.2E5 if script.startswith('navier') else 1.05E5)
+    g['geo'] = g['geo2d']([x, y])
+    return g
+
+
+def gen_kec(numpad):
+    out = {}
+    Ni, Nj = 7, 5
+    for script, fn, tag in (('euler_kec.py', 'euler_kec', 'euler'),
+                            ('navierstokes.py', 'ns_kec', 'ns')):
+        g = kec_namespace(numpad, script, Ni, Nj)
+        w = np.empty([4, Ni, Nj])
+        w[0] = 1.0
+        w[1] = 0.3 * np.sqrt(1.4E5)
+        w[2] = 0.0
+        w[3] = 1E5 / 0.4 + 0.5 * w[1] ** 2
+        w *= 1 + 1e-3 * np.random.RandomState(0).standard_normal(w.shape)
+        w0 = w.ravel()
+        dt = 0.1 if tag == 'euler' else 1. / Nj
+        for mode in ('adjoint', 'tangent'):
+            u = numpad.array(w0.copy())
+            res = g[fn](u, numpad.array(w0.copy()), g['geo'], dt)
+            pack('%s.%s' % (tag, mode), res.diff(u, mode), out)
+        out['%s.res' % tag] = res._value.copy()
+        out['%s.w0' % tag] = w0
+        out['%s.states' % tag] = np.int64(res._current_state._state_id - u._initial_state._state_id)
+    out['Ni'], out['Nj'] = np.int64(Ni), np.int64(Nj)
+    np.savez_compressed(os.path.join(HERE, 'kec_jacobian.npz'), **out)
+    print('kec jacobians done: euler nnz', int(out['euler.adjoint.raw_nnz']),
+          'ns nnz', int(out['ns.adjoint.raw_nnz']))
+
+
 if __name__ == '__main__':
     numpad = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'kec':
+        gen_kec(numpad)
+        sys.exit(0)
     gen_opcases(numpad)
     gen_cavity(numpad)
     gen_poisson_solve(numpad)
     gen_cavity_march(numpad, 8, 'small')
     gen_cavity_march(numpad, 50, 'script')
+    gen_kec(numpad)

@@ -218,3 +218,70 @@ def test_cavity_script_config1_vs_reference_golden(npd, golden):
     adj = ke.diff(force).toarray().ravel()
     np.testing.assert_allclose(adj, z['adjoint'], rtol=0, atol=1e-8 * np.abs(z['adjoint']).max())
     assert abs(np.linalg.norm(adj) - 7.079873951678084e+02) < 1e-5
+
+
+@pytest.mark.parametrize('N', [96])
+def test_cavity_adjoint_through_solve_vs_oracle(npd, orc, N):
+    """BASELINE.json configs[2] at a size the oracle finishes in seconds: one
+    implicit time step (dt = 0.02, diffusion-dominated regime -- see DESIGN.md
+    section 5 on convection-dominated Jacobians) solved by Newton with the
+    Krylov + LSC/AMG solver (no direct solve at this size), then the adjoint of
+    the kinetic energy w.r.t. the forcing: one TRANSPOSED solve
+    J^T lambda = g^T (reference adsolve.py:49-86)."""
+    from numpad_b200 import linsolve
+    from numpad_b200.workloads.cavity import CavityProblem
+    out = {}
+    for name, xp in (('gpu', npd), ('cpu', orc)):
+        P = CavityProblem(xp, N)
+        q0 = xp.array(P.fixed_state(amp=1e-3))
+        force = xp.zeros(P.n)
+        q = xp.solve(P.residual, q0, args=(q0, 0.02, force), rel_tol=1e-9, abs_tol=1e-9,
+                     verbose=False)
+        ke = 0.5 * xp.sum(q[N * N:] ** 2)
+        adj = ke.diff(force).toarray().ravel()
+        out[name] = (np.array(q._value), q._n_Newton, adj)
+        if name == 'gpu':
+            assert linsolve.last_info['method'] == 'fgmres+lsc'
+    assert out['gpu'][1] == out['cpu'][1]
+    scale = np.abs(out['cpu'][0]).max()
+    np.testing.assert_allclose(out['gpu'][0], out['cpu'][0], rtol=0, atol=1e-10 * scale)
+    np.testing.assert_allclose(out['gpu'][2], out['cpu'][2], rtol=0,
+                               atol=1e-8 * np.abs(out['cpu'][2]).max())
+
+
+@pytest.mark.parametrize('tag', ['euler', 'ns'])
+def test_kec_jacobian_vs_reference_golden(npd, golden, tag):
+    """BASELINE.json configs[3]/[4] residuals (test/euler_kec.py,
+    test/navierstokes.py: broadcasting products, axis sums, list indexing,
+    augmented slice assignment) against the unmodified reference"""
+    from numpad_b200.workloads.kec import KecProblem
+    z = golden.kec_jacobian
+    Ni, Nj = int(z['Ni']), int(z['Nj'])
+    P = KecProblem(npd, Ni, Nj, viscous=(tag == 'ns'))
+    w0 = P.fixed_state()
+    dt = 0.1 if tag == 'euler' else 1. / Nj
+    for mode in ('adjoint', 'tangent'):
+        u = npd.array(w0.copy())
+        res = P.residual(u, npd.array(w0.copy()), dt)
+        key = '%s.%s' % (tag, mode)
+        assert_csr_parity(res.diff(u, mode), load_csr(z, key), rtol=1e-12,
+                          raw_nnz=int(z[key + '.raw_nnz']), what=key)
+    scale = np.abs(z[tag + '.res']).max()
+    np.testing.assert_allclose(res._value, z[tag + '.res'], rtol=0, atol=1e-12 * scale)
+    assert res._current_state._state_id - u._initial_state._state_id == int(z[tag + '.states'])
+
+
+@pytest.mark.parametrize('tag,Ni,Nj', [('euler', 48, 32), ('ns', 40, 24)])
+def test_kec_jacobian_vs_oracle(npd, orc, tag, Ni, Nj):
+    from numpad_b200.workloads.kec import KecProblem
+    Pg = KecProblem(npd, Ni, Nj, viscous=(tag == 'ns'))
+    Po = KecProblem(orc, Ni, Nj, viscous=(tag == 'ns'))
+    w0 = Pg.fixed_state()
+    dt = 0.1 if tag == 'euler' else 1. / Nj
+    ug, uo = npd.array(w0.copy()), orc.array(w0.copy())
+    rg = Pg.residual(ug, npd.array(w0.copy()), dt)
+    ro = Po.residual(uo, orc.array(w0.copy()), dt)
+    Jo = ro.diff(uo)
+    # v = 0 in the base flow makes a handful of entries exact cancellations
+    assert_csr_parity(rg.diff(ug), Jo, rtol=1e-12, what=tag, noise=1e-15)
+    assert (Jo.diagonal() != 0).all()           # full diagonal (SURVEY section 7)

@@ -117,3 +117,24 @@ def test_poisson_solve(golden):
     assert_csr_parity(orc.sum(u).diff(f), load_csr(z, 'du_df.adjoint'), rtol=1e-13)
     assert_csr_parity(u.diff(dxa), load_csr(z, 'du_ddx.tangent'), rtol=1e-13)
     assert_csr_parity(u.diff(f, 'tangent'), load_csr(z, 'du_df.tangent'), rtol=1e-13)
+
+
+@pytest.mark.parametrize('tag', ['euler', 'ns'])
+def test_kec_jacobian(golden, tag):
+    """configs 4/5 residuals (test/euler_kec.py, test/navierstokes.py) on the
+    synthetic duct mesh: oracle + restated workload vs the reference, bit-exact"""
+    from numpad_b200.workloads.kec import KecProblem
+    z = golden.kec_jacobian
+    Ni, Nj = int(z['Ni']), int(z['Nj'])
+    P = KecProblem(orc, Ni, Nj, viscous=(tag == 'ns'))
+    w0 = P.fixed_state()
+    np.testing.assert_array_equal(w0, z[tag + '.w0'])
+    dt = 0.1 if tag == 'euler' else 1. / Nj
+    for mode in ('adjoint', 'tangent'):
+        u = orc.array(w0.copy())
+        res = P.residual(u, orc.array(w0.copy()), dt)
+        key = '%s.%s' % (tag, mode)
+        assert_csr_parity(res.diff(u, mode), load_csr(z, key), rtol=0.0,
+                          raw_nnz=int(z[key + '.raw_nnz']), what=key)
+    np.testing.assert_array_equal(res._value, z[tag + '.res'])
+    assert res._current_state.id - u._initial_state.id == int(z[tag + '.states'])
