@@ -267,6 +267,9 @@ typedef struct npb_lsc {            /* [host] ctx of npb_lsc_apply_cb */
     double* wp[8];
     double* scal;                   /* 4 device doubles */
     void* red;                      /* npb_reduce_scratch_bytes(), zeroed */
+    int32_t a_gmres, pad;           /* > 0: A-solve = that many Jacobi-GMRES steps */
+    void* a_work;                   /* npb_fgmres_workspace_bytes(nv, a_gmres, 0) */
+    int64_t a_work_bytes;
 } npb_lsc;
 
 int npb_csr_diagonal(int64_t nrows, const int32_t* indptr, const int32_t* indices,
@@ -288,6 +291,12 @@ int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices,
                       void* stream);
 int npb_gather(int64_t n, const int32_t* idx, const double* src, double* dst,
                void* stream);
+/* CG steps with device-resident scalars: p = z + (rz_new/rz_old) p ;
+ * x += (rz/pq) p, r -= (rz/pq) q */
+int npb_cg_dir(int64_t n, const double* rz_new, const double* rz_old, int first,
+               const double* z, double* p, void* stream);
+int npb_cg_update(int64_t n, const double* rz, const double* pq, const double* p,
+                  const double* q, double* x, double* r, int first, void* stream);
 int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream);
 int npb_amg_apply_cb(void* ctx, const double* x, double* y, void* stream);
 int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream);

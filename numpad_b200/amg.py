@@ -49,7 +49,8 @@ class LscStruct(ctypes.Structure):
                 ('amg_l', ctypes.c_void_p), ('cycles_a', ctypes.c_int32),
                 ('cycles_l', ctypes.c_int32), ('wv', ctypes.c_void_p * 5),
                 ('wp', ctypes.c_void_p * 8), ('scal', ctypes.c_void_p),
-                ('red', ctypes.c_void_p)]
+                ('red', ctypes.c_void_p), ('a_gmres', ctypes.c_int32), ('pad', ctypes.c_int32),
+                ('a_work', ctypes.c_void_p), ('a_work_bytes', ctypes.c_int64)]
 
 
 def csr_mat(A):
@@ -216,7 +217,7 @@ class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
     def __init__(self, J, cycles_a=2, cycles_l=3, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
-                 reuse=None):
+                 reuse=None, a_gmres=0):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -252,8 +253,17 @@ class LscPreconditioner:
         # momentum block: aggregation on the strength graph, prolongator smoothed
         # with the strength-filtered operator (keeps the two velocity components
         # apart, operator complexity ~2.5 instead of ~4)
-        self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a)
-        self.a_dinv = self.amg_a.levels[0]['dinv']
+        if a_gmres > 0:
+            # robust mode: no multigrid for the momentum block (see csrc/amg.cu)
+            self.amg_a = None
+            dA = diagonal(self.A)
+            self.a_dinv = torch.where(dA != 0, 1.0 / dA, torch.ones_like(dA))
+            wb = _lib.lib().cdll.npb_fgmres_workspace_bytes(nv, int(a_gmres), 0)
+            self.a_work = _empty(wb, torch.uint8)
+        else:
+            self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a)
+            self.a_dinv = self.amg_a.levels[0]['dinv']
+        self.a_gmres = int(a_gmres)
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]
         self.wp = [torch.zeros(max(np_, 1), dtype=torch.float64, device=device()) for _ in range(8)]
         self.scal = torch.zeros(4, dtype=torch.float64, device=device())
@@ -264,7 +274,11 @@ class LscPreconditioner:
         s.vset, s.pset = vset.data_ptr(), pset.data_ptr()
         s.A, s.G, s.D, s.Lm = csr_mat(self.A), csr_mat(self.G), csr_mat(self.D), csr_mat(self.Lm)
         s.a_dinv = self.a_dinv.data_ptr()
-        s.amg_a, s.amg_l = self.amg_a.addr, self.amg_l.addr
+        s.amg_a = self.amg_a.addr if self.amg_a is not None else None
+        s.amg_l = self.amg_l.addr
+        s.a_gmres = self.a_gmres
+        if self.a_gmres > 0:
+            s.a_work, s.a_work_bytes = self.a_work.data_ptr(), self.a_work.numel()
         s.cycles_a, s.cycles_l = int(cycles_a), int(cycles_l)
         for k in range(5):
             s.wv[k] = self.wv[k].data_ptr()
@@ -280,5 +294,5 @@ class LscPreconditioner:
             raise RuntimeError('npb_lsc_apply_cb failed: %s' % _lib.lib().last_error())
 
     def describe(self):
-        return 'LSC: nv=%d np=%d | A-AMG %s | L-AMG %s' % (
-            self.nv, self.np, self.amg_a.describe(), self.amg_l.describe())
+        a = self.amg_a.describe() if self.amg_a is not None else 'GMRES(%d)-Jacobi' % self.a_gmres
+        return 'LSC: nv=%d np=%d | A: %s | L-AMG %s' % (self.nv, self.np, a, self.amg_l.describe())

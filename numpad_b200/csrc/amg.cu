@@ -29,6 +29,23 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st);
 
+extern "C" {
+typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
+typedef int (*npb_allreduce_fn)(void* ctx, double* buf, int count, void* stream);
+struct npb_krylov_ops {
+    npb_apply_fn matvec; void* matvec_ctx;
+    npb_apply_fn precond; void* precond_ctx;
+    npb_allreduce_fn allreduce; void* allreduce_ctx;
+};
+struct npb_csr_view { int64_t nrows, nnz; const int32_t* indptr; const int32_t* indices; const double* data; };
+struct npb_krylov_info { int32_t iters, restarts, status, pad; double bnorm, rnorm0, rnorm; };
+int npb_csr_matvec_cb(void* ctx, const double* x, double* y, void* stream);
+int64_t npb_fgmres_workspace_bytes(int64_t n, int restart, int flexible);
+int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x, int restart,
+               int maxiter, double rtol, double atol, int flexible, void* work,
+               int64_t work_bytes, npb_krylov_info* info, void* stream);
+}
+
 namespace {
 
 constexpr int TPB = 256;
@@ -91,6 +108,14 @@ k_cg_update(int64_t n, const double* __restrict__ rz, const double* __restrict__
     const double alpha = den != 0.0 ? *rz / den : 0.0;
     x[i] = first ? alpha * p[i] : fma(alpha, p[i], x[i]);
     r[i] = fma(-alpha, q[i], r[i]);
+}
+
+// y = d .* x
+__global__ void __launch_bounds__(TPB)
+k_diag_scale(int64_t n, const double* __restrict__ d, const double* __restrict__ x,
+             double* __restrict__ y) {
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) y[i] = d[i] * x[i];
 }
 
 // u = a - dinv .* g
@@ -483,7 +508,37 @@ struct npb_lsc {
     double* wp[8];             // work vectors of size np
     double* scal;              // 4 device doubles (CG scalars)
     void* red;                 // zeroed reduction scratch
+    // robust mode for convection-dominated momentum blocks (a_gmres > 0): the
+    // A-solve is a_gmres steps of Jacobi-preconditioned GMRES (cannot diverge,
+    // unlike a Jacobi-smoothed V-cycle on a matrix without diagonal dominance)
+    int32_t a_gmres, pad;
+    void* a_work;              // npb_fgmres_workspace_bytes(nv, a_gmres, 0)
+    int64_t a_work_bytes;
 };
+
+struct diag_ctx { int64_t n; const double* d; };
+static int diag_scale_cb(void* ctx, const double* x, double* y, void* stream) {
+    const diag_ctx* c = (const diag_ctx*)ctx;
+    if (c->n > 0) {
+        k_diag_scale<<<npb_blocks(c->n, TPB), TPB, 0, ST(stream)>>>(c->n, c->d, x, y);
+        NPB_COUNT_LAUNCH();
+    }
+    return NPB_OK;
+}
+
+static int lsc_solve_a(const npb_lsc* c, const double* b, double* x, double* r, double* dx,
+                       cudaStream_t st) {
+    if (c->a_gmres <= 0) return amg_solve(c->amg_a, c->A, c->cycles_a, b, x, r, dx, st);
+    npb_csr_view view{c->A.nrows, c->A.nnz, c->A.indptr, c->A.indices, c->A.data};
+    diag_ctx dc{c->nv, c->a_dinv};
+    npb_krylov_ops ops{npb_csr_matvec_cb, &view, diag_scale_cb, &dc, nullptr, nullptr};
+    npb_krylov_info info;
+    NPB_CUDA(cudaMemsetAsync(x, 0, (size_t)c->nv * 8, st));
+    int rc = npb_fgmres(c->nv, &ops, b, x, c->a_gmres, c->a_gmres, 1e-3, 0.0, 0, c->a_work,
+                        c->a_work_bytes, &info, (void*)st);
+    return (rc == NPB_ERR_NOCONV) ? NPB_OK : rc;     // a fixed budget, not a tolerance
+}
+
 
 int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
     // block upper-triangular form:  p = S~^-1 r_P ;  u = A~^-1 (r_V - G p)
@@ -514,7 +569,7 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
         NPB_COUNT_LAUNCH();
     }
     // u = A~^-1 (r_V - G p)
-    if ((rc = amg_solve(c->amg_a, c->A, c->cycles_a, rv, us, t1, t2, st))) return rc;
+    if ((rc = lsc_solve_a(c, rv, us, t1, t2, st))) return rc;
     k_scatter<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, us, z);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("lsc_apply");
@@ -603,6 +658,26 @@ int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices, cons
     k_copy_right_half<<<npb_blocks((int64_t)n * n, TPB), TPB, 0, st>>>(n, W, Minv);
     NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("dense_inverse");
+    return NPB_OK;
+}
+
+// CG building blocks with device-resident scalars (used by the multi-GPU
+// preconditioner, which interleaves them with NCCL all-reduces of rz / pq)
+int npb_cg_dir(int64_t n, const double* rz_new, const double* rz_old, int first,
+               const double* z, double* p, void* stream) {
+    if (n <= 0) return NPB_OK;
+    k_cg_dir<<<npb_blocks(n, TPB), TPB, 0, ST(stream)>>>(n, rz_new, rz_old, first, z, p);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("cg_dir");
+    return NPB_OK;
+}
+
+int npb_cg_update(int64_t n, const double* rz, const double* pq, const double* p,
+                  const double* q, double* x, double* r, int first, void* stream) {
+    if (n <= 0) return NPB_OK;
+    k_cg_update<<<npb_blocks(n, TPB), TPB, 0, ST(stream)>>>(n, rz, pq, p, q, x, r, first);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("cg_update");
     return NPB_OK;
 }
 

@@ -19,10 +19,17 @@ from ._lib import KrylovOps, CsrView, KrylovInfo
 from ._dev import DevCsr, device, stream_ptr, _empty
 
 # knobs (also settable through solve(..., linear_options={...}))
-DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=60, maxiter=3000, precond='auto',
+DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=60, maxiter=600, precond='auto',
                 verbose=False)
 
 last_info = {}      # filled by every solve: iterations, residuals, method
+_hints = {'robust': False}
+
+
+def reset_hints():
+    """called at the start of every Newton solve: forget that the previous
+    sequence of Jacobians needed the robust inner solver"""
+    _hints['robust'] = False
 
 
 class LinearSolveError(RuntimeError):
@@ -126,7 +133,12 @@ def solve(A, b, transpose=False, **opts):
     b = b.reshape(-1).contiguous()
     from . import precond as _pc
     t0 = _now()
+    if o['precond'] == 'lsc' and _hints['robust']:
+        o['precond'] = 'lsc-robust'
     M, method = _pc.build(A, o['precond'])
+    if method == 'fgmres+lsc' and _hints['robust']:
+        M, method = _pc.build(A, 'lsc-robust')
+    first_try = method == 'fgmres+lsc'
     t_setup = _now() - t0
     if method == 'direct':
         x = M.solve(b)
@@ -143,8 +155,11 @@ def solve(A, b, transpose=False, **opts):
         return x
     t0 = _now()
     pc = None if M is None else (M if hasattr(M, 'c_apply') else M.apply)
+    # a multigrid-preconditioned solve that has not converged within two restart
+    # cycles will not: fail fast and let the robust retry below take over
+    maxit = min(o['maxiter'], 2 * o['restart']) if first_try else o['maxiter']
     x, res = fgmres(A, b, precond=pc, rtol=o['rtol'],
-                    atol=o['atol'], restart=min(o['restart'], n), maxiter=o['maxiter'])
+                    atol=o['atol'], restart=min(o['restart'], n), maxiter=maxit)
     res['method'] = method
     res['setup_ms'] = 1e3 * t_setup
     res['krylov_ms'] = 1e3 * (_now() - t0)
@@ -159,6 +174,12 @@ def solve(A, b, transpose=False, **opts):
     if o['verbose']:
         print('    linear solve [%s]: %d its, |r|/|b| = %.2e' %
               (method, res['iters'], res['rnorm'] / max(res['bnorm'], 1e-300)))
+    if res['status'] != 0 and method == 'fgmres+lsc':
+        # multigrid on a convection-dominated momentum block can diverge: retry
+        # with the Krylov inner solve, and keep using it for the rest of this
+        # Newton sequence
+        _hints['robust'] = True
+        return solve(A, b, **dict(o, precond='lsc-robust'))
     if res['status'] != 0 and method != 'direct' and _pc.direct_feasible(A):
         # robust fallback: pivoted banded LU (+ refinement through the front door)
         return solve(A, b, **dict(o, precond='direct'))

@@ -8,6 +8,9 @@ build(A, kind) -> (M, method):
   'lsc'    : block preconditioner for saddle-point Jacobians (rows with a
              zero diagonal = constraints): least-squares-commutator Schur
              complement with multigrid sub-solves
+  'lsc-robust': same, the momentum block solved by Jacobi-GMRES instead of a
+             V-cycle; the automatic retry when 'lsc' stagnates or diverges
+             (convection-dominated Jacobians, where Jacobi smoothing diverges)
   'auto'   : picks from the size and structure of A
 """
 import ctypes
@@ -117,11 +120,11 @@ def build(A, kind='auto'):
         return None, 'gmres'
     if kind == 'direct':
         return BandLU(A), 'direct'
-    if kind == 'lsc':
+    if kind in ('lsc', 'lsc-robust'):
         from . import amg
-        M = amg.LscPreconditioner(A, reuse=_last['lsc'])
+        M = amg.LscPreconditioner(A, reuse=_last['lsc'], a_gmres=40 if kind == 'lsc-robust' else 0)
         _last['lsc'] = M
-        return M, 'fgmres+lsc'
+        return M, 'fgmres+' + kind
     if kind == 'amg':
         from . import amg
         return amg.AmgPreconditioner(A, theta=0.25, nu=2), 'fgmres+amg'

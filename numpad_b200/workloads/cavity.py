@@ -24,6 +24,18 @@ class CavityProblem:
     def fixed_state(self, seed=0, amp=1e-2):
         return amp * np.random.RandomState(seed).standard_normal(self.n)
 
+    def partition(self, world):
+        """owner[i] (numpy int32) for a strip decomposition along the first grid
+        index: every field of a cell column goes to the strip of that column
+        (SURVEY section 8e), so rows of J reference only their own strip plus
+        a one-cell halo."""
+        N = self.N
+        strip = lambda i: np.minimum((i * world) // N, world - 1)
+        ip = np.repeat(np.arange(N), N)              # p[i, j]
+        iux = np.repeat(np.arange(N - 1), N)         # u_x interior face i+1 | cell i
+        iuy = np.repeat(np.arange(N), N - 1)         # u_y[i, j]
+        return np.concatenate([strip(ip), strip(iux), strip(iuy)]).astype(np.int32)
+
     def fields(self, q):
         """Split the unknown vector and pad the velocities with ghost faces
         that carry the wall / lid boundary conditions."""
