@@ -1,0 +1,170 @@
+"""Distributed Jacobian and the distributed Krylov solve.
+
+Same public surface as the reference's admpisolve.py (`MpiJacobian` with
+`matvec` / `approx_solve`, `_lgmres`, `_dot`, `_norm2`, the `solve_mpi` stub),
+on torch.distributed / NCCL and the CUDA kernels of the C-ABI:
+
+  * `MpiJacobian(f_diff_u, 'CSR')` takes the `{rank_j: d f_local / d u_rank_j}`
+    blocks of `diff_mpi` (device matrices or scipy) and merges them into ONE
+    row-sharded CSR whose columns are renumbered to [owned | halo]
+    (`parallel.DistCsr`).  `matvec` exchanges x halos and runs one local SpMV --
+    the reference's CSR->CSC ownership swap and partial-y exchange
+    (admpisolve.py:61-98, 146-165) are not needed;
+  * `approx_solve` is block-Jacobi across ranks, like the reference's LU of the
+    local diagonal block (admpisolve.py:167-172): a pivoted banded LU when the
+    block is small, otherwise one multigrid V-cycle;
+  * `_lgmres(A, b, x0, tol, maxiter, M, ...)` keeps the reference's calling
+    convention (operators are callables on LOCAL vectors, returns `(x, info)`,
+    stops when ||r|| < tol*||b|| or < tol) and runs the C++ FGMRES with one
+    batched all-reduce per group of inner products instead of one `Allreduce`
+    per dot (admpisolve.py:177-188, 386-390).  The LGMRES augmentation vectors
+    (`outer_k`, `outer_v`) are accepted and ignored.
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+from .admpi import COMM_WORLD, diff_mpi, diff_mpi_dev, _rank, _world   # noqa: F401
+from .adstate import DevCsr, DevEye, _is0
+from ._dev import device, _call
+from . import parallel, linsolve
+
+
+def _dev_vec(x):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device(), dtype=torch.float64).reshape(-1).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1))).to(device())
+
+
+class MpiJacobian:
+    """mode='CSR': f_diff_u[rank_i] = d f[my_rank] / d u[rank_i]  (what diff_mpi
+    returns).  mode='CSC' (column ownership) is not needed by this design."""
+
+    def __init__(self, f_diff_u, mode='CSR'):
+        if mode != 'CSR':
+            raise NotImplementedError('only row ownership (mode="CSR") is supported')
+        rank, world = _rank(), _world()
+        dev = device()
+        blocks = {}
+        for r, b in f_diff_u.items():
+            if _is0(b):
+                continue
+            if isinstance(b, DevEye):
+                b = b.todev()
+            elif not isinstance(b, DevCsr):
+                b = DevCsr.from_scipy(sp.csr_matrix(b))
+            if b.nnz:
+                blocks[r] = b.materialized()
+        n_rows = blocks[rank].shape[0] if rank in blocks else \
+            next(iter(f_diff_u.values())).shape[0]
+        # column sizes of every rank's u
+        my_cols = torch.tensor([blocks[rank].shape[1] if rank in blocks else n_rows],
+                               dtype=torch.int64, device=dev)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(sizes, my_cols)
+        else:
+            sizes = [my_cols]
+        sizes = [int(s.item()) for s in sizes]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        self.n_loc = n_rows
+        # merge the blocks side by side: COO with global columns -> CSR
+        rows, cols, vals = [], [], []
+        for r, b in blocks.items():
+            rows.append(b.rows())
+            cols.append(b.indices + int(offs[r]))
+            vals.append(b.data)
+        from ._dev import coo_to_csr
+        M = coo_to_csr((n_rows, int(offs[-1])), torch.cat(rows), torch.cat(cols).to(torch.int32),
+                       torch.cat(vals), prune=False)
+        owner = torch.cat([torch.full((sizes[r],), r, dtype=torch.int32, device=dev)
+                           for r in range(world)])
+        if world > 1:
+            self.dist = parallel.DistCsr(owner, M.indptr, M.indices, M.data, parallel._cuda_spmv)
+            self._local = parallel._local_devcsr(self.dist)
+        else:
+            self.dist = None
+            self._local = M
+        self._global = M
+        self._solver = None
+
+    def matvec(self, du):
+        x = _dev_vec(du)
+        if self.dist is None:
+            return self._global.matvec(x)
+        return self.dist.matvec(x)
+
+    def approx_solve(self, df):
+        """block-Jacobi: apply the inverse (or a V-cycle) of the local diagonal block"""
+        from . import precond, amg
+        if self._solver is None:
+            if precond.direct_feasible(self._local):
+                lu = precond.BandLU(self._local)
+                self._solver = lu.solve
+            else:
+                M = amg.AmgPreconditioner(self._local, theta=0.25, nu=2)
+
+                def vcycle(b):
+                    z = torch.empty_like(b)
+                    M.apply(b, z)
+                    return z
+                self._solver = vcycle
+        return self._solver(_dev_vec(df))
+
+
+# ----------- iterative linear solver ------------ #
+def _norm2(q):
+    q = _dev_vec(q)
+    s = (q * q).sum().reshape(1)
+    parallel.allreduce_sum(s)
+    return float(torch.sqrt(s).item())
+
+
+def _dot(p, q):
+    p, q = _dev_vec(p), _dev_vec(q)
+    s = (p * q).sum().reshape(1)
+    parallel.allreduce_sum(s)
+    return float(s.item())
+
+
+def _lgmres(A, b, x0=None, tol=1e-5, maxiter=1000, M=None, callback=None,
+            inner_m=30, outer_k=3, outer_v=None, store_outer_Av=True):
+    """Solve A x = b for row-sharded operators given as callables on local
+    vectors (reference admpisolve.py:190-453).  Returns (x, info): info 0 on
+    convergence, `maxiter` otherwise."""
+    if not callable(A):
+        raise ValueError('A must be a callable computing the local part of A x')
+    b = _dev_vec(b)
+    x0 = None if x0 is None else _dev_vec(x0)
+
+    def matvec(x, y):
+        y.copy_(_dev_vec(A(x)))
+
+    pre = None
+    if M is not None:
+        def pre(r, z):
+            z.copy_(_dev_vec(M(r)))
+
+    def allreduce(ctx, buf, count, stream):
+        parallel.allreduce_sum(linsolve._tensor_from_ptr(buf, count))
+        return 0
+
+    bn = _norm2(b)
+    x, info = linsolve.fgmres(None, b, x0=x0, precond=pre, matvec=matvec, rtol=tol, atol=tol,
+                              restart=inner_m, maxiter=maxiter,
+                              allreduce=allreduce if _world() > 1 else None)
+    if linsolve._cb_error:
+        e = linsolve._cb_error.pop()
+        linsolve._cb_error.clear()
+        raise e
+    if _rank() == 0 and callback is not None:
+        callback(x)
+    return x, (0 if info['status'] == 0 else maxiter)
+
+
+# ----------- nonlinear solver ------------ #
+def solve_mpi(func, u0, args=(), kargs={}, max_iter=10, abs_tol=1E-6, rel_tol=1E-6,
+              verbose=True):
+    """stub in the reference as well (admpisolve.py:457-459)"""
+    pass

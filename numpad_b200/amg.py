@@ -96,7 +96,7 @@ class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=600, max_levels=24):
+                 coarse_max=600, max_levels=24, agg_passes=1):
         A = A.materialized()
         self.mats, self.keep = [], []
         levels = []
@@ -114,6 +114,20 @@ class Hierarchy:
                 agg, n_agg = aggregate(cur, 0.0)
             if n_agg >= 0.9 * n or n_agg == 0:
                 break
+            for _ in range(1, agg_passes):
+                # aggregate the aggregates (distance-2 style, ~3x3 cells in 2-D):
+                # graph of aggregates = rows/cols relabelled by aggregate id,
+                # |entries| summed -- one sort
+                if n_agg <= coarse_max:
+                    break
+                rows = agg[cur.rows().long()]
+                cols = agg[cur.indices.long()]
+                Gagg = coo_to_csr((n_agg, n_agg), rows.contiguous(), cols.contiguous(),
+                                  cur.data.abs(), prune=False)
+                agg2, n2 = aggregate(Gagg, 0.0)
+                if n2 == 0 or n2 >= 0.9 * n_agg:
+                    break
+                agg, n_agg = agg2[agg.long()].contiguous(), n2
             T = sel_jac(agg, n_agg, full=True, monotone=False)
             if smooth:
                 # P = (I - omega D_F^-1 A_F) T with the strength-filtered A_F
@@ -216,8 +230,8 @@ def _submatrix(J, rows, colmap, ncols):
 class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
-    def __init__(self, J, cycles_a=2, cycles_l=3, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
-                 reuse=None, a_gmres=0):
+    def __init__(self, J, cycles_a=1, cycles_l=4, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
+                 reuse=None, a_gmres=0, agg_passes=1):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -249,7 +263,7 @@ class LscPreconditioner:
             self.Lm, self.amg_l = reuse.Lm, reuse.amg_l
         else:
             self.Lm = _csr_times_csr(self.D, self.G).scaled(-1.0).materialized()
-            self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l)
+            self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l, agg_passes=agg_passes)
         # momentum block: aggregation on the strength graph, prolongator smoothed
         # with the strength-filtered operator (keeps the two velocity components
         # apart, operator complexity ~2.5 instead of ~4)
@@ -261,7 +275,8 @@ class LscPreconditioner:
             wb = _lib.lib().cdll.npb_fgmres_workspace_bytes(nv, int(a_gmres), 0)
             self.a_work = _empty(wb, torch.uint8)
         else:
-            self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a)
+            self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a,
+                                   agg_passes=agg_passes)
             self.a_dinv = self.amg_a.levels[0]['dinv']
         self.a_gmres = int(a_gmres)
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]

@@ -157,7 +157,8 @@ def solve(A, b, transpose=False, **opts):
     pc = None if M is None else (M if hasattr(M, 'c_apply') else M.apply)
     # a multigrid-preconditioned solve that has not converged within two restart
     # cycles will not: fail fast and let the robust retry below take over
-    maxit = min(o['maxiter'], 2 * o['restart']) if first_try else o['maxiter']
+    maxit = min(o['maxiter'], 2 * o['restart']) if first_try else \
+        (max(o['maxiter'], 2000) if method == 'fgmres+lsc-robust' else o['maxiter'])
     x, res = fgmres(A, b, precond=pc, rtol=o['rtol'],
                     atol=o['atol'], restart=min(o['restart'], n), maxiter=maxit)
     res['method'] = method

@@ -287,3 +287,32 @@ def test_kec_jacobian_vs_oracle(npd, orc, tag, Ni, Nj):
     # v = 0 in the base flow makes a handful of entries exact cancellations
     assert_csr_parity(rg.diff(ug), Jo, rtol=1e-12, what=tag, noise=1e-15)
     assert (Jo.diagonal() != 0).all()           # full diagonal
+
+
+def test_admpi_single_rank(npd):
+    """admpi / admpisolve surface on one rank (the multi-rank run is
+    tools/admpi_check.py under torchrun): diff_mpi == diff, MpiJacobian.matvec,
+    block-Jacobi approx_solve and _lgmres with the reference's signature"""
+    import torch
+    from numpad_b200.admpi import COMM_WORLD, diff_mpi, diff_mpi_dev
+    from numpad_b200.admpisolve import MpiJacobian, _lgmres, _dot, _norm2
+    assert COMM_WORLD.Get_size() == 1 and COMM_WORLD.Get_rank() == 0
+    N = 300
+    u = npd.array(np.random.RandomState(0).random(N))
+    w = npd.hstack([0, u, 0])
+    f = (w[2:] + w[:-2] - 2 * w[1:-1]) * 4.0 - npd.exp(u)
+    d = diff_mpi(f, u, 'tangent')
+    assert sorted(d) == [0]
+    assert_csr_parity(d[0], f.diff(u, 'tangent'), rtol=0.0)
+    with pytest.raises(NotImplementedError):
+        diff_mpi(f, u, 'adjoint')
+    J = MpiJacobian(diff_mpi_dev(f, u, 'tangent'), 'CSR')
+    x = torch.randn(N, dtype=torch.float64, device='cuda')
+    Jh = d[0]
+    np.testing.assert_allclose(J.matvec(x).cpu().numpy(), Jh @ x.cpu().numpy(), rtol=1e-12)
+    b = J.matvec(x)
+    np.testing.assert_allclose(J.approx_solve(b).cpu().numpy(), x.cpu().numpy(), atol=1e-9)
+    sol, info = _lgmres(J.matvec, b, tol=1e-12, M=J.approx_solve)
+    assert info == 0
+    np.testing.assert_allclose(sol.cpu().numpy(), x.cpu().numpy(), atol=1e-9)
+    assert abs(_dot(x, x) - float(x @ x)) < 1e-9 and abs(_norm2(x) - float(x.norm())) < 1e-10
