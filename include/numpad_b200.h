@@ -149,11 +149,11 @@ int npb_sel_to_csr_numeric(int64_t nrows, const int32_t* map, const double* w,
                            const int32_t* indptr_out, int32_t* indices_out,
                            double* out, void* stream);
 int64_t npb_coo_to_csr_workspace(int64_t nrows, int64_t nnz);   /* bytes */
-int npb_coo_to_csr_symbolic(int64_t nrows, int64_t nnz, const int32_t* rows,
+int npb_coo_to_csr_symbolic(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t* rows,
                             const int32_t* cols, const double* vals, int prune,
                             void* ws, int64_t ws_bytes, int32_t* indptr_out,
                             int64_t* stats, void* stream);
-int npb_coo_to_csr_numeric(int64_t nrows, int64_t nnz, void* ws,
+int npb_coo_to_csr_numeric(int64_t nrows, int64_t ncols, int64_t nnz, void* ws,
                            int32_t* indices_out, double* data_out, void* stream);
 int npb_csr_expand_rows(int64_t nrows, const int32_t* indptr, int32_t* rows,
                         void* stream);

@@ -321,17 +321,17 @@ def tocsr(jac):
 # kernels behind the products / sums
 # --------------------------------------------------------------------------- #
 def coo_to_csr(shape, rows, cols, vals, prune):
-    nrows, nnz_in = int(shape[0]), int(rows.numel())
+    nrows, ncols, nnz_in = int(shape[0]), int(shape[1]), int(rows.numel())
     L = _lib.lib()
     ws_bytes = L.cdll.npb_coo_to_csr_workspace(nrows, nnz_in)
     ws = _empty(ws_bytes, torch.uint8)
     ptr = _empty(nrows + 1, torch.int32)
     stats = _empty(2, torch.int64)
-    _lib.lib().call('npb_coo_to_csr_symbolic', nrows, nnz_in, rows, cols, vals,
+    _lib.lib().call('npb_coo_to_csr_symbolic', nrows, ncols, nnz_in, rows, cols, vals,
                     1 if prune else 0, ws, ws_bytes, ptr, stats, stream_ptr())
     nnz, max_row = _read_stats(stats)
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
-    _call('npb_coo_to_csr_numeric', nrows, nnz_in, ws, idx, dat)
+    _call('npb_coo_to_csr_numeric', nrows, ncols, nnz_in, ws, idx, dat)
     return DevCsr(shape, ptr, idx, dat, (), nnz, max_row, clean=bool(prune))
 
 

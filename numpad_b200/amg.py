@@ -231,7 +231,7 @@ class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
     def __init__(self, J, cycles_a=1, cycles_l=4, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
-                 reuse=None, a_gmres=0, agg_passes=1):
+                 reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -276,7 +276,7 @@ class LscPreconditioner:
             self.a_work = _empty(wb, torch.uint8)
         else:
             self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a,
-                                   agg_passes=agg_passes)
+                                   agg_passes=agg_passes if agg_passes_a is None else agg_passes_a)
             self.a_dinv = self.amg_a.levels[0]['dinv']
         self.a_gmres = int(a_gmres)
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]

@@ -14,20 +14,23 @@ namespace {
 
 constexpr int TPB = 256;
 
+// key = row << col_bits | col with col_bits = bits needed for the largest
+// column seen by the caller: the radix sort then runs over row_bits + col_bits
+// instead of 64 bits (one 8-bit pass less for every 8 bits saved)
 __global__ void __launch_bounds__(TPB)
 k_make_keys(int64_t nnz, const int32_t* __restrict__ rows,
-            const int32_t* __restrict__ cols, uint64_t* __restrict__ keys) {
+            const int32_t* __restrict__ cols, int col_bits, uint64_t* __restrict__ keys) {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (k < nnz)
-        keys[k] = ((uint64_t)(uint32_t)rows[k] << 32) | (uint32_t)cols[k];
+        keys[k] = ((uint64_t)(uint32_t)rows[k] << col_bits) | (uint32_t)cols[k];
 }
 
 // heads of equal-key runs sum their run (in input order, like coo_tocsr),
 // decide whether the entry survives and count it for its row
 __global__ void __launch_bounds__(TPB)
 k_reduce_runs(int64_t nnz, const uint64_t* __restrict__ keys,
-              double* __restrict__ vals, int prune, int32_t* __restrict__ flag,
-              int32_t* __restrict__ row_cnt) {
+              double* __restrict__ vals, int prune, int col_bits,
+              int32_t* __restrict__ flag, int32_t* __restrict__ row_cnt) {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (k >= nnz) return;
     const uint64_t key = keys[k];
@@ -38,7 +41,7 @@ k_reduce_runs(int64_t nnz, const uint64_t* __restrict__ keys,
             s = __dadd_rn(s, vals[t]);
         vals[k] = s;
         f = (!prune || s != 0.0);
-        if (f) atomicAdd(row_cnt + (int32_t)(key >> 32), 1);
+        if (f) atomicAdd(row_cnt + (int32_t)(key >> col_bits), 1);
     }
     flag[k] = f;
 }
@@ -46,12 +49,12 @@ k_reduce_runs(int64_t nnz, const uint64_t* __restrict__ keys,
 __global__ void __launch_bounds__(TPB)
 k_compact(int64_t nnz, const uint64_t* __restrict__ keys,
           const double* __restrict__ vals, const int32_t* __restrict__ flag,
-          const int32_t* __restrict__ pos, int32_t* __restrict__ oidx,
+          const int32_t* __restrict__ pos, int col_bits, int32_t* __restrict__ oidx,
           double* __restrict__ out) {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (k >= nnz || !flag[k]) return;
     const int32_t o = pos[k];
-    oidx[o] = (int32_t)(uint32_t)(keys[k] & 0xffffffffu);
+    oidx[o] = (int32_t)(keys[k] & ((1ull << col_bits) - 1ull));
     out[o] = vals[k];
 }
 
@@ -105,10 +108,17 @@ int64_t npb_coo_to_csr_workspace(int64_t nrows, int64_t nnz) {
 
 // Phase 1: sort + reduce inside the workspace; indptr_out[nrows+1] is final,
 // stats[0] = nnz of the result, stats[1] = longest row.
-int npb_coo_to_csr_symbolic(int64_t nrows, int64_t nnz, const int32_t* rows,
+static int bits_for(int64_t n) {
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+int npb_coo_to_csr_symbolic(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t* rows,
                             const int32_t* cols, const double* vals, int prune,
                             void* ws, int64_t ws_bytes, int32_t* indptr_out,
                             int64_t* stats, void* stream) {
+    const int col_bits = bits_for(ncols);
     Layout L = make_layout(nrows, nnz);
     if ((int64_t)L.total > ws_bytes) {
         npb_set_error("coo_to_csr: workspace %lld < %lld", (long long)ws_bytes,
@@ -128,15 +138,14 @@ int npb_coo_to_csr_symbolic(int64_t nrows, int64_t nnz, const int32_t* rows,
     NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), st));
     NPB_CUDA(cudaMemsetAsync(row_cnt, 0, 4 * ((size_t)nrows + 1), st));
     if (nnz > 0) {
-        k_make_keys<<<npb_blocks(nnz, TPB), TPB, 0, st>>>(nnz, rows, cols, keys_in);
+        k_make_keys<<<npb_blocks(nnz, TPB), TPB, 0, st>>>(nnz, rows, cols, col_bits, keys_in);
         NPB_COUNT_LAUNCH();
-        int row_bits = 1;
-        while (row_bits < 32 && ((int64_t)1 << row_bits) < nrows) ++row_bits;
+        const int row_bits = bits_for(nrows);
         size_t cb = L.cub_bytes;
         NPB_CUDA(cub::DeviceRadixSort::SortPairs(base + L.cub, cb, keys_in, keys_out,
-                                                 vals, svals, nnz, 0, 32 + row_bits, st));
+                                                 vals, svals, nnz, 0, col_bits + row_bits, st));
         NPB_COUNT_LAUNCH();
-        k_reduce_runs<<<npb_blocks(nnz, TPB), TPB, 0, st>>>(nnz, keys_out, svals, prune, flag, row_cnt);
+        k_reduce_runs<<<npb_blocks(nnz, TPB), TPB, 0, st>>>(nnz, keys_out, svals, prune, col_bits, flag, row_cnt);
         NPB_COUNT_LAUNCH();
         NPB_CHECK_LAUNCH("coo_reduce_runs");
         int rc = npb_scan_launch(flag, pos, nnz, scan_ws, stats, st);
@@ -154,14 +163,14 @@ int npb_coo_to_csr_symbolic(int64_t nrows, int64_t nnz, const int32_t* rows,
 }
 
 // Phase 2: compact the surviving entries into the caller's arrays.
-int npb_coo_to_csr_numeric(int64_t nrows, int64_t nnz, void* ws,
+int npb_coo_to_csr_numeric(int64_t nrows, int64_t ncols, int64_t nnz, void* ws,
                            int32_t* indices_out, double* data_out, void* stream) {
     if (nnz <= 0) return NPB_OK;
     Layout L = make_layout(nrows, nnz);
     char* base = (char*)ws;
     k_compact<<<npb_blocks(nnz, TPB), TPB, 0, ST(stream)>>>(
         nnz, (const uint64_t*)(base + L.keys_out), (const double*)(base + L.vals),
-        (const int32_t*)(base + L.flag), (const int32_t*)(base + L.pos),
+        (const int32_t*)(base + L.flag), (const int32_t*)(base + L.pos), bits_for(ncols),
         indices_out, data_out);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("coo_compact");

@@ -9,9 +9,10 @@
 // row-sharded multi-GPU case (matvec = halo exchange + local SpMV, allreduce =
 // NCCL) and any preconditioner written on top of the C-ABI.
 //
-// Per inner iteration: 1 preconditioner apply, 1 matvec, CGS2 = 2 multi-dots
-// + 2 multi-axpys (the second also yields ||w||), 1 scale; ONE device->host
-// copy of the (j+2)-entry Hessenberg column, Givens on the host.
+// Per inner iteration: 1 preconditioner apply, 1 matvec, classical Gram-Schmidt
+// = 1 multi-dot (which also yields ||w||^2) + 1 multi-axpy (which also yields
+// ||w'||^2), a second pass only when the DGKS test asks for it, 1 scale; ONE
+// device->host copy of the Hessenberg column, Givens on the host.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -131,7 +132,7 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
         return 0;
     };
     int rc = 0, status = NPB_ERR_NOCONV;
-    int iters = 0, restarts = 0;
+    int iters = 0, restarts = 0, reorth = 0;
     double bnorm = 0, rnorm = 0, rnorm0 = 0;
 #define GM_TRY(expr) do { rc = (expr); if (rc) goto done; } while (0)
 
@@ -158,20 +159,33 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
                 double* zj = flexible ? Z + (size_t)j * ld : Z;
                 if (ops->precond) GM_TRY(ops->precond(ops->precond_ctx, vj, zj, stream));
                 else zj = vj;
-                GM_TRY(ops->matvec(ops->matvec_ctx, zj, w, stream));
-                // CGS2: h1 = V^T w; w -= V h1; h2 = V^T w; w -= V h2 (+ ||w||^2)
-                GM_TRY(npb_dot_multi_launch(n, j + 1, V, ld, w, d_h1, scratch, st));
-                GM_TRY(allreduce(d_h1, j + 1));
-                GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h1, -1.0, w, d_h2 + m + 1, scratch, st));
-                GM_TRY(npb_dot_multi_launch(n, j + 1, V, ld, w, d_h2, scratch, st));
-                GM_TRY(allreduce(d_h2, j + 1));
-                GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h2, -1.0, w, d_h2 + m + 1, scratch, st));
+                // w lives in the slot of the next basis vector
+                double* wj = V + (size_t)(j + 1) * ld;
+                GM_TRY(ops->matvec(ops->matvec_ctx, zj, wj, stream));
+                // classical Gram-Schmidt with DGKS re-orthogonalisation on demand:
+                // h1 = V^T w and ||w||^2 in ONE multi-dot (w is vector j+1 of the
+                // same array), w -= V h1 (+ ||w'||^2), host round trip; a second
+                // pass only if ||w'|| < ||w|| / sqrt(2)
+                GM_TRY(npb_dot_multi_launch(n, j + 2, V, ld, wj, d_h1, scratch, st));
+                GM_TRY(allreduce(d_h1, j + 2));
+                GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h1, -1.0, wj, d_h2 + m + 1, scratch, st));
                 GM_TRY(allreduce(d_h2 + m + 1, 1));
-                // one host round trip: both coefficient sets + the norm
                 GM_TRY(fetch(hcol.data(), dsmall, 2 * (m + 8)));
-                double hn = sqrt(hcol[(m + 8) + m + 1]);
                 double* Hj = &H[(size_t)j * (m + 1)];
-                for (int i = 0; i <= j; ++i) Hj[i] = hcol[i] + hcol[(m + 8) + i];
+                for (int i = 0; i <= j; ++i) Hj[i] = hcol[i];
+                const double w2_before = hcol[j + 1];
+                double w2_after = hcol[(m + 8) + m + 1];
+                if (w2_after < 0.5 * w2_before) {
+                    GM_TRY(npb_dot_multi_launch(n, j + 1, V, ld, wj, d_h2, scratch, st));
+                    GM_TRY(allreduce(d_h2, j + 1));
+                    GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h2, -1.0, wj, d_h2 + m + 1, scratch, st));
+                    GM_TRY(allreduce(d_h2 + m + 1, 1));
+                    GM_TRY(fetch(hcol.data(), dsmall, 2 * (m + 8)));
+                    for (int i = 0; i <= j; ++i) Hj[i] += hcol[(m + 8) + i];
+                    w2_after = hcol[(m + 8) + m + 1];
+                    ++reorth;
+                }
+                double hn = sqrt(w2_after > 0.0 ? w2_after : 0.0);
                 Hj[j + 1] = hn;
                 // Givens
                 for (int i = 0; i < j; ++i) {
@@ -187,7 +201,7 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
                 g[j] = cs[j] * g[j];
                 if (fabs(g[j + 1]) <= tol) { inner_conv = true; ++j; ++iters; break; }
                 if (hn <= 1e-300) { inner_conv = true; ++j; ++iters; break; }   // lucky breakdown
-                GM_TRY(npb_axpby_launch(n, 1.0 / hn, w, 0.0, V + (size_t)(j + 1) * ld, st));
+                GM_TRY(npb_axpby_launch(n, 1.0 / hn, wj, 0.0, wj, st));   // in-place scale
             }
         cycle_end:
             (void)inner_conv;
@@ -223,7 +237,7 @@ done:
     if (info) {
         info->iters = iters; info->restarts = restarts;
         info->status = rc ? rc : status;
-        info->pad = 0;
+        info->pad = reorth;      // number of re-orthogonalisation passes
         info->bnorm = bnorm; info->rnorm0 = rnorm0; info->rnorm = rnorm;
     }
     return rc ? rc : status;

@@ -345,7 +345,7 @@ k_axpy_multi(int64_t n, int k, const double* __restrict__ V, int64_t ld,
 
 // y = a*x + b*y   (b == 0 never reads y)
 __global__ void __launch_bounds__(TPB)
-k_axpby(int64_t n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+k_axpby(int64_t n, double a, const double* x, double b, double* y) {     // x may alias y
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * TPB)
         y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
