@@ -123,7 +123,9 @@ def workload_config(grid, n, gpus):
                         'one full Newton iteration per step' % (grid, n),
             'grid': grid, 'unknowns': n, 'linear_rtol': None,
             'l2_policy': 'inputs larger than L2 (Jacobian alone > 126 MB)',
-            'parallelism': 'replicas x%d' % gpus if gpus > 1 else 'single GPU'}
+            'parallelism': ('%d independent replicas of the single-GPU problem, one per GPU, no '
+                            'data-path collective (row-sharding of the saddle-point solve: '
+                            'DESIGN.md section 7)' % gpus) if gpus > 1 else 'single GPU'}
 
 
 # --------------------------------------------------------------------------- #
@@ -278,6 +280,13 @@ def run_ours(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = spmv_bytes / (ms_spmv * 1e-3) / 1e9
+    # DRAM traffic of this kernel from the committed `ncu --set full` capture
+    # (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(str(args.grid))
+    except Exception:
+        pass
     value = world * args.steps / (ms * 1e-3)
     e2e = world * args.steps / (ms_e2e * 1e-3)
     if rank == 0:
@@ -292,10 +301,10 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'Newton iters/sec', 'h2d_bytes_per_step': 16 * n,
                     'd2h_bytes_per_step': 8 * n, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_spmv_stream (CSR SpMV of the Jacobian)',
+            'roofline': {'bound': 'hbm', 'kernel': 'k_spmv_stream_v4<256> (CSR SpMV of the Jacobian; 36 % of the device time of a step, profiles/)',
                          'achieved': achieved, 'peak': peak,
                          'peak_source': 'measured' if peaks else 'fallback',
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'bytes_per_launch': spmv_bytes, 'us_per_launch': 1e3 * ms_spmv,
                          'frac_of_nominal_8TBs': achieved / 8000.0},
             'phases': phases, 'clocks': clocks,

@@ -281,6 +281,14 @@ int npb_csr_filter_symbolic(int64_t nrows, const int32_t* indptr, const int32_t*
 int npb_csr_filter_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
                            const double* data, double theta, const int32_t* indptr_out,
                            int32_t* indices_out, double* out, void* stream);
+/* prolongator truncation: keep |p| >= theta * row max, rescale to the row sum */
+int npb_csr_truncate_symbolic(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                              const double* data, double theta, int32_t* counts,
+                              int32_t* indptr_out, int64_t* scan_ws, int64_t* stats,
+                              void* stream);
+int npb_csr_truncate_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                             const double* data, double theta, const int32_t* indptr_out,
+                             int32_t* indices_out, double* out, void* stream);
 int npb_amg_aggregate(int64_t n, const int32_t* indptr, const int32_t* indices,
                       const double* data, double theta, int max_rounds, int8_t* state,
                       int8_t* state2, int32_t* flag, int32_t* root_id, int32_t* agg,

@@ -92,11 +92,24 @@ def filtered(A, theta):
     return DevCsr(A.shape, ptr, idx, dat, (), nnz, A.max_row, False)
 
 
+def truncated(P, theta):
+    """P without its small entries (|p| < theta * row max), rows rescaled"""
+    m = P.shape[0]
+    cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_csr_truncate_symbolic', m, P.indptr, P.indices, P.data, float(theta), cnt, ptr,
+          _scan_ws(m), stats)
+    nnz = int(stats[0].item())
+    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    _call('npb_csr_truncate_numeric', m, P.indptr, P.indices, P.data, float(theta), ptr, idx, dat)
+    return DevCsr(P.shape, ptr, idx, dat, (), nnz, P.max_row, True)
+
+
 class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=600, max_levels=24, agg_passes=1):
+                 coarse_max=600, max_levels=24, agg_passes=1, p_trunc=0.0):
         A = A.materialized()
         self.mats, self.keep = [], []
         levels = []
@@ -136,6 +149,8 @@ class Hierarchy:
                 dFinv = torch.where(dF != 0, 1.0 / dF, torch.ones_like(dF))
                 AT = _csr_times_sel(AF, T)
                 P = _csr_plus_csr(T.todev(), _diag_times_csr(dia_jac(-omega_p * dFinv), AT))
+                if p_trunc > 0:
+                    P = truncated(P.materialized(), p_trunc)
                 R = P.transpose()
                 Ac = _csr_times_csr(R, _csr_times_csr(cur, P))
             else:
@@ -231,7 +246,7 @@ class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
     def __init__(self, J, cycles_a=1, cycles_l=4, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
-                 reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None):
+                 reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None, p_trunc=0.1):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -263,7 +278,8 @@ class LscPreconditioner:
             self.Lm, self.amg_l = reuse.Lm, reuse.amg_l
         else:
             self.Lm = _csr_times_csr(self.D, self.G).scaled(-1.0).materialized()
-            self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l, agg_passes=agg_passes)
+            self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l, agg_passes=agg_passes,
+                                   p_trunc=p_trunc)
         # momentum block: aggregation on the strength graph, prolongator smoothed
         # with the strength-filtered operator (keeps the two velocity components
         # apart, operator complexity ~2.5 instead of ~4)
@@ -276,7 +292,8 @@ class LscPreconditioner:
             self.a_work = _empty(wb, torch.uint8)
         else:
             self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a,
-                                   agg_passes=agg_passes if agg_passes_a is None else agg_passes_a)
+                                   agg_passes=agg_passes if agg_passes_a is None else agg_passes_a,
+                                   p_trunc=p_trunc)
             self.a_dinv = self.amg_a.levels[0]['dinv']
         self.a_gmres = int(a_gmres)
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]

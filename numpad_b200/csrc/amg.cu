@@ -168,6 +168,32 @@ k_filter(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restri
     else cnt[r] = c;
 }
 
+// Prolongator truncation: keep the entries of a row with |p| >= theta * max|p|
+// and rescale them so that the row sum is preserved (constants stay in the
+// range of P).  Limits the stencil growth of the Galerkin coarse operators.
+template <bool FILL>
+__global__ void __launch_bounds__(TPB)
+k_truncate_rows(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                const double* __restrict__ dat, double theta, int32_t* __restrict__ cnt,
+                const int32_t* __restrict__ optr, int32_t* __restrict__ oidx,
+                double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (r >= nrows) return;
+    double mx = 0.0, sum_all = 0.0, sum_kept = 0.0;
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) { mx = fmax(mx, fabs(dat[k])); sum_all += dat[k]; }
+    const double thr = theta * mx;
+    int32_t c = 0;
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k)
+        if (fabs(dat[k]) >= thr && dat[k] != 0.0) { ++c; sum_kept += dat[k]; }
+    if (!FILL) { cnt[r] = c; return; }
+    // rescale only when the kept part carries most of the row sum (P of an
+    // M-matrix-like operator is essentially non-negative)
+    const double scale = (fabs(sum_kept) >= 0.5 * fabs(sum_all) && sum_kept != 0.0) ? sum_all / sum_kept : 1.0;
+    int32_t o = optr[r];
+    for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k)
+        if (fabs(dat[k]) >= thr && dat[k] != 0.0) { oidx[o] = idx[k]; out[o] = dat[k] * scale; ++o; }
+}
+
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
@@ -637,6 +663,26 @@ int npb_csr_filter_numeric(int64_t nrows, const int32_t* indptr, const int32_t* 
     k_filter<true><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, theta, nullptr, indptr_out, indices_out, out);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_filter_fill");
+    return NPB_OK;
+}
+
+int npb_csr_truncate_symbolic(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                              const double* data, double theta, int32_t* counts,
+                              int32_t* indptr_out, int64_t* scan_ws, int64_t* stats, void* stream) {
+    NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), ST(stream)));
+    k_truncate_rows<false><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, theta, counts, nullptr, nullptr, nullptr);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_truncate_count");
+    return npb_scan_launch(counts, indptr_out, nrows, scan_ws, stats, ST(stream));
+}
+
+int npb_csr_truncate_numeric(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                             const double* data, double theta, const int32_t* indptr_out,
+                             int32_t* indices_out, double* out, void* stream) {
+    if (nrows <= 0) return NPB_OK;
+    k_truncate_rows<true><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, theta, nullptr, indptr_out, indices_out, out);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_truncate_fill");
     return NPB_OK;
 }
 

@@ -1,0 +1,26 @@
+"""The CPU arm of bench.py (`--impl reference`: the oracle timed on the host)
+prints one JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '0', '--sample-grid', '40', '--grid', '1024'],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+              'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config',
+              'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['dtype'] == 'f64' and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] == 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
+    assert 'workload' in d['config'] and d['value'] > 0
