@@ -542,8 +542,14 @@ struct npb_lsc {
     int64_t a_work_bytes;
 };
 
-struct diag_ctx { int64_t n; const double* d; };
+// y = d .* x as an npb_apply_fn (Jacobi preconditioner; ctx = npb_diag_ctx)
+struct npb_diag_ctx { int64_t n; const double* d; };
+typedef npb_diag_ctx diag_ctx;
+int npb_diag_apply_cb(void* ctx, const double* x, double* y, void* stream);
 static int diag_scale_cb(void* ctx, const double* x, double* y, void* stream) {
+    return npb_diag_apply_cb(ctx, x, y, stream);
+}
+int npb_diag_apply_cb(void* ctx, const double* x, double* y, void* stream) {
     const diag_ctx* c = (const diag_ctx*)ctx;
     if (c->n > 0) {
         k_diag_scale<<<npb_blocks(c->n, TPB), TPB, 0, ST(stream)>>>(c->n, c->d, x, y);

@@ -138,7 +138,7 @@ def solve(A, b, transpose=False, **opts):
     M, method = _pc.build(A, o['precond'])
     if method == 'fgmres+lsc' and _hints['robust']:
         M, method = _pc.build(A, 'lsc-robust')
-    first_try = method == 'fgmres+lsc'
+    first_try = method in ('fgmres+lsc', 'fgmres+amg')
     t_setup = _now() - t0
     if method == 'direct':
         x = M.solve(b)
@@ -181,6 +181,10 @@ def solve(A, b, transpose=False, **opts):
         # Newton sequence
         _hints['robust'] = True
         return solve(A, b, **dict(o, precond='lsc-robust'))
+    if res['status'] != 0 and method == 'fgmres+amg':
+        # multigrid on a non-elliptic (e.g. compressible-flow) Jacobian: fall back
+        # to the Jacobi-preconditioned Krylov solve
+        return solve(A, b, **dict(o, precond='jacobi', maxiter=max(o['maxiter'], 1000)))
     if res['status'] != 0 and method != 'direct' and _pc.direct_feasible(A):
         # robust fallback: pivoted banded LU (+ refinement through the front door)
         return solve(A, b, **dict(o, precond='direct'))

@@ -97,6 +97,25 @@ class BandLU:
         z.copy_(self.solve(r))
 
 
+class _DiagCtx(ctypes.Structure):
+    _fields_ = [('n', ctypes.c_int64), ('d', ctypes.c_void_p)]
+
+
+class JacobiPreconditioner:
+    """z = diag(A)^-1 r as a C callback: the last resort that cannot diverge"""
+
+    def __init__(self, A):
+        from . import amg
+        d = amg.diagonal(A)
+        self.dinv = torch.where(d != 0, 1.0 / d, torch.ones_like(d))
+        self.ctx = _DiagCtx(A.shape[0], self.dinv.data_ptr())
+        self.c_apply = ctypes.cast(_lib.lib().cdll.npb_diag_apply_cb, ctypes.c_void_p).value
+        self.c_ctx = ctypes.addressof(self.ctx)
+
+    def describe(self):
+        return 'Jacobi'
+
+
 def direct_feasible(A):
     if A.shape[0] > 200000:
         return False
@@ -128,4 +147,6 @@ def build(A, kind='auto'):
     if kind == 'amg':
         from . import amg
         return amg.AmgPreconditioner(A, theta=0.25, nu=2), 'fgmres+amg'
+    if kind == 'jacobi':
+        return JacobiPreconditioner(A), 'fgmres+jacobi'
     raise ValueError('unknown preconditioner %r' % kind)
