@@ -305,6 +305,8 @@ int npb_cg_dir(int64_t n, const double* rz_new, const double* rz_old, int first,
                const double* z, double* p, void* stream);
 int npb_cg_update(int64_t n, const double* rz, const double* pq, const double* p,
                   const double* q, double* x, double* r, int first, void* stream);
+typedef struct npb_diag_ctx { int64_t n; const double* d; } npb_diag_ctx;   /* [host] */
+int npb_diag_apply_cb(void* ctx, const double* x, double* y, void* stream);  /* y = d .* x */
 int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream);
 int npb_amg_apply_cb(void* ctx, const double* x, double* y, void* stream);
 int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream);
