@@ -166,12 +166,20 @@ int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr,
              double* y, void* stream);                       /* y = A x     */
 int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      const int32_t* indices, const double* data, const double* x,
-                     double* y, int variant /* 1 stream, 2 vector, 3 stream+cp.async */,
+                     double* y, int variant /* 1 stream, 2 vector, 3 stream+cp.async,
+                     4 stream+128-bit loads, 5 persistent TMA pipeline */,
                      void* stream);
+int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA kernel; returns old */
 int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
                       const int32_t* indices, const double* data,
                       const double* x, const double* b, double* y,
                       void* stream);                         /* y = b - A x */
+/* y = epilogue(A x), kernel variant forced (0 = auto).  mode 0: y = Ax, 1: y = b - Ax,
+ * 2: y = b + Ax, 3: y = x + omega * dinv .* (b - Ax) (damped-Jacobi sweep, y != x) */
+int npb_spmv_epilogue(int64_t nrows, int64_t nnz, const int32_t* indptr,
+                      const int32_t* indices, const double* data, const double* x,
+                      int mode, const double* b, const double* dinv, double omega,
+                      double* y, int variant, void* stream);
 int64_t npb_reduce_scratch_bytes(void);   /* zero-initialised by the caller */
 int npb_dot_multi(int64_t n, int k, const double* V, int64_t ld,
                   const double* w, double* out, void* scratch, void* stream);

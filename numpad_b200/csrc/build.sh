@@ -9,7 +9,7 @@ mkdir -p build
 OBJS=""
 for f in $SRCS; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ scan.cuh -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ scan.cuh -nt "$o" ] || [ spmv_tma.cuh -nt "$o" ]; then
     echo "nvcc $f"
     $NVCC $FLAGS -c "$f" -o "$o" 2> build/${f%.cu}.ptxas.log || { cat build/${f%.cu}.ptxas.log; exit 1; }
   fi

@@ -219,6 +219,8 @@ k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
     if (row < nr && sub == 0) y[r0 + row] = spmv_finish(epi, r0 + row, acc, x);
 }
 
+#include "spmv_tma.cuh"
+
 // (b) "vector" kernel for long rows: G lanes cooperate on one row.
 template <int G>
 __global__ void __launch_bounds__(TPB)
@@ -361,6 +363,9 @@ int grid_for(int64_t n) {
 
 #define ST(s) ((cudaStream_t)(s))
 
+// 1: the auto dispatch prefers the TMA pipeline kernel (npb_spmv_set_default_tma)
+static int npb_spmv_default_tma = 1;
+
 // ------------------------------------------------------------- internal API
 // y = epilogue(A x); see spmv_epi.  `variant`: 0 auto, 1 stream, 2 vector, 3 stream + cp.async
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
@@ -370,7 +375,12 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
     spmv_epi e{mode, b, dinv, omega};
     const double mean = (double)nnz / (double)nrows;
     const bool aligned = (((uintptr_t)idx | (uintptr_t)dat) & 15) == 0;
-    if ((variant == 4 || (variant == 0 && nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)) && aligned) {
+    const bool tma_ok = aligned && nnz < (int64_t)0x7fffffff - 2 * TM_CAP;
+    if (tma_ok && (variant == 5 || (variant == 0 && npb_spmv_default_tma && mean <= 96.0 &&
+                                    nrows >= (int64_t)tma_rows_for(mean) * NPB_NUM_SMS * TM_CTAS_PER_SM * 2))) {
+        int rc = spmv_tma_dispatch(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        if (rc) return rc;
+    } else if ((variant == 4 || (variant == 0 && nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)) && aligned) {
         k_spmv_stream_v4<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
     } else if (variant == 3 && aligned) {
         k_spmv_stream_async<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
@@ -452,10 +462,31 @@ int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* i
     return npb_spmv_launch(nrows, nnz, indptr, indices, data, x, nullptr, y, 0, ST(stream));
 }
 
-// same, forcing a kernel variant (1 = stream, 2 = vector); for tests / tuning
+// tuning switch: 0 = the auto dispatch never picks the TMA pipeline kernel
+int npb_spmv_set_default_tma(int on) {
+    const int old = npb_spmv_default_tma;
+    npb_spmv_default_tma = on ? 1 : 0;
+    return old;
+}
+
+// same, forcing a kernel variant (1 = stream, 2 = vector, 3 = stream + cp.async,
+// 4 = stream + 128-bit loads, 5 = persistent TMA pipeline); for tests / tuning
 int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                      const double* data, const double* x, double* y, int variant, void* stream) {
     return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, 0, nullptr, nullptr, 0.0, y, variant,
+                       ST(stream));
+}
+
+// y = epilogue(A x) with a forced kernel variant (0 = auto):
+//   mode 0: y = Ax   1: y = b - Ax   2: y = b + Ax   3: y = x + omega dinv.(b - Ax)  (y != x)
+int npb_spmv_epilogue(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                      const double* data, const double* x, int mode, const double* b,
+                      const double* dinv, double omega, double* y, int variant, void* stream) {
+    if (mode < 0 || mode > 3 || (mode >= 1 && !b) || (mode == 3 && (!dinv || x == y))) {
+        npb_set_error("spmv_epilogue: bad mode / operands");
+        return NPB_ERR_ARG;
+    }
+    return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, mode, b, dinv, omega, y, variant,
                        ST(stream));
 }
 

@@ -264,8 +264,49 @@ def test_spmv_variants_agree(dev, shape, density):
     x = rng.standard_normal(shape[1])
     xd = torch.from_numpy(x).to(dev.device())
     want = a @ x
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 3, 4, 5):
         y = torch.full((shape[0],), np.nan, dtype=torch.float64, device=dev.device())
         dev._call('npb_spmv_variant', shape[0], A.nnz, A.indptr, A.indices, A.data, xd, y, variant)
         np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-13,
                                    atol=1e-13 * (np.abs(want).max() if a.nnz else 1))
+
+
+@pytest.mark.parametrize('nrows,ncols,per_row', [(1, 1, 1), (255, 255, 3), (70001, 70001, 9),
+                                                 (300000, 280000, 5), (20011, 9000, 40),
+                                                 (5003, 5003, 130), (40, 100000, 9000)])
+def test_spmv_tma_pipeline(dev, nrows, ncols, per_row):
+    """persistent TMA-pipelined SpMV (variant 5) with every epilogue vs numpy: ragged rows,
+    empty rows, units shorter and longer than a pipeline stage, array tails that are not a
+    multiple of 16 bytes"""
+    import torch
+    rng = np.random.RandomState(nrows % 1000 + per_row)
+    lens = rng.poisson(per_row, nrows).clip(0, ncols)
+    lens[rng.random(nrows) < 0.05] = 0
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nnz = int(ptr[-1])
+    idx = np.empty(nnz, np.int32)
+    for r in range(nrows) if nrows < 6000 else ():
+        idx[ptr[r]:ptr[r + 1]] = np.sort(rng.choice(ncols, lens[r], replace=False))
+    if nrows >= 6000:        # banded columns around the diagonal, sorted, distinct
+        base = (np.arange(nrows) * (ncols / nrows)).astype(np.int64)
+        rows = np.repeat(np.arange(nrows), lens)
+        off = np.arange(nnz) - ptr[rows]
+        idx[:] = np.clip(base[rows] - lens[rows] // 2, 0, ncols - lens[rows]) + off
+    a = sp.csr_matrix((rng.standard_normal(nnz), idx, ptr), shape=(nrows, ncols))
+    x = rng.standard_normal(max(ncols, nrows))[:ncols]
+    b = rng.standard_normal(nrows)
+    dinv = rng.standard_normal(nrows)
+    ax = a @ x
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev.device())
+    ptr_d, idx_d, dat_d = t(ptr), t(idx), t(a.data)
+    xd, bd, dd = t(x), t(b), t(dinv)
+    scale = np.abs(a).dot(np.abs(x)).max() + np.abs(b).max() if nnz else 1.0
+    for mode in (0, 1, 2, 3):
+        if mode == 3 and nrows != ncols:
+            continue
+        want = [ax, b - ax, b + ax, (x[:nrows] + 0.7 * dinv * (b - ax)) if nrows == ncols else None][mode]
+        y = torch.full((nrows,), np.nan, dtype=torch.float64, device=dev.device())
+        dev._call('npb_spmv_epilogue', nrows, nnz, ptr_d, idx_d, dat_d, xd, mode, bd, dd, 0.7, y, 5)
+        got = y.cpu().numpy()
+        tol = 1e-13 * scale * (1 + np.abs(dinv).max() if mode == 3 else 1)
+        np.testing.assert_allclose(got, want, rtol=0, atol=tol)
