@@ -169,6 +169,7 @@ int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      double* y, int variant /* 1 stream, 2 vector, 3 stream+cp.async,
                      4 stream+128-bit loads, 5 persistent TMA pipeline */,
                      void* stream);
+int npb_spmv_set_tma_geometry(int g);   /* tuning: shared-memory ring geometry -1 (auto) or 0..3; returns old */
 int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA kernel; returns old */
 int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
                       const int32_t* indices, const double* data,

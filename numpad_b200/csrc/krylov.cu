@@ -375,9 +375,9 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
     spmv_epi e{mode, b, dinv, omega};
     const double mean = (double)nnz / (double)nrows;
     const bool aligned = (((uintptr_t)idx | (uintptr_t)dat) & 15) == 0;
-    const bool tma_ok = aligned && nnz < (int64_t)0x7fffffff - 2 * TM_CAP;
+    const bool tma_ok = aligned && nnz < (int64_t)0x7fffffff - 2 * TM_CAP_MAX;
     if (tma_ok && (variant == 5 || (variant == 0 && npb_spmv_default_tma && mean <= 96.0 &&
-                                    nrows >= (int64_t)tma_rows_for(mean) * NPB_NUM_SMS * TM_CTAS_PER_SM * 2))) {
+                                    nrows >= tma_min_rows(mean)))) {
         int rc = spmv_tma_dispatch(nrows, nnz, ptr, idx, dat, x, e, y, st);
         if (rc) return rc;
     } else if ((variant == 4 || (variant == 0 && nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)) && aligned) {
@@ -414,10 +414,6 @@ static inline double* red_partial(void* scratch) { return (double*)scratch; }
 static inline unsigned int* red_ticket(void* scratch) {
     return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC);
 }
-
-int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
-                const double* dat, const double* x, int mode, const double* b,
-                const double* dinv, double omega, double* y, int variant, cudaStream_t st);
 
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st) {
@@ -466,6 +462,14 @@ int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* i
 int npb_spmv_set_default_tma(int on) {
     const int old = npb_spmv_default_tma;
     npb_spmv_default_tma = on ? 1 : 0;
+    return old;
+}
+
+// tuning switch: ring geometry of the TMA kernel (-1: by row length (default); 0: 3072 x 3
+// stages, 2 CTAs/SM; 1: 2304 x 3, 2; 2: 2304 x 2, 3; 3: 1536 x 3, 4); returns the old one
+int npb_spmv_set_tma_geometry(int g) {
+    const int old = npb_tma_geometry;
+    if (g >= -1 && g <= 3) npb_tma_geometry = g;
     return old;
 }
 

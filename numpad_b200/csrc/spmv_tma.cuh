@@ -17,17 +17,24 @@
 // Algorithmic bytes per call: 12*nnz + 4*(nrows+1) + 16*nrows.
 #pragma once
 
-constexpr int TM_CAP = 3072;                 // entries per stage (36 KB)
-constexpr int TM_STAGES = 3;
 constexpr int TM_CONSUMERS = 256;
 constexpr int TM_THREADS = TM_CONSUMERS + 32;
-constexpr int TM_CTAS_PER_SM = 2;
+constexpr int TM_CAP_MAX = 3072;
 
+// ring geometry: entries per stage, stages, resident CTAs per SM.  Shared memory the
+// ring does not take stays L1 for the gathers of x, so the ring is no larger than the
+// bandwidth-delay product needs.
+template <int CAP_, int STAGES_, int CTAS_>
+struct tm_geom {
+    static constexpr int CAP = CAP_, STAGES = STAGES_, CTAS = CTAS_;
+};
+
+template <class G>
 struct tm_smem {
-    alignas(128) double val[TM_STAGES][TM_CAP];
-    alignas(128) int32_t idx[TM_STAGES][TM_CAP];
-    alignas(8) unsigned long long full[TM_STAGES];
-    unsigned long long empty[TM_STAGES];
+    alignas(128) double val[G::STAGES][G::CAP];
+    alignas(128) int32_t idx[G::STAGES][G::CAP];
+    alignas(8) unsigned long long full[G::STAGES];
+    unsigned long long empty[G::STAGES];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -63,16 +70,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-template <int ROWS, int RPT>
-__global__ void __launch_bounds__(TM_THREADS, TM_CTAS_PER_SM)
+template <int ROWS, int RPT, class G>
+__global__ void __launch_bounds__(TM_THREADS, G::CTAS)
 k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict__ ptr,
            const int32_t* __restrict__ idx, const double* __restrict__ dat,
            const double* x, spmv_epi epi, double* y) {
     constexpr int TPR = TM_CONSUMERS / ROWS;
     constexpr int UROWS = ROWS * RPT;            // rows per unit
+    constexpr int GB = 12 / RPT;                 // gathers in flight per row and batch
     static_assert(RPT == 1 || TPR == 1, "several rows per thread only with one thread per row");
+    constexpr int TM_CAP = G::CAP, TM_STAGES = G::STAGES;
     extern __shared__ __align__(128) unsigned char tm_raw[];
-    tm_smem& S = *reinterpret_cast<tm_smem*>(
+    tm_smem<G>& S = *reinterpret_cast<tm_smem<G>*>(
         (reinterpret_cast<uintptr_t>(tm_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -191,23 +200,38 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
             mbar_wait(&S.full[stage], phase);
             const int32_t* si = &S.idx[stage][0];
             const double* sv = &S.val[stage][0];
+            // gathers of all RPT rows are issued GB at a time before any of them is
+            // used: one memory latency per batch instead of one per row / per 4 entries
+            int32_t kk[RPT], ee[RPT];
+            bool more = false;
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
-                const int32_t e = min(re[j], hi) - lo;
-                int32_t k = max(rs[j], lo) - lo + sub;
-                double a_ = acc[j];
-                for (; k + 3 * TPR < e; k += 4 * TPR) {
-                    const double x0 = __ldg(x + si[k]);
-                    const double x1 = __ldg(x + si[k + TPR]);
-                    const double x2 = __ldg(x + si[k + 2 * TPR]);
-                    const double x3 = __ldg(x + si[k + 3 * TPR]);
-                    a_ = fma(sv[k], x0, a_);
-                    a_ = fma(sv[k + TPR], x1, a_);
-                    a_ = fma(sv[k + 2 * TPR], x2, a_);
-                    a_ = fma(sv[k + 3 * TPR], x3, a_);
+                ee[j] = min(re[j], hi) - lo;
+                kk[j] = max(rs[j], lo) - lo + sub;
+                more |= kk[j] < ee[j];
+            }
+            while (more) {
+                double xv[RPT][GB];
+#pragma unroll
+                for (int j = 0; j < RPT; ++j)
+#pragma unroll
+                    for (int g = 0; g < GB; ++g) {
+                        const int32_t k = kk[j] + g * TPR;
+                        xv[j][g] = (k < ee[j]) ? __ldg(x + si[k]) : 0.0;
+                    }
+                more = false;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    double a_ = acc[j];
+#pragma unroll
+                    for (int g = 0; g < GB; ++g) {
+                        const int32_t k = kk[j] + g * TPR;
+                        if (k < ee[j]) a_ = fma(sv[k], xv[j][g], a_);
+                    }
+                    acc[j] = a_;
+                    kk[j] += GB * TPR;
+                    more |= kk[j] < ee[j];
                 }
-                for (; k < e; k += TPR) a_ = fma(sv[k], __ldg(x + si[k]), a_);
-                acc[j] = a_;
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&S.empty[stage]);
@@ -244,47 +268,75 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
 // unit shape for a mean row length: ROWS rows are summed side by side (TPR = 256 / ROWS
 // threads each), RPT such groups make a unit; picked so that a mean unit fills most of a stage
 struct tma_shape { int rows, rpt; };
-static inline tma_shape tma_shape_for(double mean) {
-    if (mean <= 2.9) return {256, 4};
-    if (mean <= 5.8) return {256, 2};
-    if (mean <= 11.5) return {256, 1};
-    if (mean <= 23.0) return {128, 1};
-    if (mean <= 46.0) return {64, 1};
+static inline tma_shape tma_shape_for(double mean, int cap) {
+    const double f = cap / 3072.0;
+    if (mean <= 2.9 * f) return {256, 4};
+    if (mean <= 5.8 * f) return {256, 2};
+    if (mean <= 11.5 * f) return {256, 1};
+    if (mean <= 23.0 * f) return {128, 1};
+    if (mean <= 46.0 * f) return {64, 1};
     return {32, 1};
 }
-static inline int tma_rows_for(double mean) {
-    const tma_shape s = tma_shape_for(mean);
-    return s.rows * s.rpt;
+
+// ring geometry: -1 = by mean row length (measured on the operators of a 2048^2 cavity
+// step, tools/spmv_bench.py: very short and long rows run best on 3 CTAs x 2 stages x
+// 2304 entries -- more consumer warps and more L1 for the gathers -- the 5..20 entry
+// stencil rows on 2 CTAs x 3 stages x 3072), 0..3 = forced (tuning)
+static int npb_tma_geometry = -1;
+static inline int tma_geometry_for(double mean) {
+    if (npb_tma_geometry >= 0) return npb_tma_geometry;
+    return (mean <= 4.5 || mean >= 20.0) ? 2 : 0;
+}
+static inline int tma_cap(int g) { return g == 0 ? 3072 : (g == 3 ? 1536 : 2304); }
+static inline int tma_ctas(int g) { return g == 2 ? 3 : (g == 3 ? 4 : 2); }
+// rows below which the persistent grid cannot be filled twice over
+static inline int64_t tma_min_rows(double mean) {
+    const int g = tma_geometry_for(mean);
+    const tma_shape s = tma_shape_for(mean, tma_cap(g));
+    return (int64_t)s.rows * s.rpt * NPB_NUM_SMS * tma_ctas(g) * 2;
 }
 
-template <int ROWS, int RPT>
+template <int ROWS, int RPT, class G>
 static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                            const double* dat, const double* x, const spmv_epi& e, double* y,
                            cudaStream_t st) {
     static bool configured = false;
-    const size_t sh = sizeof(tm_smem) + 128;
+    const size_t sh = sizeof(tm_smem<G>) + 128;
     if (!configured) {
-        NPB_CUDA(cudaFuncSetAttribute(k_spmv_tma<ROWS, RPT>,
+        NPB_CUDA(cudaFuncSetAttribute(k_spmv_tma<ROWS, RPT, G>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         configured = true;
     }
     const int64_t nunits = (nrows + ROWS * RPT - 1) / (ROWS * RPT);
-    const int64_t cap = (int64_t)NPB_NUM_SMS * TM_CTAS_PER_SM;
+    const int64_t cap = (int64_t)NPB_NUM_SMS * G::CTAS;
     const int grid = (int)(nunits < cap ? nunits : cap);
-    k_spmv_tma<ROWS, RPT><<<grid, TM_THREADS, sh, st>>>(nrows, nnz, nunits, ptr, idx, dat, x, e, y);
+    k_spmv_tma<ROWS, RPT, G><<<grid, TM_THREADS, sh, st>>>(nrows, nnz, nunits, ptr, idx, dat, x, e, y);
     return NPB_OK;
+}
+
+template <class G>
+static int spmv_tma_dispatch_g(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                               const double* dat, const double* x, const spmv_epi& e, double* y,
+                               cudaStream_t st) {
+    const tma_shape s = tma_shape_for((double)nnz / (double)nrows, G::CAP);
+    if (s.rpt == 4) return launch_spmv_tma<256, 4, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+    if (s.rpt == 2) return launch_spmv_tma<256, 2, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+    switch (s.rows) {
+        case 256: return launch_spmv_tma<256, 1, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 128: return launch_spmv_tma<128, 1, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 64: return launch_spmv_tma<64, 1, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        default: return launch_spmv_tma<32, 1, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+    }
 }
 
 static int spmv_tma_dispatch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                              const double* dat, const double* x, const spmv_epi& e, double* y,
                              cudaStream_t st) {
-    const tma_shape s = tma_shape_for((double)nnz / (double)nrows);
-    if (s.rpt == 4) return launch_spmv_tma<256, 4>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-    if (s.rpt == 2) return launch_spmv_tma<256, 2>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-    switch (s.rows) {
-        case 256: return launch_spmv_tma<256, 1>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        case 128: return launch_spmv_tma<128, 1>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        case 64: return launch_spmv_tma<64, 1>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        default: return launch_spmv_tma<32, 1>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+    switch (tma_geometry_for((double)nnz / (double)nrows)) {
+        case 1: return spmv_tma_dispatch_g<tm_geom<2304, 3, 2>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 2: return spmv_tma_dispatch_g<tm_geom<2304, 2, 3>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 3: return spmv_tma_dispatch_g<tm_geom<1536, 3, 4>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        default: return spmv_tma_dispatch_g<tm_geom<3072, 3, 2>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
     }
 }
+

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--grid', type=int, default=1024)
 ap.add_argument('--variants', default='0,1,4,5')
 ap.add_argument('--levels', type=int, default=3)
+ap.add_argument('--geoms', default='')
 a = ap.parse_args()
 P = CavityProblem(npd, a.grid); u0 = P.fixed_state()
 u = npd.array(u0.copy()); res = P.residual(u, npd.array(u0), 1.0, 0)
@@ -28,7 +29,8 @@ for name, h in (('A', M.amg_a), ('L', M.amg_l)):
             ops.append(('%s.P%d' % (name, l), lev['P']))
             ops.append(('%s.R%d' % (name, l), lev['R']))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-variants = [int(v) for v in a.variants.split(',')]
+variants = [int(v) for v in a.variants.split(',')] + [50 + int(g) for g in a.geoms.split(',') if g]
+from numpad_b200 import _lib
 peak = 6545.9
 print('%-8s %10s %11s %6s | %s' % ('op', 'rows', 'nnz', 'nnz/r', '  '.join('v%d us  GB/s frac' % v for v in variants)))
 for name, A in ops:
@@ -39,12 +41,15 @@ for name, A in ops:
     out = []
     ref = None
     for v in variants:
+        if v >= 50:
+            _lib.lib().cdll.npb_spmv_set_tma_geometry(v - 50); v = 5
+        run = lambda v=v: _dev._call('npb_spmv_variant', m, A.nnz, A.indptr, A.indices, A.data, x, y, v)
         for _ in range(3):
-            _dev._call('npb_spmv_variant', m, A.nnz, A.indptr, A.indices, A.data, x, y, v)
+            run()
         torch.cuda.synchronize(); e0.record()
         reps = 30
         for _ in range(reps):
-            _dev._call('npb_spmv_variant', m, A.nnz, A.indptr, A.indices, A.data, x, y, v)
+            run()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         if ref is None:
