@@ -303,6 +303,14 @@ int npb_amg_aggregate(int64_t n, const int32_t* indptr, const int32_t* indices,
                       int8_t* state2, int32_t* flag, int32_t* root_id, int32_t* agg,
                       int32_t* undecided, int64_t* scan_ws, int64_t* stats,
                       void* stream);
+/* distance-2 MIS aggregation (aggregates of ~7 nodes on a 5-point stencil): keys = 2 n
+ * uint64 scratch, state / near int8[n], label / label2 / flag / agg int32[n],
+ * root_id int32[n + 1], undecided device int32; stats[0] = number of aggregates */
+int npb_amg_aggregate_mis2(int64_t n, const int32_t* indptr, const int32_t* indices,
+                           const double* data, double theta, int max_rounds, int8_t* state,
+                           int8_t* near, uint64_t* keys, int32_t* label, int32_t* label2,
+                           int32_t* flag, int32_t* root_id, int32_t* agg, int32_t* undecided,
+                           int64_t* scan_ws, int64_t* stats, void* stream);
 int npb_dense_inverse(int n, const int32_t* indptr, const int32_t* indices,
                       const double* data, double* W, double* Minv, int32_t* info,
                       void* stream);

@@ -66,9 +66,23 @@ def diagonal(A):
     return d
 
 
-def aggregate(A, theta, max_rounds=12):
-    """-> (agg int32[n], n_agg)"""
+def aggregate(A, theta, max_rounds=12, kind='mis1'):
+    """-> (agg int32[n], n_agg).  kind 'mis1': roots = maximal independent set of the
+    strength graph (aggregates of ~2.75 nodes on a 5-point stencil); 'mis2': distance-2
+    independent set (~7 nodes)"""
     n = A.shape[0]
+    if kind == 'mis2':
+        state, near = _empty(n, torch.int8), _empty(n, torch.int8)
+        keys = _empty(2 * n, torch.int64)
+        label, label2, flag = (_empty(n, torch.int32) for _ in range(3))
+        root_id, agg = _empty(n + 1, torch.int32), _empty(n, torch.int32)
+        und = _empty(2, torch.int32)
+        stats = _empty(2, torch.int64)
+        _call('npb_amg_aggregate_mis2', n, A.indptr, A.indices, A.data, float(theta),
+              int(max(max_rounds, 40)), state, near, keys, label, label2, flag, root_id, agg, und,
+              _scan_ws(n), stats)
+        n_agg, _ = _read_stats(stats)
+        return agg, n_agg
     state, state2 = _empty(n, torch.int8), _empty(n, torch.int8)
     flag, root_id, agg = _empty(n, torch.int32), _empty(n + 1, torch.int32), _empty(n, torch.int32)
     und = _empty(2, torch.int32)
@@ -109,11 +123,12 @@ class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=600, max_levels=24, agg_passes=1, p_trunc=0.0):
+                 coarse_max=600, max_levels=24, agg_passes=1, p_trunc=0.0, agg='mis1'):
         A = A.materialized()
         self.mats, self.keep = [], []
         levels = []
         cur = A
+        agg_kind = agg
         while True:
             n = cur.shape[0]
             d = diagonal(cur)
@@ -122,9 +137,9 @@ class Hierarchy:
             levels.append(lev)
             if n <= coarse_max or len(levels) >= max_levels:
                 break
-            agg, n_agg = aggregate(cur, theta)
+            agg, n_agg = aggregate(cur, theta, kind=agg_kind)
             if n_agg > 0.6 * n and theta > 0:      # filtered graph too sparse down here
-                agg, n_agg = aggregate(cur, 0.0)
+                agg, n_agg = aggregate(cur, 0.0, kind=agg_kind)
             if n_agg >= 0.9 * n or n_agg == 0:
                 break
             for _ in range(1, agg_passes):
@@ -137,7 +152,7 @@ class Hierarchy:
                 cols = agg[cur.indices.long()]
                 Gagg = coo_to_csr((n_agg, n_agg), rows.contiguous(), cols.contiguous(),
                                   cur.data.abs(), prune=False)
-                agg2, n2 = aggregate(Gagg, 0.0)
+                agg2, n2 = aggregate(Gagg, 0.0, kind='mis1')
                 if n2 == 0 or n2 >= 0.9 * n_agg:
                     break
                 agg, n_agg = agg2[agg.long()].contiguous(), n2
@@ -245,8 +260,9 @@ def _submatrix(J, rows, colmap, ncols):
 class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
-    def __init__(self, J, cycles_a=1, cycles_l=4, theta_a=0.25, nu_a=2, nu_l=1, smooth_a=True,
-                 reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None, p_trunc=0.1):
+    def __init__(self, J, cycles_a=1, cycles_l=4, theta_a=0.25, nu_a=4, nu_l=1, smooth_a=True,
+                 reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None, p_trunc=0.1,
+                 agg_l='mis1', agg_a='mis2'):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -279,10 +295,12 @@ class LscPreconditioner:
         else:
             self.Lm = _csr_times_csr(self.D, self.G).scaled(-1.0).materialized()
             self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l, agg_passes=agg_passes,
-                                   p_trunc=p_trunc)
-        # momentum block: aggregation on the strength graph, prolongator smoothed
-        # with the strength-filtered operator (keeps the two velocity components
-        # apart, operator complexity ~2.5 instead of ~4)
+                                   p_trunc=p_trunc, agg=agg_l)
+        # momentum block: distance-2 aggregation on the strength graph, prolongator
+        # smoothed with the strength-filtered operator (keeps the two velocity
+        # components apart); operator complexity 1.4 (2.97 with distance-1 aggregates:
+        # their 32-entry coarse rows made this hierarchy 60 % of the setup time) paid
+        # for with 4 Jacobi sweeps instead of 2 -- same outer iteration count at 2048^2
         if a_gmres > 0:
             # robust mode: no multigrid for the momentum block (see csrc/amg.cu)
             self.amg_a = None
@@ -293,7 +311,7 @@ class LscPreconditioner:
         else:
             self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a,
                                    agg_passes=agg_passes if agg_passes_a is None else agg_passes_a,
-                                   p_trunc=p_trunc)
+                                   p_trunc=p_trunc, agg=agg_a)
             self.a_dinv = self.amg_a.levels[0]['dinv']
         self.a_gmres = int(a_gmres)
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]

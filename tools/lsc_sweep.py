@@ -14,11 +14,15 @@ J = npd.diff_dev(res, u).materialized(); b = res._dev.reshape(-1).contiguous()
 for cfg in a.configs.split(';'):
     vals = cfg.split(',')
     ptr_ = float(vals[6]) if len(vals) > 6 else 0.0
+    agl = vals[7] if len(vals) > 7 else 'mis1'
+    aga = vals[8] if len(vals) > 8 else 'mis1'
+    nua = int(vals[9]) if len(vals) > 9 else 2
     ca, cl, nul, sm, ap_, apa = ([int(v) for v in vals[:6]] + [1, 1])[:6]
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    M = amg.LscPreconditioner(J, cycles_a=ca, cycles_l=cl, nu_l=nul, smooth_a=bool(sm), agg_passes=ap_, agg_passes_a=apa, p_trunc=ptr_)
+    M = amg.LscPreconditioner(J, cycles_a=ca, cycles_l=cl, nu_l=nul, smooth_a=bool(sm), agg_passes=ap_, agg_passes_a=apa, p_trunc=ptr_, agg_l=agl, agg_a=aga, nu_a=nua)
     torch.cuda.synchronize(); t1 = time.perf_counter()
     x, info = linsolve.fgmres(J, b, precond=M, rtol=1e-10, restart=60, maxiter=600)
     torch.cuda.synchronize(); t2 = time.perf_counter()
+    print('agg %s/%s nu_a=%d ' % (agl, aga, nua), end='')
     print('grid %d cycles_a=%d pcg_l=%d nu_l=%d smooth_a=%d passes(L,A)=%d,%d trunc=%.2f: its %d status %d setup %.0f ms krylov %.0f ms | %s'
           % (a.grid, ca, cl, nul, sm, ap_, apa, ptr_, info['iters'], info['status'], 1e3*(t1-t0), 1e3*(t2-t1), M.describe()), flush=True)

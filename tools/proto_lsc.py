@@ -122,11 +122,12 @@ def truncate(P, theta):
 
 class Hier:
     def __init__(self, A, theta=0.0, nu=1, omega=0.67, omega_p=0.67, coarse_max=600, agg='mis1',
-                 p_trunc=0.1, smoother='jacobi', seed=0, cheb_deg=2, filt=True):
+                 p_trunc=0.1, smoother='jacobi', seed=0, cheb_deg=2, filt=True, gal='full', omega_c=None, max_levels=20, coarse_sweeps=None):
         rng = np.random.RandomState(seed)
         self.levels = []
         cur = A.tocsr()
         self.nu, self.omega, self.smoother, self.cheb_deg = nu, omega, smoother, cheb_deg
+        self.coarse_sweeps = coarse_sweeps
         while True:
             n = cur.shape[0]
             d = cur.diagonal()
@@ -141,7 +142,7 @@ class Hier:
                     v /= lam
                 lev['lam'] = 1.1 * lam
             self.levels.append(lev)
-            if n <= coarse_max or len(self.levels) > 20:
+            if n <= coarse_max or len(self.levels) >= max_levels:
                 break
             ag, na = aggregate(cur, theta, agg, rng)
             if na > 0.6 * n and theta > 0:
@@ -157,7 +158,12 @@ class Hier:
                 P = truncate(P, p_trunc)
             lev['P'] = P.tocsr()
             lev['R'] = P.T.tocsr()
-            cur = (lev['R'] @ cur @ P).tocsr()
+            if gal == 'filtered' and theta > 0:
+                cur = (lev['R'] @ AF @ P).tocsr()
+            elif gal == 'postfilter' and theta > 0:
+                cur = filtered((lev['R'] @ cur @ P).tocsr(), theta)
+            else:
+                cur = (lev['R'] @ cur @ P).tocsr()
         self.cinv = None
         if self.levels[-1]['A'].shape[0] <= 2500:
             try:
@@ -201,7 +207,7 @@ class Hier:
         if l == len(self.levels) - 1:
             if self.cinv is not None:
                 return self.cinv @ b
-            return self.smooth(l, b, None, 2 * self.nu + 6)
+            return self.smooth(l, b, None, self.coarse_sweeps or (2 * self.nu + 6))
         x = self.smooth(l, b, None, self.nu)
         r = b - mv(L['A'], x)
         bc = mv(L['R'], r)
@@ -293,6 +299,17 @@ VARIANTS = {
     'exactAL': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2), -1, -1),
     'base_a2': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2), 4, 2),
     'base_c2_a2': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2), 2, 2),
+    'galF': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, gal='filtered'), 4, 1),
+    'galP': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, gal='postfilter'), 4, 1),
+    'galF_mis2L': (dict(theta=0.0, nu=1, agg='mis2'), dict(theta=0.25, nu=2, gal='filtered'), 4, 1),
+    'galF_mis2': (dict(theta=0.0, nu=1, agg='mis2'), dict(theta=0.25, nu=2, gal='filtered', agg='mis2'), 4, 1),
+    'galF_mis2_nu3': (dict(theta=0.0, nu=1, agg='mis2'), dict(theta=0.25, nu=3, gal='filtered', agg='mis2'), 4, 1),
+    'A2lev': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=2), 4, 1),
+    'A3lev': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=3), 4, 1),
+    'A3lev_s4': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=3, coarse_sweeps=4), 4, 1),
+    'A4lev': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=4), 4, 1),
+    'A3lev_mis2': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=3, agg='mis2'), 4, 1),
+    'A2lev_mis2': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=2, agg='mis2'), 4, 1),
     'mis2_t0': (dict(theta=0.0, nu=1, agg='mis2', p_trunc=0.0), dict(theta=0.25, nu=2, agg='mis2', p_trunc=0.0), 4, 1),
 }
 
