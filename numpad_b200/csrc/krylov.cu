@@ -307,7 +307,11 @@ k_dot_multi(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
     }
 }
 
-// w -= sum_j h[j] V_j (j < k), and out_norm2 = ||w_new||^2
+// w += sum_j hs[j] V_j (j < k, hs = sign * h), and out_norm2 = ||w_new||^2.
+// Two elements per thread (128-bit loads) and four basis vectors per round: 8 x 16 B
+// in flight per thread -- the kernel streams (k + 2) vectors and has nothing to hide
+// the latency with but its own loads.  VEC = false: any alignment / odd n.
+template <bool VEC>
 __global__ void __launch_bounds__(TPB)
 k_axpy_multi(int64_t n, int k, const double* __restrict__ V, int64_t ld,
              const double* __restrict__ h, double sign, double* __restrict__ w,
@@ -318,7 +322,35 @@ k_axpy_multi(int64_t n, int k, const double* __restrict__ V, int64_t ld,
     for (int j = threadIdx.x; j < k; j += TPB) hs[j] = sign * h[j];
     __syncthreads();
     double nrm[1] = {0.0};
-    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
+    if (VEC) {
+        const int64_t n2 = n >> 1;
+        for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n2;
+             i += (int64_t)gridDim.x * TPB) {
+            double2 s0 = make_double2(0.0, 0.0), s1 = s0;
+            int j = 0;
+            for (; j + 3 < k; j += 4) {
+                const double2 a0 = reinterpret_cast<const double2*>(V + (int64_t)j * ld)[i];
+                const double2 a1 = reinterpret_cast<const double2*>(V + (int64_t)(j + 1) * ld)[i];
+                const double2 a2 = reinterpret_cast<const double2*>(V + (int64_t)(j + 2) * ld)[i];
+                const double2 a3 = reinterpret_cast<const double2*>(V + (int64_t)(j + 3) * ld)[i];
+                s0.x = fma(hs[j], a0.x, s0.x);         s0.y = fma(hs[j], a0.y, s0.y);
+                s1.x = fma(hs[j + 1], a1.x, s1.x);     s1.y = fma(hs[j + 1], a1.y, s1.y);
+                s0.x = fma(hs[j + 2], a2.x, s0.x);     s0.y = fma(hs[j + 2], a2.y, s0.y);
+                s1.x = fma(hs[j + 3], a3.x, s1.x);     s1.y = fma(hs[j + 3], a3.y, s1.y);
+            }
+            for (; j < k; ++j) {
+                const double2 a0 = reinterpret_cast<const double2*>(V + (int64_t)j * ld)[i];
+                s0.x = fma(hs[j], a0.x, s0.x);         s0.y = fma(hs[j], a0.y, s0.y);
+            }
+            double2 wi = reinterpret_cast<double2*>(w)[i];
+            wi.x += s0.x + s1.x;
+            wi.y += s0.y + s1.y;
+            reinterpret_cast<double2*>(w)[i] = wi;
+            nrm[0] = fma(wi.x, wi.x, fma(wi.y, wi.y, nrm[0]));
+        }
+    }
+    // scalar path: everything (VEC = false) or the odd last element
+    for (int64_t i = (VEC ? (n & ~(int64_t)1) : 0) + (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * TPB) {
         double s0 = 0.0, s1 = 0.0;
         int j = 0;
@@ -432,8 +464,13 @@ int npb_axpy_multi_launch(int64_t n, int k, const double* V, int64_t ld, const d
                           double sign, double* w, double* out_norm2, void* scratch,
                           cudaStream_t st) {
     size_t sh = sizeof(double) * ((size_t)k + TPB / 32);
-    k_axpy_multi<<<grid_for(n), TPB, sh, st>>>(n, k, V, ld, h, sign, w, red_partial(scratch),
-                                               red_ticket(scratch), out_norm2);
+    const bool vec = ((((uintptr_t)V | (uintptr_t)w) & 15) == 0) && (ld % 2 == 0 || k <= 1);
+    if (vec)
+        k_axpy_multi<true><<<grid_for((n + 1) / 2), TPB, sh, st>>>(n, k, V, ld, h, sign, w, red_partial(scratch),
+                                                                  red_ticket(scratch), out_norm2);
+    else
+        k_axpy_multi<false><<<grid_for(n), TPB, sh, st>>>(n, k, V, ld, h, sign, w, red_partial(scratch),
+                                                         red_ticket(scratch), out_norm2);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("axpy_multi");
     return NPB_OK;

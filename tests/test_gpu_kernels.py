@@ -310,3 +310,70 @@ def test_spmv_tma_pipeline(dev, nrows, ncols, per_row):
         got = y.cpu().numpy()
         tol = 1e-13 * scale * (1 + np.abs(dinv).max() if mode == 3 else 1)
         np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize('n,k', [(1, 1), (7, 3), (1000, 1), (4097, 5), (200001, 17), (300000, 40)])
+def test_multi_dot_and_axpy(dev, n, k):
+    """Gram-Schmidt building blocks of the FGMRES (csrc/krylov.cu): out = V^T w, and
+    w += sign * V h with ||w||^2, against numpy (odd lengths, k above and below the
+    16-vector pass, padded leading dimension)"""
+    import torch
+    from numpad_b200 import _lib
+    rng = np.random.RandomState(n % 97 + k)
+    ld = (n + 31) // 32 * 32
+    V = np.zeros((k, ld))
+    V[:, :n] = rng.standard_normal((k, n))
+    w = rng.standard_normal(n)
+    h = rng.standard_normal(k)
+    Vd = torch.from_numpy(V).to(dev.device())
+    wd = torch.from_numpy(w.copy()).to(dev.device())
+    hd = torch.from_numpy(h).to(dev.device())
+    scratch = torch.zeros(_lib.lib().cdll.npb_reduce_scratch_bytes(), dtype=torch.uint8,
+                          device=dev.device())
+    out = torch.zeros(k, dtype=torch.float64, device=dev.device())
+    dev._call('npb_dot_multi', n, k, Vd, ld, wd, out, scratch)
+    want = V[:, :n] @ w
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0,
+                               atol=1e-13 * np.abs(V[:, :n]).dot(np.abs(w)).max())
+    nrm = torch.zeros(1, dtype=torch.float64, device=dev.device())
+    dev._call('npb_axpy_multi', n, k, Vd, ld, hd, -1.0, wd, nrm, scratch)
+    w2 = w - h @ V[:, :n]
+    np.testing.assert_allclose(wd.cpu().numpy(), w2, rtol=0,
+                               atol=1e-13 * (np.abs(w) + np.abs(h) @ np.abs(V[:, :n])).max())
+    np.testing.assert_allclose(float(nrm.item()), w2 @ w2, rtol=1e-13)
+    # a view that starts on an odd element takes the scalar path
+    if n > 8:
+        w3 = torch.from_numpy(w.copy()).to(dev.device())
+        Vo = torch.from_numpy(np.ascontiguousarray(V[:, :])).to(dev.device())
+        dev._call('npb_axpy_multi', n - 1, k, Vo.reshape(-1)[1:], ld, hd, 1.0, w3[1:], nrm, scratch)
+        w4 = w[1:] + h @ V[:, 1:n]
+        np.testing.assert_allclose(w3[1:].cpu().numpy(), w4, rtol=0,
+                                   atol=1e-13 * (np.abs(w) .max() + (np.abs(h) @ np.abs(V[:, :n])).max()))
+
+
+@pytest.mark.parametrize('kind', ['mis1', 'mis2'])
+def test_aggregation_properties(dev, kind):
+    """MIS aggregation on a 2-D 5-point operator: every node gets an aggregate id in
+    range, ids are dense, aggregates are connected through strong edges to their root
+    within 1 (mis1) / 2 (mis2) steps, and MIS-2 aggregates are ~7 nodes, MIS-1 ~2.75"""
+    from numpad_b200 import amg
+    n1 = 96
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n1, n1))
+    a = sp.csr_matrix(sp.kron(sp.identity(n1), T) + sp.kron(T, sp.identity(n1)))
+    a.sort_indices()
+    A = dev.DevCsr.from_scipy(a)
+    agg, n_agg = amg.aggregate(A, 0.0, kind=kind)
+    g = agg.cpu().numpy()
+    n = a.shape[0]
+    assert g.min() == 0 and g.max() == n_agg - 1
+    sizes = np.bincount(g, minlength=n_agg)
+    assert sizes.min() >= 1
+    mean = n / n_agg
+    assert (2.2 < mean < 3.4) if kind == 'mis1' else (5.5 < mean < 9.5), mean
+    # connectivity: aggregate-local graph is connected (BFS inside each aggregate)
+    from scipy.sparse.csgraph import connected_components
+    coo = a.tocoo()
+    same = g[coo.row] == g[coo.col]
+    sub = sp.csr_matrix((np.ones(same.sum()), (coo.row[same], coo.col[same])), shape=a.shape)
+    ncomp, _ = connected_components(sub, directed=False)
+    assert ncomp == n_agg
