@@ -236,17 +236,32 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
  * Setup pieces (device): diagonal extraction, MIS aggregation, dense inverse
  * of the coarsest operator.  Solve phase: npb_amg_vcycle, and the two
  * npb_apply_fn callbacks usable as `precond` of npb_fgmres. */
+/* Halo of a row-sharded operator (multi-GPU, one process per GPU).  Local column numbering:
+ * [0, n_own) = columns this rank owns, n_own + q * maxb + k = k-th boundary value of rank q.
+ * Before the local SpMV every rank packs x[send_idx] into its slot of `recv` and one
+ * all-gather over the library's NCCL communicator fills the other slots. */
+typedef struct npb_halo {
+    const void* dist;               /* handle of npb_dist_init; NULL: not sharded */
+    int64_t n_own;
+    const int32_t* send_idx;        /* [n_send] local indices of the values to publish */
+    int32_t n_send, maxb;
+    double* recv;                   /* [world * maxb] */
+} npb_halo;
+
 typedef struct npb_csr_mat {
     int64_t nrows, ncols, nnz;
     const int32_t* indptr;
     const int32_t* indices;
     const double* data;
+    npb_halo halo;
 } npb_csr_mat;
 
 typedef struct npb_amg_level {      /* [host] */
     npb_csr_mat A, P, R;            /* operator, prolongation, restriction */
     const double* dinv;             /* 1 / diag(A) */
     double *x, *x2, *b, *r;         /* work vectors of the level's size */
+    int32_t gather, pad;            /* != 0: last row-sharded level; the levels below are  */
+    const int64_t* offsets;         /* replicated: [host] world + 1 slice bounds of their rhs */
 } npb_amg_level;
 
 typedef struct npb_amg {            /* [host] */
@@ -254,6 +269,7 @@ typedef struct npb_amg {            /* [host] */
     double omega;
     const double* coarse_inv;       /* dense inverse of the coarsest operator */
     npb_amg_level* levels;
+    const void* dist;               /* npb_dist_init handle when levels are row-sharded */
 } npb_amg;
 
 typedef struct npb_amg_precond {    /* [host] ctx of npb_amg_apply_cb */
@@ -280,6 +296,18 @@ typedef struct npb_lsc {            /* [host] ctx of npb_lsc_apply_cb */
     void* a_work;                   /* npb_fgmres_workspace_bytes(nv, a_gmres, 0) */
     int64_t a_work_bytes;
 } npb_lsc;
+
+/* ---- multi-GPU: the library's own NCCL communicator (row-sharded solve, SURVEY 8e;
+ * stands where the reference calls MPI in admpisolve.py:146-188).  nccl_path may be
+ * NULL / "" (the copy torch has loaded is found by soname). */
+int npb_dist_unique_id(const char* nccl_path, char* id128);        /* rank 0; host broadcasts */
+int npb_dist_init(const char* nccl_path, const char* id128, int rank, int world,
+                  void** handle);                                  /* collective */
+int npb_dist_free(void* handle);
+int npb_dist_rank(void* handle);
+int npb_dist_world(void* handle);
+int npb_dist_allreduce_cb(void* ctx, double* buf, int count, void* stream); /* npb_allreduce_fn */
+int npb_mat_matvec_cb(void* ctx, const double* x, double* y, void* stream); /* ctx = npb_csr_mat */
 
 int npb_csr_diagonal(int64_t nrows, const int32_t* indptr, const int32_t* indices,
                      const double* data, double* diag, void* stream);

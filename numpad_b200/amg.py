@@ -17,23 +17,30 @@ from ._dev import (DevCsr, sel_jac, dia_jac, device, stream_ptr, _empty, _call, 
                    _csr_plus_csr, _sel_times_csr, coo_to_csr)
 
 
+class Halo(ctypes.Structure):            # npb_halo: filled by shard.py for row-sharded operators
+    _fields_ = [('dist', ctypes.c_void_p), ('n_own', ctypes.c_int64),
+                ('send_idx', ctypes.c_void_p), ('n_send', ctypes.c_int32),
+                ('maxb', ctypes.c_int32), ('recv', ctypes.c_void_p)]
+
+
 class CsrMat(ctypes.Structure):
     _fields_ = [('nrows', ctypes.c_int64), ('ncols', ctypes.c_int64), ('nnz', ctypes.c_int64),
                 ('indptr', ctypes.c_void_p), ('indices', ctypes.c_void_p),
-                ('data', ctypes.c_void_p)]
+                ('data', ctypes.c_void_p), ('halo', Halo)]
 
 
 class AmgLevel(ctypes.Structure):
     _fields_ = [('A', CsrMat), ('P', CsrMat), ('R', CsrMat), ('dinv', ctypes.c_void_p),
                 ('x', ctypes.c_void_p), ('x2', ctypes.c_void_p), ('b', ctypes.c_void_p),
-                ('r', ctypes.c_void_p)]
+                ('r', ctypes.c_void_p), ('gather', ctypes.c_int32), ('pad', ctypes.c_int32),
+                ('offsets', ctypes.c_void_p)]
 
 
 class AmgStruct(ctypes.Structure):
     _fields_ = [('nlevels', ctypes.c_int32), ('nu_pre', ctypes.c_int32),
                 ('nu_post', ctypes.c_int32), ('coarse_n', ctypes.c_int32),
                 ('omega', ctypes.c_double), ('coarse_inv', ctypes.c_void_p),
-                ('levels', ctypes.POINTER(AmgLevel))]
+                ('levels', ctypes.POINTER(AmgLevel)), ('dist', ctypes.c_void_p)]
 
 
 class AmgPrecondStruct(ctypes.Structure):
@@ -66,7 +73,7 @@ def diagonal(A):
     return d
 
 
-def aggregate(A, theta, max_rounds=12, kind='mis1'):
+def aggregate(A, theta, max_rounds=12, kind='mis1', with_roots=False):
     """-> (agg int32[n], n_agg).  kind 'mis1': roots = maximal independent set of the
     strength graph (aggregates of ~2.75 nodes on a 5-point stencil); 'mis2': distance-2
     independent set (~7 nodes)"""
@@ -82,7 +89,7 @@ def aggregate(A, theta, max_rounds=12, kind='mis1'):
               int(max(max_rounds, 40)), state, near, keys, label, label2, flag, root_id, agg, und,
               _scan_ws(n), stats)
         n_agg, _ = _read_stats(stats)
-        return agg, n_agg
+        return (agg, n_agg, root_id) if with_roots else (agg, n_agg)
     state, state2 = _empty(n, torch.int8), _empty(n, torch.int8)
     flag, root_id, agg = _empty(n, torch.int32), _empty(n + 1, torch.int32), _empty(n, torch.int32)
     und = _empty(2, torch.int32)
@@ -90,7 +97,8 @@ def aggregate(A, theta, max_rounds=12, kind='mis1'):
     _call('npb_amg_aggregate', n, A.indptr, A.indices, A.data, float(theta), int(max_rounds),
           state, state2, flag, root_id, agg, und, _scan_ws(n), stats)
     n_agg, _ = _read_stats(stats)
-    return agg, n_agg
+    # root_id[i] = number of roots below node i: aggregate ids follow the order of their roots
+    return (agg, n_agg, root_id) if with_roots else (agg, n_agg)
 
 
 def filtered(A, theta):
@@ -137,9 +145,9 @@ class Hierarchy:
             levels.append(lev)
             if n <= coarse_max or len(levels) >= max_levels:
                 break
-            agg, n_agg = aggregate(cur, theta, kind=agg_kind)
+            agg, n_agg, root_id = aggregate(cur, theta, kind=agg_kind, with_roots=True)
             if n_agg > 0.6 * n and theta > 0:      # filtered graph too sparse down here
-                agg, n_agg = aggregate(cur, 0.0, kind=agg_kind)
+                agg, n_agg, root_id = aggregate(cur, 0.0, kind=agg_kind, with_roots=True)
             if n_agg >= 0.9 * n or n_agg == 0:
                 break
             for _ in range(1, agg_passes):
@@ -155,7 +163,8 @@ class Hierarchy:
                 agg2, n2 = aggregate(Gagg, 0.0, kind='mis1')
                 if n2 == 0 or n2 >= 0.9 * n_agg:
                     break
-                agg, n_agg = agg2[agg.long()].contiguous(), n2
+                agg, n_agg, root_id = agg2[agg.long()].contiguous(), n2, None
+            lev['root_id'] = root_id       # shard.py: coarse ownership follows the roots
             T = sel_jac(agg, n_agg, full=True, monotone=False)
             if smooth:
                 # P = (I - omega D_F^-1 A_F) T with the strength-filtered A_F

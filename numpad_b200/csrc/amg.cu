@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "dist.cuh"
 #include "scan.cuh"
 
 int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
@@ -25,7 +26,8 @@ int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_
 int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st);
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                 const double* dat, const double* x, int mode, const double* b,
-                const double* dinv, double omega, double* y, int variant, cudaStream_t st);
+                const double* dinv, double omega, double* y, int variant, cudaStream_t st,
+                const npb_halo* halo);
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st);
 
@@ -494,7 +496,21 @@ struct npb_csr_mat {
     const int32_t* indptr;
     const int32_t* indices;
     const double* data;
+    npb_halo halo;         // halo.dist != NULL: rows of a row-sharded operator (dist.cuh)
 };
+
+// y = epilogue(M x): 0: Mx  1: b - Mx  2: b + Mx  3: x + omega dinv (b - Mx); a sharded
+// operator first publishes / fetches the boundary values of x
+static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* b, double* y,
+                           int mode, cudaStream_t st, const double* dinv = nullptr,
+                           double omega = 0.0) {
+    if (M.halo.dist) {
+        int rc = npb_dist_halo_exchange(M.halo, x, st);
+        if (rc) return rc;
+    }
+    return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y, 0,
+                       st, &M.halo);
+}
 
 struct npb_amg_level {
     npb_csr_mat A;         // level operator
@@ -505,6 +521,11 @@ struct npb_amg_level {
     double* x2;
     double* b;
     double* r;
+    // multi-GPU: the last row-sharded level (gather != 0) hands its restricted residual
+    // to the replicated levels below: every rank computes its slice [offsets[rank],
+    // offsets[rank+1]) of the coarse right-hand side and the slices are all-gathered
+    int32_t gather, pad;
+    const int64_t* offsets;     // [host] world + 1 entries
 };
 
 struct npb_amg {
@@ -514,13 +535,13 @@ struct npb_amg {
     double omega;
     const double* coarse_inv;   // dense row-major inverse of the coarsest operator
     npb_amg_level* levels;      // [host] array of nlevels descriptors
+    const void* dist;           // npb_dist* when the fine levels are row-sharded, else NULL
 };
 
 static int jacobi_sweep(const npb_amg_level& L, double omega, const double* b, const double* xin,
                         double* xout, cudaStream_t st) {
     // xout = xin + omega dinv (b - A xin): the SpMV kernel with the Jacobi epilogue
-    return npb_spmv_ex(L.A.nrows, L.A.nnz, L.A.indptr, L.A.indices, L.A.data, xin, 3, b, L.dinv,
-                       omega, xout, 0, st);
+    return spmv_mat(L.A, xin, b, xout, 3, st, L.dinv, omega);
 }
 
 // x <- V-cycle(b) from a zero initial guess.  b and x have the fine size and
@@ -555,10 +576,17 @@ int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
             break;
         }
         // r = b - A x ; b_{l+1} = R r
-        int rc = npb_spmv_launch(n, L.A.nnz, L.A.indptr, L.A.indices, L.A.data, L.x, bl, L.r, 1, st);
+        int rc = spmv_mat(L.A, L.x, bl, L.r, 1, st);
         if (rc) return rc;
         npb_amg_level& C = h->levels[l + 1];
-        rc = npb_spmv_launch(L.R.nrows, L.R.nnz, L.R.indptr, L.R.indices, L.R.data, L.r, nullptr, C.b, 0, st);
+        if (L.gather) {
+            const npb_dist* d = (const npb_dist*)h->dist;
+            double* mine = C.b + L.offsets[d->rank];
+            rc = spmv_mat(L.R, L.r, nullptr, mine, 0, st);
+            if (!rc) rc = npb_dist_allgatherv(d, mine, C.b, L.offsets, st);
+        } else {
+            rc = spmv_mat(L.R, L.r, nullptr, C.b, 0, st);
+        }
         if (rc) return rc;
     }
     // upward
@@ -568,7 +596,7 @@ int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
         const int64_t n = L.A.nrows;
         const double* bl = (l == 0) ? b : L.b;
         // x += P x_{l+1}
-        int rc = npb_spmv_launch(n, L.P.nnz, L.P.indptr, L.P.indices, L.P.data, C.x, L.x, L.x, 2, st);
+        int rc = spmv_mat(L.P, C.x, L.x, L.x, 2, st);
         if (rc) return rc;
         double* cur = L.x;
         double* oth = L.x2;
@@ -593,7 +621,7 @@ static int amg_solve(const npb_amg* h, const npb_csr_mat& A, int k, const double
                      double* r, double* dx, cudaStream_t st) {
     int rc = npb_amg_vcycle(h, b, x, (void*)st);
     for (int it = 1; it < k && !rc; ++it) {
-        rc = npb_spmv_launch(A.nrows, A.nnz, A.indptr, A.indices, A.data, x, b, r, 1, st);
+        rc = spmv_mat(A, x, b, r, 1, st);
         if (!rc) rc = npb_amg_vcycle(h, r, dx, (void*)st);
         if (!rc) rc = npb_axpby_launch(A.nrows, 1.0, dx, 1.0, x, st);
     }
@@ -614,14 +642,21 @@ static int amg_pcg(const npb_amg* h, const npb_csr_mat& A, int k, const double* 
         double* rz_old = scal + ((i + 1) & 1);
         if ((rc = npb_amg_vcycle(h, r, z, (void*)st))) return rc;
         if ((rc = npb_dot_multi_launch(n, 1, r, n, z, rz_new, red, st))) return rc;
+        if ((rc = npb_dist_allreduce_sum((const npb_dist*)h->dist, rz_new, 1, st))) return rc;
         k_cg_dir<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, rz_old, i == 0, z, p);
         NPB_COUNT_LAUNCH();
-        if ((rc = npb_spmv_launch(n, A.nnz, A.indptr, A.indices, A.data, p, nullptr, q, 0, st))) return rc;
+        if ((rc = spmv_mat(A, p, nullptr, q, 0, st))) return rc;
         if ((rc = npb_dot_multi_launch(n, 1, p, n, q, scal + 2, red, st))) return rc;
+        if ((rc = npb_dist_allreduce_sum((const npb_dist*)h->dist, scal + 2, 1, st))) return rc;
         k_cg_update<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, scal + 2, p, q, x, r, i == 0);
         NPB_COUNT_LAUNCH();
     }
     return NPB_OK;
+}
+
+// y = M x as an npb_apply_fn; ctx = npb_csr_mat (row-sharded or not)
+int npb_mat_matvec_cb(void* ctx, const double* x, double* y, void* stream) {
+    return spmv_mat(*(const npb_csr_mat*)ctx, x, nullptr, y, 0, ST(stream));
 }
 
 // y = k V-cycles applied to x: usable directly as an npb_apply_fn
@@ -708,14 +743,14 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
         // p1 = L^-1 r_P            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
         if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, rp, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         // q = D A G p1
-        if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, nullptr, t1, 0, st))) return rc;
-        if ((rc = npb_spmv_launch(nv, c->A.nnz, c->A.indptr, c->A.indices, c->A.data, t1, nullptr, t2, 0, st))) return rc;
-        if ((rc = npb_spmv_launch(np, c->D.nnz, c->D.indptr, c->D.indices, c->D.data, t2, nullptr, q, 0, st))) return rc;
+        if ((rc = spmv_mat(c->G, p1, nullptr, t1, 0, st))) return rc;
+        if ((rc = spmv_mat(c->A, t1, nullptr, t2, 0, st))) return rc;
+        if ((rc = spmv_mat(c->D, t2, nullptr, q, 0, st))) return rc;
         // p = -L^-1 q
         if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         if ((rc = npb_axpby_launch(np, 0.0, p1, -1.0, p1, st))) return rc;
         // r_V <- r_V - G p
-        if ((rc = npb_spmv_launch(nv, c->G.nnz, c->G.indptr, c->G.indices, c->G.data, p1, rv, rv, 1, st))) return rc;
+        if ((rc = spmv_mat(c->G, p1, rv, rv, 1, st))) return rc;
         k_scatter<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, p1, z);
         NPB_COUNT_LAUNCH();
     }

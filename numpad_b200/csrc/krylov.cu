@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dist.cuh"
 
 namespace {
 
@@ -30,7 +31,15 @@ struct spmv_epi {
     const double* b;
     const double* dinv;
     double omega;
+    // row-sharded operators (dist.cuh): local columns >= n_own are boundary values of
+    // other ranks, gathered into xh; a single-GPU operator has n_own = INT32_MAX
+    const double* xh;
+    int32_t n_own;
 };
+
+__device__ __forceinline__ double ldx(const double* x, const spmv_epi& e, int32_t c) {
+    return c < e.n_own ? __ldg(x + c) : __ldg(e.xh + (c - e.n_own));
+}
 
 __device__ __forceinline__ double spmv_finish(const spmv_epi& e, int64_t r, double s,
                                               const double* x) {
@@ -77,7 +86,7 @@ k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
         const int32_t lim = min(base + SP_TILE, k1);
 #pragma unroll 4
         for (int32_t k = base + tid; k < lim; k += SP_THREADS)
-            sprod[k - base] = dat[k] * __ldg(x + idx[k]);
+            sprod[k - base] = dat[k] * ldx(x, epi, idx[k]);
         __syncthreads();
         const int32_t s = max(rs, base), e = min(re, lim);
         for (int32_t k = s + sub; k < e; k += TPR) acc += sprod[k - base];
@@ -135,7 +144,7 @@ k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
         const int32_t lo = max(base, k0);
 #pragma unroll 4
         for (int32_t k = lo + tid; k < lim; k += SP_THREADS)
-            sdat[k - base] *= __ldg(x + sidx[k - base]);
+            sdat[k - base] *= ldx(x, epi, sidx[k - base]);
         __syncthreads();
         const int32_t s = max(rs, base), e = min(re, lim);
         for (int32_t k = s + sub; k < e; k += TPR) acc += sdat[k - base];
@@ -199,10 +208,10 @@ k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
             const int32_t k = base + (j * SP_THREADS + tid) * 4;
             if (k < lim) {
                 double2 p0, p1;
-                p0.x = da[j].x * __ldg(x + iv[j].x);
-                p0.y = da[j].y * __ldg(x + iv[j].y);
-                p1.x = db[j].x * __ldg(x + iv[j].z);
-                p1.y = db[j].y * __ldg(x + iv[j].w);
+                p0.x = da[j].x * ldx(x, epi, iv[j].x);
+                p0.y = da[j].y * ldx(x, epi, iv[j].y);
+                p1.x = db[j].x * ldx(x, epi, iv[j].z);
+                p1.y = db[j].y * ldx(x, epi, iv[j].w);
                 *reinterpret_cast<double2*>(sprod + (k - base)) = p0;
                 *reinterpret_cast<double2*>(sprod + (k - base) + 2) = p1;
             }
@@ -233,7 +242,7 @@ k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
     if (r < nrows) {
         const int32_t e = ptr[r + 1];
         for (int32_t k = ptr[r] + lane; k < e; k += G)
-            s = fma(dat[k], __ldg(x + idx[k]), s);
+            s = fma(dat[k], ldx(x, epi, idx[k]), s);
     }
 #pragma unroll
     for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -402,9 +411,11 @@ static int npb_spmv_default_tma = 1;
 // y = epilogue(A x); see spmv_epi.  `variant`: 0 auto, 1 stream, 2 vector, 3 stream + cp.async
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                 const double* dat, const double* x, int mode, const double* b,
-                const double* dinv, double omega, double* y, int variant, cudaStream_t st) {
+                const double* dinv, double omega, double* y, int variant, cudaStream_t st,
+                const npb_halo* halo) {
     if (nrows <= 0) return NPB_OK;
-    spmv_epi e{mode, b, dinv, omega};
+    spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff};
+    if (halo && halo->dist) { e.xh = halo->recv; e.n_own = (int32_t)halo->n_own; }
     const double mean = (double)nnz / (double)nrows;
     const bool aligned = (((uintptr_t)idx | (uintptr_t)dat) & 15) == 0;
     const bool tma_ok = aligned && nnz < (int64_t)0x7fffffff - 2 * TM_CAP_MAX;
@@ -438,7 +449,7 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
 int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                     const double* dat, const double* x, const double* b, double* y,
                     int mode, cudaStream_t st) {
-    return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st);
+    return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st, nullptr);
 }
 
 // scratch: RED_BLOCKS*KC doubles of partials followed by one uint ticket
@@ -515,7 +526,7 @@ int npb_spmv_set_tma_geometry(int g) {
 int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                      const double* data, const double* x, double* y, int variant, void* stream) {
     return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, 0, nullptr, nullptr, 0.0, y, variant,
-                       ST(stream));
+                       ST(stream), nullptr);
 }
 
 // y = epilogue(A x) with a forced kernel variant (0 = auto):
@@ -528,7 +539,7 @@ int npb_spmv_epilogue(int64_t nrows, int64_t nnz, const int32_t* indptr, const i
         return NPB_ERR_ARG;
     }
     return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, mode, b, dinv, omega, y, variant,
-                       ST(stream));
+                       ST(stream), nullptr);
 }
 
 // y = b - A x

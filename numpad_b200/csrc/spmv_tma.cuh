@@ -217,7 +217,7 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
 #pragma unroll
                     for (int g = 0; g < GB; ++g) {
                         const int32_t k = kk[j] + g * TPR;
-                        xv[j][g] = (k < ee[j]) ? __ldg(x + si[k]) : 0.0;
+                        xv[j][g] = (k < ee[j]) ? ldx(x, epi, si[k]) : 0.0;
                     }
                 more = false;
 #pragma unroll

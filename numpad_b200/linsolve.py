@@ -44,7 +44,7 @@ def _csr_view(A):
 
 
 def fgmres(A, b, x0=None, precond=None, rtol=1e-12, atol=0.0, restart=60, maxiter=3000,
-           flexible=True, allreduce=None, matvec=None):
+           flexible=True, allreduce=None, matvec=None, matvec_c=None, allreduce_c=None):
     """Solve A x = b on the device.  `A` is a DevCsr (or None when `matvec` is
     given); `precond`, `matvec` are python callables (x_ptr, y_ptr) wrapped as
     C callbacks, or ints holding the address of a C callback + ctx pair."""
@@ -54,7 +54,9 @@ def fgmres(A, b, x0=None, precond=None, rtol=1e-12, atol=0.0, restart=60, maxite
     x = torch.zeros(n, dtype=torch.float64, device=device()) if x0 is None else x0.clone()
     ops = KrylovOps()
     keep = []
-    if matvec is None:
+    if matvec_c is not None:              # (address of an npb_apply_fn, address of its ctx)
+        ops.matvec, ops.matvec_ctx = matvec_c
+    elif matvec is None:
         A = A.materialized()
         view = _csr_view(A)
         keep += [A, view]
@@ -71,7 +73,9 @@ def fgmres(A, b, x0=None, precond=None, rtol=1e-12, atol=0.0, restart=60, maxite
         cb = _lib.APPLY_FN(_wrap_apply(precond, n))
         keep.append(cb)
         ops.precond = ctypes.cast(cb, ctypes.c_void_p).value
-    if allreduce is not None:
+    if allreduce_c is not None:           # (address of an npb_allreduce_fn, its ctx)
+        ops.allreduce, ops.allreduce_ctx = allreduce_c
+    elif allreduce is not None:
         cb = _lib.ALLREDUCE_FN(allreduce)
         keep.append(cb)
         ops.allreduce = ctypes.cast(cb, ctypes.c_void_p).value

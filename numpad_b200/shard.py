@@ -1,0 +1,355 @@
+"""Row-sharded Newton linear solve across the GPUs of one node.
+
+One process per GPU.  The Jacobian is permuted to strip-major order (every field of a
+grid strip contiguous), each rank keeps the rows of its strip of every operator -- the
+Jacobian, the blocks of the least-squares-commutator preconditioner and the large levels
+of both multigrid hierarchies -- and the C++ solve phase (csrc/amg.cu, gmres.cu) runs
+unchanged on the local rows: an SpMV is preceded by `pack boundary values -> all-gather`
+on the library's own NCCL communicator (csrc/dist.cu), an inner product is followed by
+an all-reduce of the device scalars.  The small multigrid levels are replicated: the
+last sharded level all-gathers its restricted residual and every rank runs the coarse
+part of the V-cycle redundantly (latency, not bandwidth, is what costs there).
+
+Numerically this is the single-GPU solver (same hierarchies, same smoother, same Krylov
+recurrences; only the order of the floating-point sums in the inner products differs),
+so iteration counts do not depend on the number of GPUs -- unlike the block-Jacobi
+preconditioner of the reference's MpiJacobian.approx_solve (admpisolve.py:167-172),
+which the saddle-point structure of the cavity Jacobian does not tolerate.
+
+This round the SETUP is replicated: every rank builds the same global hierarchies
+(deterministic kernels) and slices its rows out.  The slicing logic (`localize`) is
+plain torch and is tested on CPU; the halo numbering it produces is what
+`npb_halo` (include/numpad_b200.h) documents.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+# levels with fewer rows than this are replicated instead of sharded
+REPLICATE_BELOW = 120000
+
+_handle = {'ptr': None, 'rank': 0, 'world': 1}
+
+
+def _nccl_path():
+    try:
+        import nvidia.nccl
+        p = os.path.join(os.path.dirname(nvidia.nccl.__file__), 'lib', 'libnccl.so.2')
+        return p if os.path.exists(p) else ''
+    except Exception:
+        return ''
+
+
+def init(group=None):
+    """Collective: create the library's NCCL communicator over the ranks of the default
+    torch.distributed process group.  Returns the handle (int address)."""
+    import torch.distributed as dist
+    from . import _lib
+    if _handle['ptr'] is not None:
+        return _handle['ptr']
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    L = _lib.lib().cdll
+    path = _nccl_path().encode()
+    uid = ctypes.create_string_buffer(128)
+    if rank == 0:
+        rc = L.npb_dist_unique_id(path, uid)
+        if rc:
+            raise RuntimeError('npb_dist_unique_id failed: %s' % _lib.lib().last_error())
+    t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).clone()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    t = t.to(dev)
+    dist.broadcast(t, 0, group=group)
+    uid = ctypes.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+    h = ctypes.c_void_p()
+    rc = L.npb_dist_init(path, uid, rank, world, ctypes.byref(h))
+    if rc:
+        raise RuntimeError('npb_dist_init failed: %s' % _lib.lib().last_error())
+    _handle.update(ptr=h.value, rank=rank, world=world)
+    return h.value
+
+
+def shutdown():
+    from . import _lib
+    if _handle['ptr'] is not None:
+        _lib.lib().cdll.npb_dist_free(ctypes.c_void_p(_handle['ptr']))
+        _handle.update(ptr=None, rank=0, world=1)
+
+
+# --------------------------------------------------------------------------- #
+# slicing a replicated global CSR operator into the rows of one rank (pure torch)
+# --------------------------------------------------------------------------- #
+class LocalOp:
+    """rows [rcuts[rank], rcuts[rank+1]) of a global CSR matrix with the columns renumbered
+    [owned | boundary values of rank 0 | rank 1 | ...] (npb_halo in the C header)."""
+    __slots__ = ('shape', 'indptr', 'indices', 'data', 'nnz', 'n_own', 'send_idx', 'maxb',
+                 'recv', 'sharded_cols')
+
+
+def localize(indptr, indices, data, shape, rcuts, ccuts, rank, world, replicated_cols=False):
+    """-> LocalOp.  rcuts / ccuts: world + 1 increasing python ints (row / column ownership
+    ranges).  replicated_cols: the operand vector is replicated (global column numbering is
+    kept, no halo)."""
+    dev = indices.device
+    op = LocalOp()
+    r0, r1 = int(rcuts[rank]), int(rcuts[rank + 1])
+    kc = indptr[torch.as_tensor(list(rcuts), dtype=torch.int64, device=dev)].to(torch.int64)
+    kcl = [int(v) for v in kc.tolist()]
+    k0, k1 = kcl[rank], kcl[rank + 1]
+    op.indptr = (indptr[r0:r1 + 1] - k0).to(torch.int32).contiguous()
+    op.data = data[k0:k1]                      # a view: values are not copied
+    op.nnz = k1 - k0
+    op.sharded_cols = not replicated_cols
+    if replicated_cols:
+        op.shape = (r1 - r0, shape[1])
+        op.indices = indices[k0:k1]
+        op.n_own, op.maxb = shape[1], 0
+        op.send_idx = torch.zeros(0, dtype=torch.int32, device=dev)
+        op.recv = torch.zeros(1, dtype=torch.float64, device=dev)
+        return op
+    cc = torch.as_tensor(list(ccuts), dtype=torch.int64, device=dev)
+    n_own = int(ccuts[rank + 1]) - int(ccuts[rank])
+    # boundary sets of ALL ranks (every rank derives the same lists from the replicated
+    # matrix): columns referenced by a row of another rank
+    nnz = int(indices.numel())
+    cols = indices.to(torch.int64)
+    col_owner = torch.searchsorted(cc, cols, right=True) - 1
+    ent = torch.arange(nnz, dtype=torch.int64, device=dev)
+    row_owner = torch.searchsorted(kc, ent, right=True) - 1
+    row_owner.clamp_(max=world - 1)
+    remote = col_owner != row_owner
+    bcols = torch.unique(cols[remote])         # sorted
+    bstart = torch.searchsorted(bcols, cc)     # world + 1 segment bounds
+    counts = bstart[1:] - bstart[:-1]
+    maxb = int(counts.max().item()) if world > 0 else 0
+    lc, lo = cols[k0:k1], col_owner[k0:k1]
+    own = lo == rank
+    pos = torch.searchsorted(bcols, lc)
+    halo = n_own + lo * maxb + (pos - bstart[lo.clamp(0, world - 1)])
+    op.indices = torch.where(own, lc - int(ccuts[rank]), halo).to(torch.int32).contiguous()
+    b0, b1 = int(bstart[rank].item()), int(bstart[rank + 1].item())
+    op.send_idx = (bcols[b0:b1] - int(ccuts[rank])).to(torch.int32).contiguous()
+    op.n_own, op.maxb = n_own, maxb
+    op.shape = (r1 - r0, n_own + world * maxb)
+    op.recv = torch.zeros(max(world * maxb, 1), dtype=torch.float64, device=dev)
+    return op
+
+
+def local_matvec_reference(op, x_own, gathered):
+    """y = op @ [x_own | gathered] with plain torch (CPU tests of the numbering)"""
+    xe = torch.cat([x_own, gathered])
+    rows = torch.repeat_interleave(torch.arange(op.shape[0], device=x_own.device),
+                                   (op.indptr[1:] - op.indptr[:-1]).long())
+    y = torch.zeros(op.shape[0], dtype=x_own.dtype, device=x_own.device)
+    y.index_add_(0, rows, op.data * xe[op.indices.long()])
+    return y
+
+
+def strip_permutation(owner, world):
+    """stable sort of the unknowns by owning rank -> (perm, inv, cuts): new index i holds
+    old index perm[i]; cuts = world + 1 range bounds in the new numbering"""
+    owner = torch.as_tensor(owner)
+    perm = torch.sort(owner.to(torch.int64), stable=True).indices
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel(), dtype=torch.int64, device=perm.device)
+    counts = torch.bincount(owner.to(torch.int64), minlength=world)
+    cuts = [0] + [int(v) for v in torch.cumsum(counts, 0).tolist()]
+    return perm, inv, cuts
+
+
+# --------------------------------------------------------------------------- #
+# device side: sharded hierarchies, LSC preconditioner, FGMRES
+# --------------------------------------------------------------------------- #
+def _fill_mat(m, op, handle):
+    """fill an amg.CsrMat from a LocalOp"""
+    m.nrows, m.ncols, m.nnz = op.shape[0], op.shape[1], op.nnz
+    m.indptr, m.indices, m.data = op.indptr.data_ptr(), op.indices.data_ptr(), op.data.data_ptr()
+    if op.sharded_cols:
+        m.halo.dist = handle
+        m.halo.n_own = op.n_own
+        m.halo.send_idx = op.send_idx.data_ptr()
+        m.halo.n_send = int(op.send_idx.numel())
+        m.halo.maxb = op.maxb
+        m.halo.recv = op.recv.data_ptr()
+    return m
+
+
+def _loc(A, rcuts, ccuts, replicated_cols=False):
+    A = A.materialized()
+    return localize(A.indptr, A.indices, A.data, A.shape, rcuts, ccuts, _handle['rank'],
+                    _handle['world'], replicated_cols)
+
+
+class ShardedHierarchy:
+    """An amg.Hierarchy (built on the global operator, replicated) whose large levels are
+    applied on the local rows."""
+
+    def __init__(self, h, cuts):
+        from . import amg
+        from ._dev import device
+        rank, world, handle = _handle['rank'], _handle['world'], _handle['ptr']
+        self.h, self.keep = h, []
+        nl = len(h.levels)
+        # cuts of every level: a coarse index belongs to the rank owning its root
+        lev_cuts = [list(cuts)]
+        for l in range(nl - 1):
+            rid = h.levels[l].get('root_id')
+            if rid is None:
+                raise RuntimeError('hierarchy without root ids cannot be sharded')
+            c = rid[torch.as_tensor(lev_cuts[-1], dtype=torch.int64, device=rid.device)]
+            lev_cuts.append([int(v) for v in c.tolist()])
+        # first replicated level: the first one below REPLICATE_BELOW rows (at least the last)
+        first_rep = nl - 1
+        for l in range(1, nl):
+            if h.sizes[l] < REPLICATE_BELOW:
+                first_rep = l
+                break
+        self.first_rep, self.lev_cuts = first_rep, lev_cuts
+        self.arr = (amg.AmgLevel * nl)()
+        self.work = []
+        for l, lev in enumerate(h.levels):
+            L = self.arr[l]
+            if l >= first_rep:                 # replicated: the global level as it is
+                src = h.arr[l]
+                ctypes.memmove(ctypes.addressof(L), ctypes.addressof(src), ctypes.sizeof(amg.AmgLevel))
+                continue
+            c, cn = lev_cuts[l], lev_cuts[l + 1]
+            a = _loc(lev['A'], c, c)
+            last = (l + 1 == first_rep)
+            p = _loc(lev['P'], c, cn, replicated_cols=last)
+            r = _loc(lev['R'], cn, c)
+            self.keep += [a, p, r]
+            _fill_mat(L.A, a, handle); _fill_mat(L.P, p, handle); _fill_mat(L.R, r, handle)
+            dinv = lev['dinv'][c[rank]:c[rank + 1]]
+            n = c[rank + 1] - c[rank]
+            w = [torch.zeros(max(n, 1), dtype=torch.float64, device=device()) for _ in range(4)]
+            self.work.append(w)
+            self.keep.append(dinv)
+            L.dinv = dinv.data_ptr()
+            L.x, L.x2, L.b, L.r = [t.data_ptr() for t in w]
+            if last:
+                off = (ctypes.c_int64 * (world + 1))(*cn)
+                self.keep.append(off)
+                L.gather = 1
+                L.offsets = ctypes.cast(off, ctypes.c_void_p).value
+        s = self.struct = amg.AmgStruct()
+        ctypes.memmove(ctypes.addressof(s), ctypes.addressof(h.struct), ctypes.sizeof(amg.AmgStruct))
+        s.levels = ctypes.cast(self.arr, ctypes.POINTER(amg.AmgLevel))
+        s.dist = handle
+
+    @property
+    def addr(self):
+        return ctypes.addressof(self.struct)
+
+
+class ShardedLsc:
+    """amg.LscPreconditioner applied on the rows of this rank (csrc/amg.cu npb_lsc_apply_cb
+    with sharded operators)."""
+
+    def __init__(self, M, cuts):
+        from . import amg, _lib
+        from ._dev import device
+        rank, handle = _handle['rank'], _handle['ptr']
+        if M.amg_a is None:
+            raise RuntimeError('the robust (Krylov) momentum solve is not sharded')
+        self.M = M
+        dev = M.vset.device
+        ct = torch.as_tensor(cuts, dtype=torch.int32, device=dev)
+        cv = [int(v) for v in torch.searchsorted(M.vset, ct).tolist()]
+        cp = [int(v) for v in torch.searchsorted(M.pset, ct).tolist()]
+        self.cuts, self.cv, self.cp = list(cuts), cv, cp
+        self.vset = (M.vset[cv[rank]:cv[rank + 1]] - cuts[rank]).contiguous()
+        self.pset = (M.pset[cp[rank]:cp[rank + 1]] - cuts[rank]).contiguous()
+        nv, np_ = cv[rank + 1] - cv[rank], cp[rank + 1] - cp[rank]
+        self.A, self.G = _loc(M.A, cv, cv), _loc(M.G, cv, cp)
+        self.D, self.Lm = _loc(M.D, cp, cv), _loc(M.Lm, cp, cp)
+        self.amg_a = ShardedHierarchy(M.amg_a, cv)
+        self.amg_l = ShardedHierarchy(M.amg_l, cp)
+        self.a_dinv = M.a_dinv[cv[rank]:cv[rank + 1]]
+        self.wv = [torch.zeros(max(nv, 1), dtype=torch.float64, device=device()) for _ in range(5)]
+        self.wp = [torch.zeros(max(np_, 1), dtype=torch.float64, device=device()) for _ in range(8)]
+        self.scal = torch.zeros(4, dtype=torch.float64, device=device())
+        self.red = torch.zeros(_lib.lib().cdll.npb_reduce_scratch_bytes(), dtype=torch.uint8,
+                               device=device())
+        s = self.struct = amg.LscStruct()
+        s.n, s.nv, s.np = cuts[rank + 1] - cuts[rank], nv, np_
+        s.vset, s.pset = self.vset.data_ptr(), self.pset.data_ptr()
+        for m, op in ((s.A, self.A), (s.G, self.G), (s.D, self.D), (s.Lm, self.Lm)):
+            _fill_mat(m, op, handle)
+        s.a_dinv = self.a_dinv.data_ptr()
+        s.amg_a, s.amg_l = self.amg_a.addr, self.amg_l.addr
+        s.a_gmres = 0
+        s.cycles_a, s.cycles_l = M.struct.cycles_a, M.struct.cycles_l
+        for k in range(5):
+            s.wv[k] = self.wv[k].data_ptr()
+        for k in range(8):
+            s.wp[k] = self.wp[k].data_ptr()
+        s.scal, s.red = self.scal.data_ptr(), self.red.data_ptr()
+        self.c_apply = ctypes.cast(_lib.lib().cdll.npb_lsc_apply_cb, ctypes.c_void_p).value
+        self.c_ctx = ctypes.addressof(s)
+
+
+last_info = {}
+
+
+def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=None):
+    """x = J^-1 b with the rows of every operator sharded over the ranks of the process
+    group (collective; J and b replicated on every rank, x returned replicated).
+    owner[i] = rank that owns unknown i (numpy / torch int array; None: equal contiguous
+    ranges of the natural ordering)."""
+    import time
+    import torch.distributed as dist
+    from . import amg, linsolve, _lib
+    from ._dev import device, coo_to_csr, DevCsr
+    handle = init()
+    rank, world = _handle['rank'], _handle['world']
+    J = J.materialized()
+    n = J.shape[0]
+    dev = device()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    if owner is None:
+        owner = torch.clamp((torch.arange(n, device=dev) * world) // n, max=world - 1)
+    owner = torch.as_tensor(owner).to(dev)
+    perm, inv, cuts = strip_permutation(owner, world)
+    # J' = Pi J Pi^T (strip-major), replicated
+    rows = inv[J.rows().long()].to(torch.int32)
+    cols = inv[J.indices.long()].to(torch.int32)
+    Jp = coo_to_csr(J.shape, rows, cols, J.data, prune=False)
+    bp = b.reshape(-1)[perm].contiguous()
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    M = amg.LscPreconditioner(Jp, **(lsc_options or {}))
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    S = ShardedLsc(M, cuts)
+    Jl = _loc(Jp, cuts, cuts)
+    jm = amg.CsrMat()
+    _fill_mat(jm, Jl, handle)
+    torch.cuda.synchronize(); t3 = time.perf_counter()
+    L = _lib.lib().cdll
+    mv = ctypes.cast(L.npb_mat_matvec_cb, ctypes.c_void_p).value
+    ar = ctypes.cast(L.npb_dist_allreduce_cb, ctypes.c_void_p).value
+    b_loc = bp[cuts[rank]:cuts[rank + 1]].contiguous()
+    x_loc, res = linsolve.fgmres(None, b_loc, precond=S, rtol=rtol, restart=restart, maxiter=maxiter,
+                                 matvec_c=(mv, ctypes.addressof(jm)), allreduce_c=(ar, handle))
+    torch.cuda.synchronize(); t4 = time.perf_counter()
+    # gather the strips and undo the permutation
+    xp = torch.empty(n, dtype=torch.float64, device=dev)
+    parts = [xp[cuts[q]:cuts[q + 1]] for q in range(world)]
+    parts[rank].copy_(x_loc)
+    for q in range(world):
+        if parts[q].numel():
+            dist.broadcast(parts[q], q)
+    x = torch.empty_like(xp)
+    x[perm] = xp
+    torch.cuda.synchronize(); t5 = time.perf_counter()
+    res.update(method='fgmres+lsc (row-sharded, %d ranks)' % world, permute_ms=1e3 * (t1 - t0),
+               setup_ms=1e3 * (t2 - t1), localize_ms=1e3 * (t3 - t2), krylov_ms=1e3 * (t4 - t3),
+               gather_ms=1e3 * (t5 - t4), precond=M.describe(),
+               first_replicated_level=(S.amg_a.first_rep, S.amg_l.first_rep),
+               halo=(Jl.maxb, S.A.maxb, S.Lm.maxb))
+    last_info.clear()
+    last_info.update(res)
+    if res['status'] != 0:
+        raise linsolve.LinearSolveError('sharded linear solve did not converge: %d iterations, '
+                                        '|r|/|b| = %.3e' % (res['iters'], res['rnorm'] / max(res['bnorm'], 1e-300)))
+    return x
