@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--rtol', type=float, default=1e-10)
     ap.add_argument('--restart', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parallel', default='sharded', choices=['sharded', 'replicas'],
+                    help='N > 1: one problem row-sharded over the GPUs (strong scaling) or N independent replicas')
     return ap.parse_args()
 
 
@@ -107,8 +109,9 @@ def run_reference(args):
         'value': cb['value'], 'unit': 'Newton iters/sec', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * cb['sample_seconds'], 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args.grid, n, args.gpus),
+        'scaling': 'strong' if (args.gpus > 1 and args.parallel == 'sharded') else 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.grid, n, args.gpus, args.parallel),
         'cpu_baseline': cb,
         'e2e': {'value': cb['value'], 'unit': 'Newton iters/sec', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -117,15 +120,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(grid, n, gpus):
+def workload_config(grid, n, gpus, parallel='sharded'):
     return {'workload': 'lid-driven cavity %d^2 (test/cavity.py residual), n=%d unknowns, '
                         'Re=1e4, dt=1, fixed state 1e-2*RandomState(0).standard_normal(n); '
                         'one full Newton iteration per step' % (grid, n),
             'grid': grid, 'unknowns': n, 'linear_rtol': None,
             'l2_policy': 'inputs larger than L2 (Jacobian alone > 126 MB)',
-            'parallelism': ('%d independent replicas of the single-GPU problem, one per GPU, no '
-                            'data-path collective (row-sharding of the saddle-point solve: '
-                            'DESIGN.md section 7)' % gpus) if gpus > 1 else 'single GPU'}
+            'parallelism': 'single GPU' if gpus <= 1 else (
+                ('%d independent replicas of the single-GPU problem, one per GPU, no data-path '
+                 'collective' % gpus) if parallel == 'replicas' else
+                ('ONE problem, linear solve row-sharded over %d GPUs in grid strips (halo all-gather '
+                 'before every SpMV, all-reduce after every inner product, NCCL over NVLink); residual, '
+                 'Jacobian assembly and multigrid setup replicated on every rank (DESIGN.md section 7)'
+                 % gpus))}
 
 
 # --------------------------------------------------------------------------- #
@@ -184,10 +191,12 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     import numpad_b200 as npd
-    from numpad_b200 import linsolve, _lib, precond
+    from numpad_b200 import linsolve, _lib, precond, shard
     from numpad_b200.workloads.cavity import CavityProblem
     dev = torch.device('cuda', local)
+    sharded = world > 1 and args.parallel == 'sharded'
     P = CavityProblem(npd, args.grid)
+    owner = P.partition(world) if sharded else None
     n = P.n
     u0 = P.fixed_state()
     u_host = torch.from_numpy(u0.copy()).pin_memory()
@@ -211,16 +220,22 @@ def run_ours(args):
         # every step pays the full preconditioner setup (no hierarchy is carried
         # over from the previous step, although a real Newton march could)
         precond._last['lsc'] = None
-        du = linsolve.solve(J, res._dev.reshape(-1), rtol=args.rtol, restart=args.restart)
+        if sharded:
+            du = shard.solve(J, res._dev.reshape(-1), owner=owner, rtol=args.rtol, restart=args.restart)
+        else:
+            du = linsolve.solve(J, res._dev.reshape(-1), rtol=args.rtol, restart=args.restart)
         if record:
             ev[3].record()
             torch.cuda.synchronize()
-            li = linsolve.last_info
+            li = shard.last_info if sharded else linsolve.last_info
             phases.update(residual_ms=ev[0].elapsed_time(ev[1]), assembly_ms=ev[1].elapsed_time(ev[2]),
                           linear_solve_ms=ev[2].elapsed_time(ev[3]), precond_setup_ms=li.get('setup_ms'),
                           krylov_ms=li.get('krylov_ms'), krylov_iters=li.get('iters'),
                           method=li.get('method'), nnz=J.nnz, relres=li['rnorm'] / li['bnorm'],
                           precond=li.get('precond'))
+            if sharded:
+                phases.update(permute_ms=li.get('permute_ms'), localize_ms=li.get('localize_ms'),
+                              halo_values_per_exchange=li.get('halo'))
         return J, du
 
     def barrier():
@@ -287,17 +302,19 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(str(args.grid))
     except Exception:
         pass
-    value = world * args.steps / (ms * 1e-3)
-    e2e = world * args.steps / (ms_e2e * 1e-3)
+    # replicas: N problems per step; sharded: one problem per step (strong scaling)
+    per_step = 1 if (sharded or world == 1) else world
+    value = per_step * args.steps / (ms * 1e-3)
+    e2e = per_step * args.steps / (ms_e2e * 1e-3)
     if rank == 0:
-        cfg = workload_config(args.grid, n, world)
+        cfg = workload_config(args.grid, n, world, args.parallel)
         cfg['linear_rtol'] = args.rtol
         line = {
             'metric': 'Newton iters/sec (Jacobian assembly+solve), cavity',
             'value': value, 'unit': 'Newton iters/sec', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': cfg,
+            'higher_is_better': True, 'scaling': 'strong' if sharded else 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
             'e2e': {'value': e2e, 'unit': 'Newton iters/sec', 'h2d_bytes_per_step': 16 * n,
                     'd2h_bytes_per_step': 8 * n, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,
@@ -313,6 +330,7 @@ def run_ours(args):
             line['cpu_baseline'] = cpu_baseline(args.grid, args.sample_grid)
         print(json.dumps(line))
     if world > 1:
+        shard.shutdown()
         dist.destroy_process_group()
 
 

@@ -246,6 +246,10 @@ typedef struct npb_halo {
     const int32_t* send_idx;        /* [n_send] local indices of the values to publish */
     int32_t n_send, maxb;
     double* recv;                   /* [world * maxb] */
+    /* direct-store path: offsets into the symmetric heap (npb_dist_heap_alloc) of 2 x world x
+     * maxb doubles and of world 64-bit arrival counters; < 0: NCCL all-gather into recv */
+    int64_t p2p_data, p2p_flags;
+    unsigned long long* seq;        /* [host] exchange counter of this operator */
 } npb_halo;
 
 typedef struct npb_csr_mat {
@@ -304,10 +308,17 @@ int npb_dist_unique_id(const char* nccl_path, char* id128);        /* rank 0; ho
 int npb_dist_init(const char* nccl_path, const char* id128, int rank, int world,
                   void** handle);                                  /* collective */
 int npb_dist_free(void* handle);
+/* symmetric heap for exchanges by direct stores into NVLink peer memory (same layout on
+ * every rank; all_handles = world x 64 bytes of CUDA IPC handles in rank order) */
+int npb_dist_heap_create(void* handle, int64_t bytes, char* ipc64);
+int npb_dist_heap_open(void* handle, const char* all_handles);         /* collective */
+int64_t npb_dist_heap_alloc(void* handle, int64_t bytes);              /* offset or < 0 */
+int npb_dist_heap_reset(void* handle, void* stream);    /* between barriers: drop all allocs */
 int npb_dist_rank(void* handle);
 int npb_dist_world(void* handle);
 int npb_dist_allreduce_cb(void* ctx, double* buf, int count, void* stream); /* npb_allreduce_fn */
 int npb_mat_matvec_cb(void* ctx, const double* x, double* y, void* stream); /* ctx = npb_csr_mat */
+int npb_mat_halo_exchange(void* ctx, const double* x, void* stream);   /* the exchange alone */
 
 int npb_csr_diagonal(int64_t nrows, const int32_t* indptr, const int32_t* indices,
                      const double* data, double* diag, void* stream);

@@ -20,7 +20,9 @@ from ._dev import (DevCsr, sel_jac, dia_jac, device, stream_ptr, _empty, _call, 
 class Halo(ctypes.Structure):            # npb_halo: filled by shard.py for row-sharded operators
     _fields_ = [('dist', ctypes.c_void_p), ('n_own', ctypes.c_int64),
                 ('send_idx', ctypes.c_void_p), ('n_send', ctypes.c_int32),
-                ('maxb', ctypes.c_int32), ('recv', ctypes.c_void_p)]
+                ('maxb', ctypes.c_int32), ('recv', ctypes.c_void_p),
+                ('p2p_data', ctypes.c_int64), ('p2p_flags', ctypes.c_int64),
+                ('seq', ctypes.c_void_p)]
 
 
 class CsrMat(ctypes.Structure):

@@ -505,11 +505,16 @@ static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* 
                            int mode, cudaStream_t st, const double* dinv = nullptr,
                            double omega = 0.0) {
     if (M.halo.dist) {
-        int rc = npb_dist_halo_exchange(M.halo, x, st);
+        npb_halo h = M.halo;
+        const double* xh = nullptr;
+        int rc = npb_dist_halo_exchange(M.halo, x, st, &xh);
         if (rc) return rc;
+        h.recv = const_cast<double*>(xh);
+        return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y,
+                           0, st, &h);
     }
     return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y, 0,
-                       st, &M.halo);
+                       st, nullptr);
 }
 
 struct npb_amg_level {
@@ -657,6 +662,13 @@ static int amg_pcg(const npb_amg* h, const npb_csr_mat& A, int k, const double* 
 // y = M x as an npb_apply_fn; ctx = npb_csr_mat (row-sharded or not)
 int npb_mat_matvec_cb(void* ctx, const double* x, double* y, void* stream) {
     return spmv_mat(*(const npb_csr_mat*)ctx, x, nullptr, y, 0, ST(stream));
+}
+
+// only the halo exchange of a sharded operator (tools/shard_micro.py)
+int npb_mat_halo_exchange(void* ctx, const double* x, void* stream) {
+    const npb_csr_mat& M = *(const npb_csr_mat*)ctx;
+    const double* xh = nullptr;
+    return M.halo.dist ? npb_dist_halo_exchange(M.halo, x, ST(stream), &xh) : NPB_OK;
 }
 
 // y = k V-cycles applied to x: usable directly as an npb_apply_fn

@@ -84,12 +84,101 @@ k_pack(int n, const int32_t* __restrict__ idx, const double* __restrict__ x,
     if (i < n) out[i] = x[idx[i]];
 }
 
+// ---- direct-store exchanges over NVLink peer memory --------------------------------
+// Every rank stores its values straight into the slot it owns in each peer's heap, fences
+// at system scope and bumps an arrival counter on the peer; then it waits until the
+// counters of all peers have reached this exchange's sequence number.  Two parities of
+// the data slots: a rank can be at most one exchange ahead of a peer that still reads
+// the previous one (it cannot start exchange k+2 before every peer has published k+1,
+// i.e. has finished reading k).
+struct peer_ptrs { char* base[NPB_MAX_PEERS]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void wait_peers(const unsigned long long* flags, int world, int rank,
+                                           unsigned long long seq) {
+    // threads 0 .. world-1 each watch one peer's arrival counter (in LOCAL memory)
+    const int q = threadIdx.x;
+    if (q < world && q != rank) {
+        unsigned long long spins = 0;
+        while (ld_acquire_sys(flags + q) < seq)
+            if (++spins > (1ull << 31)) __trap();      // a dead peer must not hang the GPU
+    }
+    __syncthreads();
+}
+
+// one CTA: out slot of every peer <- x[idx[0..n)], then wait for the peers' slots
+__global__ void __launch_bounds__(1024)
+k_push_halo(int n, const int32_t* __restrict__ idx, const double* __restrict__ x, peer_ptrs pp,
+            int64_t data_off, int64_t flag_off, int64_t slot, int world, int rank,
+            unsigned long long seq) {
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const double v = x[idx[i]];
+        for (int q = 0; q < world; ++q)
+            if (q != rank) reinterpret_cast<double*>(pp.base[q] + data_off)[slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world && threadIdx.x != rank)
+        st_release_sys(reinterpret_cast<unsigned long long*>(pp.base[threadIdx.x] + flag_off) + rank, seq);
+    wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
+}
+
+// buf[0..count) <- sum over ranks (fixed rank order: identical bits on every rank)
+__global__ void __launch_bounds__(NPB_RED_SLOT)
+k_allreduce_p2p(double* __restrict__ buf, int count, peer_ptrs pp, int64_t data_off,
+                int64_t flag_off, int64_t parity_off, int world, int rank, unsigned long long seq) {
+    const int t = threadIdx.x;
+    if (t < count) {
+        const double v = buf[t];
+        for (int q = 0; q < world; ++q)
+            reinterpret_cast<double*>(pp.base[q] + data_off)[parity_off + (int64_t)rank * NPB_RED_SLOT + t] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < world && t != rank)
+        st_release_sys(reinterpret_cast<unsigned long long*>(pp.base[t] + flag_off) + rank, seq);
+    wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
+    if (t < count) {
+        const volatile double* mine = reinterpret_cast<const volatile double*>(pp.base[rank] + data_off) + parity_off;
+        double s = 0.0;
+        for (int q = 0; q < world; ++q) s += mine[(int64_t)q * NPB_RED_SLOT + t];
+        buf[t] = s;
+    }
+}
+
+static inline peer_ptrs make_peers(const npb_dist* d) {
+    peer_ptrs pp;
+    for (int q = 0; q < NPB_MAX_PEERS; ++q) pp.base[q] = d->heap[q];
+    return pp;
+}
+
 }  // namespace
 
 // ---- internal API (dist.cuh) ------------------------------------------------------
-int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st) {
+int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, const double** xh) {
     // boundary values of x -> this rank's slot of the gather buffer -> every rank
     const npb_dist* d = (const npb_dist*)h.dist;
+    if (h.p2p_data >= 0 && d->heap[d->rank]) {
+        const unsigned long long seq = ++(*h.seq);
+        const int64_t parity_off = (int64_t)(seq & 1) * d->world * h.maxb;
+        if (h.maxb > 0) {
+            k_push_halo<<<1, 1024, 0, st>>>(h.n_send, h.send_idx, x, make_peers(d), h.p2p_data,
+                                            h.p2p_flags, parity_off + (int64_t)d->rank * h.maxb,
+                                            d->world, d->rank, seq);
+            NPB_COUNT_LAUNCH();
+        }
+        *xh = reinterpret_cast<const double*>(d->heap[d->rank] + h.p2p_data) + parity_off;
+        return NPB_OK;
+    }
+    *xh = h.recv;
     double* mine = h.recv + (int64_t)d->rank * h.maxb;
     if (h.n_send > 0) {
         k_pack<<<npb_blocks(h.n_send, 256), 256, 0, st>>>(h.n_send, h.send_idx, x, mine);
@@ -100,8 +189,17 @@ int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st) 
     return NPB_OK;
 }
 
-int npb_dist_allreduce_sum(const npb_dist* d, double* buf, int count, cudaStream_t st) {
+int npb_dist_allreduce_sum(const npb_dist* dc, double* buf, int count, cudaStream_t st) {
+    npb_dist* d = const_cast<npb_dist*>(dc);
     if (!d || d->world <= 1 || count <= 0) return NPB_OK;
+    if (d->red_data >= 0 && count <= NPB_RED_SLOT) {
+        const unsigned long long seq = ++d->red_seq;
+        k_allreduce_p2p<<<1, NPB_RED_SLOT, 0, st>>>(buf, count, make_peers(d), d->red_data, d->red_flags,
+                                                   (int64_t)(seq & 1) * d->world * NPB_RED_SLOT,
+                                                   d->world, d->rank, seq);
+        NPB_COUNT_LAUNCH();
+        return NPB_OK;
+    }
     NPB_NCCL(g_nccl.allreduce(buf, buf, (size_t)count, NCCL_DOUBLE, NCCL_SUM, d->comm, st));
     return NPB_OK;
 }
@@ -157,9 +255,76 @@ int npb_dist_init(const char* nccl_path, const char* id128, int rank, int world,
 int npb_dist_free(void* handle) {
     npb_dist* d = (npb_dist*)handle;
     if (!d) return NPB_OK;
+    cudaDeviceSynchronize();
+    for (int q = 0; q < d->world && q < NPB_MAX_PEERS; ++q) {
+        if (!d->heap[q]) continue;
+        if (q == d->rank) cudaFree(d->heap[q]); else cudaIpcCloseMemHandle(d->heap[q]);
+    }
     if (d->comm && g_nccl.destroy) g_nccl.destroy(d->comm);
     delete d;
     return NPB_OK;
+}
+
+// ---- symmetric heap (direct-store exchanges).  create: cudaMalloc + zero + IPC handle (64
+// bytes) of this rank's heap; open: collective, all_handles = world x 64 bytes in rank
+// order; alloc: bump allocation, the same call sequence on every rank gives the same
+// offsets everywhere.  Without a heap every exchange goes through NCCL.
+int npb_dist_heap_create(void* handle, int64_t bytes, char* ipc64) {
+    npb_dist* d = (npb_dist*)handle;
+    if (!d || d->world > NPB_MAX_PEERS || bytes <= 0) return NPB_ERR_ARG;
+    void* p = nullptr;
+    NPB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    NPB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t hnd;
+    NPB_CUDA(cudaIpcGetMemHandle(&hnd, p));
+    memcpy(ipc64, &hnd, sizeof(hnd) < 64 ? sizeof(hnd) : 64);
+    d->heap[d->rank] = (char*)p;
+    d->heap_bytes = bytes;
+    d->heap_used = 0;
+    return NPB_OK;
+}
+
+int npb_dist_heap_open(void* handle, const char* all_handles) {
+    npb_dist* d = (npb_dist*)handle;
+    if (!d || !d->heap[d->rank]) return NPB_ERR_ARG;
+    for (int q = 0; q < d->world; ++q) {
+        if (q == d->rank) continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, all_handles + (size_t)q * 64, sizeof(hnd) < 64 ? sizeof(hnd) : 64);
+        void* p = nullptr;
+        NPB_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        d->heap[q] = (char*)p;
+    }
+    // all-reduce slots: 2 parities x world x NPB_RED_SLOT doubles + world counters
+    d->red_data = 0;
+    d->red_flags = (int64_t)2 * d->world * NPB_RED_SLOT * 8;
+    d->heap_used = d->red_flags + 256;
+    d->red_seq = 0;
+    return NPB_OK;
+}
+
+// forget every allocation but the all-reduce slots and zero the freed part.  The caller
+// brackets this with barriers: no peer may still push into the old layout, none may push
+// into the new one before the memset has run.
+int npb_dist_heap_reset(void* handle, void* stream) {
+    npb_dist* d = (npb_dist*)handle;
+    if (!d || !d->heap[d->rank]) return NPB_ERR_ARG;
+    const int64_t base = d->red_flags + 256;
+    NPB_CUDA(cudaMemsetAsync(d->heap[d->rank] + base, 0, (size_t)(d->heap_used - base), (cudaStream_t)stream));
+    NPB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    d->heap_used = base;
+    return NPB_OK;
+}
+
+// -> offset of `bytes` (rounded up to 256) in the heap, or < 0 when it is full
+int64_t npb_dist_heap_alloc(void* handle, int64_t bytes) {
+    npb_dist* d = (npb_dist*)handle;
+    if (!d || !d->heap[d->rank] || bytes < 0) return -1;
+    const int64_t b = (bytes + 255) / 256 * 256;
+    if (d->heap_used + b > d->heap_bytes) return -1;
+    const int64_t off = d->heap_used;
+    d->heap_used += b;
+    return off;
 }
 
 int npb_dist_rank(void* handle) { return handle ? ((npb_dist*)handle)->rank : 0; }

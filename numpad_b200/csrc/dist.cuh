@@ -3,9 +3,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+constexpr int NPB_MAX_PEERS = 8;       // direct-store exchanges: one node, <= 8 GPUs
+constexpr int NPB_RED_SLOT = 128;      // doubles per rank in the all-reduce slots
+
 struct npb_dist {            // one per process: the library's NCCL communicator
     void* comm = nullptr;
     int rank = 0, world = 1;
+    // symmetric heap for direct-store exchanges over NVLink peer memory: the same
+    // cudaMalloc'ed layout on every rank, opened on the peers through CUDA IPC
+    char* heap[NPB_MAX_PEERS] = {};        // heap[q] = base of rank q's heap in this process
+    int64_t heap_bytes = 0, heap_used = 0;
+    int64_t red_data = -1, red_flags = -1; // offsets of the all-reduce slots
+    unsigned long long red_seq = 0;
 };
 
 // Halo of one row-sharded operator.  Local column numbering: [0, n_own) = the columns this
@@ -18,9 +27,14 @@ struct npb_halo {
     const int32_t* send_idx;     // [n_send] local indices of the boundary values to publish
     int32_t n_send, maxb;
     double* recv;                // [world * maxb]
+    // direct-store path (npb_dist_heap_*): offsets into the symmetric heap of 2 x world x maxb
+    // doubles (two parities) and world 64-bit arrival counters; seq = [host] exchange counter
+    int64_t p2p_data, p2p_flags;  // < 0: use the NCCL all-gather into `recv`
+    unsigned long long* seq;
 };
 
-int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st);
+// publishes / fetches the boundary values of x; *xh = where the SpMV reads them
+int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, const double** xh);
 int npb_dist_allreduce_sum(const npb_dist* d, double* buf, int count, cudaStream_t st);
 int npb_dist_allgatherv(const npb_dist* d, const double* mine, double* full,
                         const int64_t* offsets, cudaStream_t st);

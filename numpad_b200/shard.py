@@ -30,7 +30,10 @@ import torch
 # levels with fewer rows than this are replicated instead of sharded
 REPLICATE_BELOW = 120000
 
-_handle = {'ptr': None, 'rank': 0, 'world': 1}
+# bytes of the symmetric heap for direct-store exchanges (0 / NPB_DIST_P2P=0: NCCL only)
+HEAP_BYTES = 64 << 20
+
+_handle = {'ptr': None, 'rank': 0, 'world': 1, 'p2p': False}
 
 
 def _nccl_path():
@@ -66,7 +69,21 @@ def init(group=None):
     rc = L.npb_dist_init(path, uid, rank, world, ctypes.byref(h))
     if rc:
         raise RuntimeError('npb_dist_init failed: %s' % _lib.lib().last_error())
-    _handle.update(ptr=h.value, rank=rank, world=world)
+    _handle.update(ptr=h.value, rank=rank, world=world, p2p=False)
+    if HEAP_BYTES and world <= 8 and os.environ.get('NPB_DIST_P2P', '1') != '0':
+        ipc = ctypes.create_string_buffer(64)
+        rc = L.npb_dist_heap_create(h, HEAP_BYTES, ipc)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            mine = torch.frombuffer(bytearray(ipc.raw), dtype=torch.uint8).clone().to(dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine, group=group)
+            blob = b''.join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+            rc = L.npb_dist_heap_open(h, blob)
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            _handle['p2p'] = int(ok.item()) == 1
     return h.value
 
 
@@ -74,7 +91,7 @@ def shutdown():
     from . import _lib
     if _handle['ptr'] is not None:
         _lib.lib().cdll.npb_dist_free(ctypes.c_void_p(_handle['ptr']))
-        _handle.update(ptr=None, rank=0, world=1)
+        _handle.update(ptr=None, rank=0, world=1, p2p=False)
 
 
 # --------------------------------------------------------------------------- #
@@ -98,12 +115,13 @@ def localize(indptr, indices, data, shape, rcuts, ccuts, rank, world, replicated
     kcl = [int(v) for v in kc.tolist()]
     k0, k1 = kcl[rank], kcl[rank + 1]
     op.indptr = (indptr[r0:r1 + 1] - k0).to(torch.int32).contiguous()
-    op.data = data[k0:k1]                      # a view: values are not copied
+    # a view when the slice starts on a 16-byte boundary (the TMA SpMV needs that), else a copy
+    op.data = data[k0:k1] if k0 % 2 == 0 else data[k0:k1].clone()
     op.nnz = k1 - k0
     op.sharded_cols = not replicated_cols
     if replicated_cols:
         op.shape = (r1 - r0, shape[1])
-        op.indices = indices[k0:k1]
+        op.indices = indices[k0:k1] if k0 % 4 == 0 else indices[k0:k1].clone()
         op.n_own, op.maxb = shape[1], 0
         op.send_idx = torch.zeros(0, dtype=torch.int32, device=dev)
         op.recv = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -172,7 +190,36 @@ def _fill_mat(m, op, handle):
         m.halo.n_send = int(op.send_idx.numel())
         m.halo.maxb = op.maxb
         m.halo.recv = op.recv.data_ptr()
+        m.halo.p2p_data = m.halo.p2p_flags = -1
+        if _handle['p2p'] and op.maxb > 0:
+            from . import _lib
+            L = _lib.lib().cdll
+            world = _handle['world']
+            d = L.npb_dist_heap_alloc(ctypes.c_void_p(handle), 2 * world * op.maxb * 8)
+            f = L.npb_dist_heap_alloc(ctypes.c_void_p(handle), world * 8)
+            if d >= 0 and f >= 0:
+                seq = ctypes.c_ulonglong(0)
+                _seq_keep.append(seq)
+                m.halo.p2p_data, m.halo.p2p_flags = d, f
+                m.halo.seq = ctypes.addressof(seq)
     return m
+
+
+_seq_keep = []          # host exchange counters of the current solve's operators
+
+
+def _heap_reset():
+    """collective: recycle the symmetric heap between solves"""
+    import torch.distributed as dist
+    from . import _lib
+    from ._dev import stream_ptr
+    if not _handle['p2p']:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    _lib.lib().call('npb_dist_heap_reset', ctypes.c_void_p(_handle['ptr']), stream_ptr())
+    _seq_keep.clear()
+    dist.barrier()
 
 
 def _loc(A, rcuts, ccuts, replicated_cols=False):
@@ -320,6 +367,7 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
     torch.cuda.synchronize(); t1 = time.perf_counter()
     M = amg.LscPreconditioner(Jp, **(lsc_options or {}))
     torch.cuda.synchronize(); t2 = time.perf_counter()
+    _heap_reset()
     S = ShardedLsc(M, cuts)
     Jl = _loc(Jp, cuts, cuts)
     jm = amg.CsrMat()
@@ -346,7 +394,8 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
                setup_ms=1e3 * (t2 - t1), localize_ms=1e3 * (t3 - t2), krylov_ms=1e3 * (t4 - t3),
                gather_ms=1e3 * (t5 - t4), precond=M.describe(),
                first_replicated_level=(S.amg_a.first_rep, S.amg_l.first_rep),
-               halo=(Jl.maxb, S.A.maxb, S.Lm.maxb))
+               halo=(Jl.maxb, S.A.maxb, S.Lm.maxb),
+               exchange='direct stores into NVLink peer memory' if _handle['p2p'] else 'NCCL all-gather')
     last_info.clear()
     last_info.update(res)
     if res['status'] != 0:
