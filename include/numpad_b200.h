@@ -266,6 +266,8 @@ typedef struct npb_amg_level {      /* [host] */
     double *x, *x2, *b, *r;         /* work vectors of the level's size */
     int32_t gather, pad;            /* != 0: last row-sharded level; the levels below are  */
     const int64_t* offsets;         /* replicated: [host] world + 1 slice bounds of their rhs */
+    int64_t g_data, g_flags;        /* direct-store gather: heap offsets of 2 x offsets[world]  */
+    unsigned long long* g_seq;      /* doubles / world counters (< 0: NCCL); [host] counter     */
 } npb_amg_level;
 
 typedef struct npb_amg {            /* [host] */

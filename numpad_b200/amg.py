@@ -35,7 +35,8 @@ class AmgLevel(ctypes.Structure):
     _fields_ = [('A', CsrMat), ('P', CsrMat), ('R', CsrMat), ('dinv', ctypes.c_void_p),
                 ('x', ctypes.c_void_p), ('x2', ctypes.c_void_p), ('b', ctypes.c_void_p),
                 ('r', ctypes.c_void_p), ('gather', ctypes.c_int32), ('pad', ctypes.c_int32),
-                ('offsets', ctypes.c_void_p)]
+                ('offsets', ctypes.c_void_p), ('g_data', ctypes.c_int64),
+                ('g_flags', ctypes.c_int64), ('g_seq', ctypes.c_void_p)]
 
 
 class AmgStruct(ctypes.Structure):

@@ -531,6 +531,10 @@ struct npb_amg_level {
     // offsets[rank+1]) of the coarse right-hand side and the slices are all-gathered
     int32_t gather, pad;
     const int64_t* offsets;     // [host] world + 1 entries
+    // direct-store variant: the coarse right-hand side lives in the symmetric heap
+    // (2 parities x offsets[world] doubles at g_data, world arrival counters at g_flags)
+    int64_t g_data, g_flags;    // < 0: NCCL broadcasts into the next level's b
+    unsigned long long* g_seq;  // [host] exchange counter
 };
 
 struct npb_amg {
@@ -586,9 +590,17 @@ int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
         npb_amg_level& C = h->levels[l + 1];
         if (L.gather) {
             const npb_dist* d = (const npb_dist*)h->dist;
-            double* mine = C.b + L.offsets[d->rank];
-            rc = spmv_mat(L.R, L.r, nullptr, mine, 0, st);
-            if (!rc) rc = npb_dist_allgatherv(d, mine, C.b, L.offsets, st);
+            if (L.g_data >= 0 && npb_dist_heap_ptr(d, 0)) {
+                const unsigned long long seq = ++(*L.g_seq);
+                const int64_t elem_off = (int64_t)(seq & 1) * L.offsets[d->world];
+                C.b = npb_dist_heap_ptr(d, L.g_data) + elem_off;
+                rc = spmv_mat(L.R, L.r, nullptr, C.b + L.offsets[d->rank], 0, st);
+                if (!rc) rc = npb_dist_push_slice(d, L.g_data, L.g_flags, elem_off, L.offsets, seq, st);
+            } else {
+                double* mine = C.b + L.offsets[d->rank];
+                rc = spmv_mat(L.R, L.r, nullptr, mine, 0, st);
+                if (!rc) rc = npb_dist_allgatherv(d, mine, C.b, L.offsets, st);
+            }
         } else {
             rc = spmv_mat(L.R, L.r, nullptr, C.b, 0, st);
         }

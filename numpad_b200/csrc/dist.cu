@@ -131,6 +131,24 @@ k_push_halo(int n, const int32_t* __restrict__ idx, const double* __restrict__ x
     wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
 }
 
+// one CTA: the slice [off, off + n) of this rank's copy of a replicated vector -> the same
+// place in every peer's copy; then wait for the peers' slices
+__global__ void __launch_bounds__(1024)
+k_push_slice(int64_t n, peer_ptrs pp, int64_t data_off, int64_t flag_off, int64_t off, int world,
+             int rank, unsigned long long seq) {
+    const double* mine = reinterpret_cast<const double*>(pp.base[rank] + data_off) + off;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        const double v = mine[i];
+        for (int q = 0; q < world; ++q)
+            if (q != rank) reinterpret_cast<double*>(pp.base[q] + data_off)[off + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world && threadIdx.x != rank)
+        st_release_sys(reinterpret_cast<unsigned long long*>(pp.base[threadIdx.x] + flag_off) + rank, seq);
+    wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
+}
+
 // buf[0..count) <- sum over ranks (fixed rank order: identical bits on every rank)
 __global__ void __launch_bounds__(NPB_RED_SLOT)
 k_allreduce_p2p(double* __restrict__ buf, int count, peer_ptrs pp, int64_t data_off,
@@ -201,6 +219,21 @@ int npb_dist_allreduce_sum(const npb_dist* dc, double* buf, int count, cudaStrea
         return NPB_OK;
     }
     NPB_NCCL(g_nccl.allreduce(buf, buf, (size_t)count, NCCL_DOUBLE, NCCL_SUM, d->comm, st));
+    return NPB_OK;
+}
+
+double* npb_dist_heap_ptr(const npb_dist* d, int64_t off) {
+    return (d && d->heap[d->rank]) ? reinterpret_cast<double*>(d->heap[d->rank] + off) : nullptr;
+}
+
+// direct-store all-gather of a replicated vector living in the symmetric heap at data_off
+// (+ elem_off doubles for the parity): this rank's slice [offsets[rank], offsets[rank+1]) is
+// already written in its own copy
+int npb_dist_push_slice(const npb_dist* d, int64_t data_off, int64_t flag_off, int64_t elem_off,
+                        const int64_t* offsets, unsigned long long seq, cudaStream_t st) {
+    k_push_slice<<<1, 1024, 0, st>>>(offsets[d->rank + 1] - offsets[d->rank], make_peers(d), data_off,
+                                     flag_off, elem_off + offsets[d->rank], d->world, d->rank, seq);
+    NPB_COUNT_LAUNCH();
     return NPB_OK;
 }
 

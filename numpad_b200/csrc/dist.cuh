@@ -38,3 +38,6 @@ int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, 
 int npb_dist_allreduce_sum(const npb_dist* d, double* buf, int count, cudaStream_t st);
 int npb_dist_allgatherv(const npb_dist* d, const double* mine, double* full,
                         const int64_t* offsets, cudaStream_t st);
+double* npb_dist_heap_ptr(const npb_dist* d, int64_t off);
+int npb_dist_push_slice(const npb_dist* d, int64_t data_off, int64_t flag_off, int64_t elem_off,
+                        const int64_t* offsets, unsigned long long seq, cudaStream_t st);

@@ -126,27 +126,31 @@ def localize(indptr, indices, data, shape, rcuts, ccuts, rank, world, replicated
         op.send_idx = torch.zeros(0, dtype=torch.int32, device=dev)
         op.recv = torch.zeros(1, dtype=torch.float64, device=dev)
         return op
-    cc = torch.as_tensor(list(ccuts), dtype=torch.int64, device=dev)
     n_own = int(ccuts[rank + 1]) - int(ccuts[rank])
     # boundary sets of ALL ranks (every rank derives the same lists from the replicated
-    # matrix): columns referenced by a row of another rank
-    nnz = int(indices.numel())
-    cols = indices.to(torch.int64)
-    col_owner = torch.searchsorted(cc, cols, right=True) - 1
-    ent = torch.arange(nnz, dtype=torch.int64, device=dev)
-    row_owner = torch.searchsorted(kc, ent, right=True) - 1
-    row_owner.clamp_(max=world - 1)
-    remote = col_owner != row_owner
-    bcols = torch.unique(cols[remote])         # sorted
+    # matrix): columns referenced by a row of another rank.  The entries of rank q's rows
+    # are the contiguous range [kc[q], kc[q+1]): two comparisons per entry, no search.
+    rem = []
+    for q in range(world):
+        seg = indices[kcl[q]:kcl[q + 1]]
+        m = (seg < int(ccuts[q])) | (seg >= int(ccuts[q + 1]))
+        rem.append(seg[m])
+    bcols = torch.unique(torch.cat(rem)) if world > 1 else indices[:0]    # sorted
+    cc = torch.as_tensor(list(ccuts), dtype=bcols.dtype, device=dev)
     bstart = torch.searchsorted(bcols, cc)     # world + 1 segment bounds
-    counts = bstart[1:] - bstart[:-1]
-    maxb = int(counts.max().item()) if world > 0 else 0
-    lc, lo = cols[k0:k1], col_owner[k0:k1]
-    own = lo == rank
-    pos = torch.searchsorted(bcols, lc)
-    halo = n_own + lo * maxb + (pos - bstart[lo.clamp(0, world - 1)])
-    op.indices = torch.where(own, lc - int(ccuts[rank]), halo).to(torch.int32).contiguous()
-    b0, b1 = int(bstart[rank].item()), int(bstart[rank + 1].item())
+    bstart_l = [int(v) for v in bstart.tolist()]
+    maxb = max([bstart_l[q + 1] - bstart_l[q] for q in range(world)] + [0])
+    lc = indices[k0:k1]
+    own = (lc >= int(ccuts[rank])) & (lc < int(ccuts[rank + 1]))
+    new_idx = (lc - int(ccuts[rank])).to(torch.int32)
+    ridx = torch.nonzero(~own).reshape(-1)                 # the few entries that read a halo
+    if ridx.numel():
+        rc_ = lc[ridx]
+        lo = torch.searchsorted(cc, rc_, right=True) - 1
+        pos = torch.searchsorted(bcols, rc_)
+        new_idx[ridx] = (n_own + lo * maxb + (pos - bstart[lo])).to(torch.int32)
+    op.indices = new_idx.contiguous()
+    b0, b1 = bstart_l[rank], bstart_l[rank + 1]
     op.send_idx = (bcols[b0:b1] - int(ccuts[rank])).to(torch.int32).contiguous()
     op.n_own, op.maxb = n_own, maxb
     op.shape = (r1 - r0, n_own + world * maxb)
@@ -280,6 +284,16 @@ class ShardedHierarchy:
                 self.keep.append(off)
                 L.gather = 1
                 L.offsets = ctypes.cast(off, ctypes.c_void_p).value
+                L.g_data = L.g_flags = -1
+                if _handle['p2p']:
+                    from . import _lib
+                    Lc = _lib.lib().cdll
+                    d = Lc.npb_dist_heap_alloc(ctypes.c_void_p(handle), 2 * cn[world] * 8)
+                    f = Lc.npb_dist_heap_alloc(ctypes.c_void_p(handle), world * 8)
+                    if d >= 0 and f >= 0:
+                        seq = ctypes.c_ulonglong(0)
+                        _seq_keep.append(seq)
+                        L.g_data, L.g_flags, L.g_seq = d, f, ctypes.addressof(seq)
         s = self.struct = amg.AmgStruct()
         ctypes.memmove(ctypes.addressof(s), ctypes.addressof(h.struct), ctypes.sizeof(amg.AmgStruct))
         s.levels = ctypes.cast(self.arr, ctypes.POINTER(amg.AmgLevel))
