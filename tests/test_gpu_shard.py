@@ -1,0 +1,50 @@
+"""The row-sharded solve path (numpad_b200/shard.py + csrc/dist.cu) on ONE GPU: a world of
+one rank runs the same code -- library NCCL communicator, sliced operators, sharded V-cycles
+with replicated coarse levels, FGMRES with the all-reduce hook -- and must reproduce the
+plain single-GPU solve.  Multi-rank runs: tools/shard_check.py under torchrun."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_world_of_one_matches_single_gpu_solve():
+    import torch
+    import torch.distributed as dist
+    import numpad_b200 as npd
+    from numpad_b200 import linsolve, shard, precond
+    from numpad_b200.workloads.cavity import CavityProblem
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=0, world_size=1,
+                                device_id=torch.device('cuda', torch.cuda.current_device()))
+    try:
+        P = CavityProblem(npd, 160)
+        u0 = P.fixed_state()
+        u = npd.array(u0.copy())
+        res = P.residual(u, npd.array(u0), 1.0, 0)
+        J = npd.diff_dev(res, u).materialized()
+        b = res._dev.reshape(-1).contiguous()
+        precond._last['lsc'] = None
+        x1 = linsolve.solve(J, b, rtol=1e-11, precond='lsc', restart=100)
+        its1 = linsolve.last_info['iters']
+        old = shard.REPLICATE_BELOW
+        shard.REPLICATE_BELOW = 5000          # shard two levels, replicate the rest
+        try:
+            x2 = shard.solve(J, b, owner=P.partition(1), rtol=1e-11, restart=100)
+        finally:
+            shard.REPLICATE_BELOW = old
+        info = dict(shard.last_info)
+        assert info['first_replicated_level'][1] >= 2
+        rel = float((b - J.matvec(x2)).norm() / b.norm())
+        assert rel < 5e-11
+        assert abs(info['iters'] - its1) <= 2
+        assert float((x2 - x1).norm() / x1.norm()) < 1e-8
+    finally:
+        shard.shutdown()
+        if created:
+            dist.destroy_process_group()

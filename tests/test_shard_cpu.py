@@ -84,3 +84,67 @@ def test_strip_permutation_of_the_cavity_partition():
     for r in range(world):
         seg = perm[cuts[r]:cuts[r + 1]]
         assert bool((seg[1:] > seg[:-1]).all())
+
+
+# --------------------------------------------------------------------------- #
+# world-size-2/3 gloo: the same numbering with a REAL all-gather between processes
+# --------------------------------------------------------------------------- #
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from numpad_b200.workloads.cavity import CavityProblem
+        # a strip-permuted cavity-like operator: 2-D 9-point stencil on 3 interleaved fields
+        n1 = 14
+        T = sp.diags([-1.0, 2.5, -1.2], [-1, 0, 1], shape=(n1, n1))
+        a = sp.kron(sp.identity(n1), T) + sp.kron(T, sp.identity(n1)) + 0.1 * sp.kron(T, T)
+        a = sp.csr_matrix(sp.kron(np.array([[1, .2, 0], [.1, 1, .3], [0, .4, 1]]), a))
+        a.sort_indices()
+        n = a.shape[0]
+        owner = torch.from_numpy(np.tile((np.arange(n1 * n1) // n1 * world) // n1, 3).astype(np.int32))
+        perm, inv, cuts = shard.strip_permutation(owner, world)
+        ap = a[perm.numpy()][:, perm.numpy()].tocsr()
+        ap.sort_indices()
+        x = np.random.RandomState(5).standard_normal(n)
+        op = shard.localize(torch.from_numpy(ap.indptr.astype(np.int32)),
+                            torch.from_numpy(ap.indices.astype(np.int32)),
+                            torch.from_numpy(ap.data), ap.shape, cuts, cuts, rank, world)
+        x_own = torch.from_numpy(x[cuts[rank]:cuts[rank + 1]])
+        mine = torch.zeros(max(op.maxb, 1), dtype=torch.float64)
+        mine[:op.send_idx.numel()] = x_own[op.send_idx.long()]
+        slots = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(slots, mine)                    # what ncclAllGather / the direct stores do
+        gathered = torch.cat([s[:op.maxb] for s in slots]) if op.maxb else torch.zeros(0, dtype=torch.float64)
+        y = shard.local_matvec_reference(op, x_own, gathered)
+        want = (ap @ x)[cuts[rank]:cuts[rank + 1]]
+        assert np.allclose(y.numpy(), want, rtol=0, atol=1e-12), 'sharded SpMV'
+        # inner product: local partial sums + all-reduce == global dot
+        part = torch.tensor([float(y @ y)], dtype=torch.float64)
+        dist.all_reduce(part)
+        full = ap @ x
+        assert abs(part.item() - full @ full) <= 1e-10 * (full @ full), 'all-reduced dot'
+        ret[rank] = 'ok'
+    except Exception as e:                              # surface the failure in the parent
+        ret[rank] = repr(e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_spmv_over_gloo(world):
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_gloo_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert [ret.get(r) for r in range(world)] == ['ok'] * world, dict(ret)
