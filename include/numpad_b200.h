@@ -127,6 +127,28 @@ int npb_spadd_numeric(int64_t nrows, const int32_t* a_indptr,
 
 /* ---- S1: general csr * csr (scipy csr_matmat), expansion to COO; finish
  * with npb_coo_to_csr_* (prune = 1: csr_matmat never stores a zero). */
+/* row-batched SpGEMM with shared-memory expansion / sort / run sums (csrc/spgemm.cu): the
+ * fast path of the general product when no row of C has more than cap / 2 partial products.
+ * bound: ub[m], ubptr[m + 1], stats = {sum of ub, max ub}; numeric: brow[batches + 1],
+ * scratch tidx / tval of `total` entries, cnt / tstart[m]; the caller scans cnt into
+ * c_indptr, allocates C and calls compact. */
+int npb_spgemm_rows_cap(void);
+int64_t npb_spgemm_rows_batches(int64_t total, int64_t max_ub);
+int npb_spgemm_rows_bound(int64_t m, const int32_t* a_indptr, const int32_t* a_indices,
+                          const int32_t* b_indptr, int32_t* ub, int32_t* ubptr,
+                          int64_t* scan_ws, int64_t* stats, void* stream);
+int npb_spgemm_rows_numeric(int64_t m, int64_t total, int64_t max_ub, const int32_t* a_indptr,
+                            const int32_t* a_indices, const double* a_data,
+                            const npb_scales* a_scales, const int32_t* b_indptr,
+                            const int32_t* b_indices, const double* b_data,
+                            const npb_scales* b_scales, const int32_t* ubptr, int prune,
+                            int32_t* brow, int32_t* tidx, double* tval, int32_t* cnt,
+                            int32_t* tstart, void* stream);
+int npb_spgemm_rows_indptr(int64_t m, const int32_t* cnt, int32_t* c_indptr, int64_t* scan_ws,
+                           int64_t* stats, void* stream);
+int npb_spgemm_rows_compact(int64_t m, const int32_t* cnt, const int32_t* tstart,
+                            const int32_t* c_indptr, const int32_t* tidx, const double* tval,
+                            int32_t* c_indices, double* c_data, void* stream);
 int npb_spgemm_expand_symbolic(int64_t a_nnz, const int32_t* a_indices,
                                const int32_t* b_indptr, int32_t* counts,
                                int32_t* offsets, int64_t* scan_ws,

@@ -447,12 +447,47 @@ def _vstack(blocks, shape):
                   torch.cat([b.data for b in bm]), (), off, max(b.max_row for b in blocks), True)
 
 
+USE_SPGEMM_ROWS = True
+
+
+def _csr_times_csr_rows(A, B):
+    """general product, row-batched with shared-memory staging (csrc/spgemm.cu); None when a
+    row has too many partial products for a batch (the caller takes the sort-based path).
+    Same arithmetic and summation order as the sort-based path."""
+    m = A.shape[0]
+    L = _lib.lib().cdll
+    ub, ubptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+    stats = _empty(2, torch.int64)
+    _call('npb_spgemm_rows_bound', m, A.indptr, A.indices, B.indptr, ub, ubptr, _scan_ws(m), stats)
+    total, max_ub = _read_stats(stats)
+    if max_ub > L.npb_spgemm_rows_cap() // 2 or total > INT32_MAX - 8:
+        return None
+    nb = L.npb_spgemm_rows_batches(total, max_ub)
+    brow = _empty(nb + 1, torch.int32)
+    tidx, tval = _empty(total, torch.int32), _empty(total, torch.float64)
+    cnt, tstart = _empty(m, torch.int32), _empty(m, torch.int32)
+    _call('npb_spgemm_rows_numeric', m, total, max_ub, A.indptr, A.indices, A.data,
+          make_scales(A.scales), B.indptr, B.indices, B.data, make_scales(B.scales), ubptr, 1,
+          brow, tidx, tval, cnt, tstart)
+    ptr = _empty(m + 1, torch.int32)
+    st2 = _empty(2, torch.int64)
+    _call('npb_spgemm_rows_indptr', m, cnt, ptr, _scan_ws(m), st2)
+    nnz, max_row = _read_stats(st2)
+    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    _call('npb_spgemm_rows_compact', m, cnt, tstart, ptr, tidx, tval, idx, dat)
+    return DevCsr((A.shape[0], B.shape[1]), ptr, idx, dat, (), nnz, max_row, True)
+
+
 def _csr_times_csr(A, B):
-    """general product through expansion + sort (scipy csr_matmat semantics:
-    duplicates summed, exact-zero sums dropped)"""
+    """general product (scipy csr_matmat semantics: duplicates summed, exact-zero sums
+    dropped): row-batched in shared memory when every row fits, else expansion + sort"""
     shape = (A.shape[0], B.shape[1])
     if A.nnz == 0 or B.nnz == 0:
         return DevCsr.empty(shape)
+    if USE_SPGEMM_ROWS:
+        C = _csr_times_csr_rows(A, B)
+        if C is not None:
+            return C
     cnt, off = _empty(A.nnz, torch.int32), _empty(A.nnz + 1, torch.int32)
     stats = _empty(2, torch.int64)
     _call('npb_spgemm_expand_symbolic', A.nnz, A.indices, B.indptr, cnt, off,

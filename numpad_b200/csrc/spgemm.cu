@@ -1,0 +1,273 @@
+// Row-batched general SpGEMM  C = A B  with shared-memory staging.
+//
+// Role: the general `csr_matmat` of the chain rule (reference adstate.py:290-297 ->
+// scipy _sparsetools csr_matmat) and the Galerkin products R (A P) of the multigrid setup.
+// The first version expanded every partial product to HBM and ran a device-wide radix
+// sort over all of them (coo.cu) -- ~8 passes over 16 B per product.  Here consecutive
+// rows of A are batched so that a batch's partial products (<= CAP) fit in shared memory:
+// one CTA expands them there, sorts them by (row, column) with a block radix sort (stable:
+// duplicates stay in generation order, so sums are deterministic and ordered like the
+// expansion), adds the runs and writes only the unique entries -- one pass over A, the
+// referenced rows of B, and C.
+//
+// Algorithmic bytes: bytes(A) + (rows of B as referenced, mostly L2 hits) + bytes(C).
+// Rows whose products do not fit (ub > CAP / 2) make the caller fall back to coo.cu.
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+constexpr int SG_THREADS = 256;
+constexpr int SG_ITEMS = 8;
+constexpr int SG_CAP = SG_THREADS * SG_ITEMS;       // partial products per batch
+
+// ub[i] = max(1, sum over entries (i,k) of max(1, nnz(B_k))): products, entries and rows of a
+// batch are all bounded by the sum of ub over its rows
+__global__ void __launch_bounds__(256)
+k_sg_ub(int64_t m, const int32_t* __restrict__ aptr, const int32_t* __restrict__ aidx,
+        const int32_t* __restrict__ bptr, int32_t* __restrict__ ub, int64_t* __restrict__ stats) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int32_t u = 0;
+    if (i < m) {
+        int64_t s = 0;
+        for (int32_t e = aptr[i], e1 = aptr[i + 1]; e < e1; ++e) {
+            const int32_t k = aidx[e];
+            const int32_t l = bptr[k + 1] - bptr[k];
+            s += l > 1 ? l : 1;
+        }
+        u = (int32_t)(s < 1 ? 1 : (s > 0x3fffffff ? 0x3fffffff : s));
+        ub[i] = u;
+    }
+    // stats[1] = largest ub (the scan fills stats[0])
+    for (int d = 16; d; d >>= 1) u = max(u, __shfl_xor_sync(0xffffffffu, u, d));
+    if ((threadIdx.x & 31) == 0 && u > 0) atomicMax((long long*)(stats + 1), (long long)u);
+}
+
+__global__ void __launch_bounds__(256)
+k_sg_max(int64_t m, const int32_t* __restrict__ cnt, int64_t* __restrict__ stats) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int32_t u = i < m ? cnt[i] : 0;
+    for (int d = 16; d; d >>= 1) u = max(u, __shfl_xor_sync(0xffffffffu, u, d));
+    if ((threadIdx.x & 31) == 0 && u > 0) atomicMax((long long*)(stats + 1), (long long)u);
+}
+
+// batch b = rows [first r with ubptr[r] >= b T, first r with ubptr[r] >= (b+1) T)
+__global__ void __launch_bounds__(256)
+k_sg_batches(int64_t m, const int32_t* __restrict__ ubptr, int64_t T, int64_t nb,
+             int32_t* __restrict__ brow) {
+    int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (b > nb) return;
+    if (b == nb) { brow[b] = (int32_t)m; return; }
+    const int64_t target = b * T;
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)ubptr[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    brow[b] = (int32_t)lo;
+}
+
+struct sg_smem {
+    union {
+        typename cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>::TempStorage sort;
+        typename cub::BlockScan<int, SG_THREADS>::TempStorage scan;
+    } tmp;
+    unsigned long long key[SG_CAP + 1];
+    double val[SG_CAP];
+    int32_t rptr[SG_CAP + 1];
+};
+
+__global__ void __launch_bounds__(SG_THREADS)
+k_sg_numeric(const int32_t* __restrict__ brow, const int32_t* __restrict__ aptr,
+             const int32_t* __restrict__ aidx, const double* __restrict__ adat, npb_scales sa,
+             const int32_t* __restrict__ bptr, const int32_t* __restrict__ bidx,
+             const double* __restrict__ bdat, npb_scales sb, const int32_t* __restrict__ ubptr,
+             int key_bits, int prune, int32_t* __restrict__ tidx, double* __restrict__ tval,
+             int32_t* __restrict__ cnt, int32_t* __restrict__ tstart) {
+    extern __shared__ __align__(16) unsigned char sg_raw[];
+    sg_smem& S = *reinterpret_cast<sg_smem*>(sg_raw);
+    const int tid = threadIdx.x;
+    const int32_t r0 = brow[blockIdx.x], r1 = brow[blockIdx.x + 1];
+    const int nr = r1 - r0;
+    if (nr <= 0) return;
+    for (int i = tid; i <= nr; i += SG_THREADS) S.rptr[i] = aptr[r0 + i];
+    __syncthreads();
+    const int32_t e0 = S.rptr[0], ne = S.rptr[nr] - e0;       // <= SG_CAP by construction
+    // 1. products per entry, exclusive offsets (blocked arrangement: entry tid*ITEMS + j)
+    int len[SG_ITEMS], off[SG_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SG_ITEMS; ++j) {
+        const int e = tid * SG_ITEMS + j;
+        len[j] = 0;
+        if (e < ne) { const int32_t k = aidx[e0 + e]; len[j] = bptr[k + 1] - bptr[k]; }
+    }
+    int total;
+    cub::BlockScan<int, SG_THREADS>(S.tmp.scan).ExclusiveSum(len, off, total);
+    __syncthreads();
+    for (int p = total + tid; p < SG_CAP + 1; p += SG_THREADS) S.key[p] = ~0ull;
+    // 2. expansion into shared memory: key = (row - r0) << 32 | column
+#pragma unroll
+    for (int j = 0; j < SG_ITEMS; ++j) {
+        const int e = tid * SG_ITEMS + j;
+        if (e >= ne || len[j] == 0) continue;
+        int lo = 0, hi = nr;                       // row of entry e: last i with rptr[i] - e0 <= e
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.rptr[mid] - e0 <= e) lo = mid; else hi = mid; }
+        const unsigned long long rk = (unsigned long long)lo << 32;
+        const int32_t k = aidx[e0 + e];
+        const double a = npb_apply(sa, adat[e0 + e]);
+        const int32_t b0 = bptr[k];
+        for (int t = 0; t < len[j]; ++t) {
+            S.key[off[j] + t] = rk | (unsigned long long)(uint32_t)bidx[b0 + t];
+            S.val[off[j] + t] = __dmul_rn(a, npb_apply(sb, bdat[b0 + t]));
+        }
+    }
+    __syncthreads();
+    // 3. stable sort by (row, column)
+    unsigned long long k8[SG_ITEMS];
+    double v8[SG_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SG_ITEMS; ++j) { k8[j] = S.key[tid * SG_ITEMS + j]; v8[j] = S.val[tid * SG_ITEMS + j]; }
+    __syncthreads();
+    cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>(S.tmp.sort).Sort(k8, v8, 0, key_bits);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SG_ITEMS; ++j) { S.key[tid * SG_ITEMS + j] = k8[j]; S.val[tid * SG_ITEMS + j] = v8[j]; }
+    __syncthreads();
+    // 4. heads of equal-key runs: sum the run in order, decide survival, rank the survivors
+    double sum[SG_ITEMS];
+    int keep[SG_ITEMS], nkeep = 0;
+#pragma unroll
+    for (int j = 0; j < SG_ITEMS; ++j) {
+        const int p = tid * SG_ITEMS + j;
+        keep[j] = 0;
+        sum[j] = 0.0;
+        if (p < total && (p == 0 || S.key[p - 1] != k8[j])) {
+            double s = v8[j];
+            for (int q = p + 1; q < total && S.key[q] == k8[j]; ++q) s = __dadd_rn(s, S.val[q]);
+            sum[j] = s;
+            keep[j] = (!prune || s != 0.0) ? 1 : 0;
+            nkeep += keep[j];
+        }
+    }
+    int base;
+    cub::BlockScan<int, SG_THREADS>(S.tmp.scan).ExclusiveSum(nkeep, base);
+    const int64_t t0 = ubptr[r0];
+#pragma unroll
+    for (int j = 0; j < SG_ITEMS; ++j) {
+        if (!keep[j]) continue;
+        const int32_t row = r0 + (int32_t)(k8[j] >> 32);
+        tidx[t0 + base] = (int32_t)(uint32_t)k8[j];
+        tval[t0 + base] = sum[j];
+        // first kept entry of its row records where the row starts in the scratch arrays:
+        // the smallest position among the row's survivors
+        atomicMin(tstart + row, (int32_t)(t0 + base));
+        atomicAdd(cnt + row, 1);
+        ++base;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sg_compact(int64_t m, const int32_t* __restrict__ cnt, const int32_t* __restrict__ tstart,
+             const int32_t* __restrict__ cptr, const int32_t* __restrict__ tidx,
+             const double* __restrict__ tval, int32_t* __restrict__ cidx, double* __restrict__ cdat) {
+    // 8 lanes per row
+    const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
+    if (r >= m) return;
+    const int32_t n = cnt[r], s = tstart[r], d = cptr[r];
+    for (int32_t k = lane; k < n; k += 8) { cidx[d + k] = tidx[s + k]; cdat[d + k] = tval[s + k]; }
+}
+
+__global__ void __launch_bounds__(256)
+k_sg_init(int64_t m, int32_t* __restrict__ cnt, int32_t* __restrict__ tstart) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < m) { cnt[i] = 0; tstart[i] = 0x7fffffff; }
+}
+
+}  // namespace
+
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int npb_spgemm_rows_cap(void) { return SG_CAP; }
+
+// phase 1: ub (m), ubptr (m + 1) = exclusive scan; stats[0] = total products bound,
+// stats[1] = largest ub.  The caller checks stats[1] <= npb_spgemm_rows_cap() / 2.
+int npb_spgemm_rows_bound(int64_t m, const int32_t* a_indptr, const int32_t* a_indices,
+                          const int32_t* b_indptr, int32_t* ub, int32_t* ubptr,
+                          int64_t* scan_ws, int64_t* stats, void* stream) {
+    if (m <= 0) return NPB_ERR_ARG;
+    NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), ST(stream)));
+    k_sg_ub<<<npb_blocks(m, 256), 256, 0, ST(stream)>>>(m, a_indptr, a_indices, b_indptr, ub, stats);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("spgemm_rows_ub");
+    return npb_scan_launch(ub, ubptr, m, scan_ws, stats, ST(stream));
+}
+
+// phase 2: batches of rows (brow: nb + 1 entries, nb = total / T + 1 with T = cap - max_ub),
+// expansion + sort + run sums in shared memory; unique entries land in tidx / tval (`total`
+// entries of scratch) and cnt / tstart (m) describe them per row.  key_bits = 32 + bits
+// needed for the largest number of rows in a batch (<= cap).
+int npb_spgemm_rows_numeric(int64_t m, int64_t total, int64_t max_ub, const int32_t* a_indptr,
+                            const int32_t* a_indices, const double* a_data,
+                            const npb_scales* a_scales, const int32_t* b_indptr,
+                            const int32_t* b_indices, const double* b_data,
+                            const npb_scales* b_scales, const int32_t* ubptr, int prune,
+                            int32_t* brow, int32_t* tidx, double* tval, int32_t* cnt,
+                            int32_t* tstart, void* stream) {
+    cudaStream_t st = ST(stream);
+    if (max_ub > SG_CAP / 2) { npb_set_error("spgemm_rows: row with %lld products", (long long)max_ub); return NPB_ERR_ARG; }
+    const int64_t T = SG_CAP - max_ub;
+    const int64_t nb = total / T + 1;
+    k_sg_batches<<<npb_blocks(nb + 1, 256), 256, 0, st>>>(m, ubptr, T, nb, brow);
+    k_sg_init<<<npb_blocks(m, 256), 256, 0, st>>>(m, cnt, tstart);
+    static bool configured = false;
+    const size_t sh = sizeof(sg_smem) + 16;
+    if (!configured) {
+        NPB_CUDA(cudaFuncSetAttribute(k_sg_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        configured = true;
+    }
+    int rb = 1;
+    while ((1 << rb) < SG_CAP) ++rb;
+    k_sg_numeric<<<(unsigned)nb, SG_THREADS, sh, st>>>(brow, a_indptr, a_indices, a_data, *a_scales,
+                                                      b_indptr, b_indices, b_data, *b_scales, ubptr,
+                                                      32 + rb + 1, prune, tidx, tval, cnt, tstart);
+    NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH(); NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("spgemm_rows_numeric");
+    return NPB_OK;
+}
+
+// how many batches phase 2 uses (size of brow minus one)
+int64_t npb_spgemm_rows_batches(int64_t total, int64_t max_ub) {
+    const int64_t T = SG_CAP - max_ub;
+    return T > 0 ? total / T + 1 : -1;
+}
+
+// c_indptr = exclusive scan of cnt; stats = {nnz(C), longest row}
+int npb_spgemm_rows_indptr(int64_t m, const int32_t* cnt, int32_t* c_indptr, int64_t* scan_ws,
+                           int64_t* stats, void* stream) {
+    NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), ST(stream)));
+    if (m > 0) {
+        k_sg_max<<<npb_blocks(m, 256), 256, 0, ST(stream)>>>(m, cnt, stats);
+        NPB_COUNT_LAUNCH();
+    }
+    return npb_scan_launch(cnt, c_indptr, m, scan_ws, stats, ST(stream));
+}
+
+// phase 3 (after npb_spgemm_rows_indptr and the allocation of C)
+int npb_spgemm_rows_compact(int64_t m, const int32_t* cnt, const int32_t* tstart,
+                            const int32_t* c_indptr, const int32_t* tidx, const double* tval,
+                            int32_t* c_indices, double* c_data, void* stream) {
+    if (m <= 0) return NPB_OK;
+    k_sg_compact<<<npb_blocks(m * 8, 256), 256, 0, ST(stream)>>>(m, cnt, tstart, c_indptr, tidx, tval,
+                                                                c_indices, c_data);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("spgemm_rows_compact");
+    return NPB_OK;
+}
+
+}  // extern "C"

@@ -377,3 +377,40 @@ def test_aggregation_properties(dev, kind):
     sub = sp.csr_matrix((np.ones(same.sum()), (coo.row[same], coo.col[same])), shape=a.shape)
     ncomp, _ = connected_components(sub, directed=False)
     assert ncomp == n_agg
+
+
+@pytest.mark.parametrize('m,k,n,da,db', [(1, 1, 1, 1.0, 1.0), (300, 200, 250, 0.05, 0.05),
+                                         (20000, 15000, 18000, 0.0004, 0.0006),
+                                         (5000, 5000, 5000, 0.004, 0.01), (64, 3000, 4000, 0.3, 0.05)])
+def test_row_batched_spgemm(dev, m, k, n, da, db):
+    """csrc/spgemm.cu against scipy and against the sort-based path (bit-identical: same
+    products, same summation order): empty rows, exact cancellations (pruned), duplicate
+    columns inside a row, and a case whose rows exceed the batch capacity (falls back)"""
+    import torch
+    rng = np.random.RandomState(m + n)
+    a = rand_csr(rng, m, k, da, zero_frac=0.02)
+    b = rand_csr(rng, k, n, db)
+    # exact cancellations: duplicate a column of b with the opposite sign in a second row
+    if k > 10 and b.nnz > 0:
+        b = b.tolil(); b[1] = -b[0]; b = sp.csr_matrix(b); b.sort_indices()
+        a = a.tolil(); a[0] = 0; a[0, 0] = 2.0; a[0, 1] = 2.0; a = sp.csr_matrix(a); a.sort_indices()
+    A, B = dev.DevCsr.from_scipy(a), dev.DevCsr.from_scipy(b)
+    fast = dev._csr_times_csr_rows(A, B)
+    old = dev.USE_SPGEMM_ROWS
+    dev.USE_SPGEMM_ROWS = False
+    try:
+        slow = dev._csr_times_csr(A, B)
+    finally:
+        dev.USE_SPGEMM_ROWS = old
+    want = sp.csr_matrix(a @ b)
+    if fast is None:                       # a row with more partial products than half a batch
+        ub = (a != 0).astype(np.int64) @ np.maximum(np.diff(b.indptr), 1)
+        from numpad_b200 import _lib
+        assert ub.max() > _lib.lib().cdll.npb_spgemm_rows_cap() // 2
+        check(slow, want)
+        return
+    assert m != 64
+    check(fast, want)
+    f, s = fast.toscipy(), slow.toscipy()
+    assert np.array_equal(f.indptr, s.indptr) and np.array_equal(f.indices, s.indices)
+    assert np.array_equal(f.data, s.data)
