@@ -149,6 +149,11 @@ int npb_spgemm_rows_indptr(int64_t m, const int32_t* cnt, int32_t* c_indptr, int
 int npb_spgemm_rows_compact(int64_t m, const int32_t* cnt, const int32_t* tstart,
                             const int32_t* c_indptr, const int32_t* tidx, const double* tval,
                             int32_t* c_indices, double* c_data, void* stream);
+/* columns relabelled by an injective map, every (short) row re-sorted: the column half of a
+ * symmetric permutation P A P^T (shard.py); indptr is shared with the input */
+int npb_csr_relabel_sort_rows(int64_t m, const int32_t* indptr, const int32_t* indices,
+                              const double* data, const int32_t* map, int32_t* indices_out,
+                              double* data_out, void* stream);
 int npb_spgemm_expand_symbolic(int64_t a_nnz, const int32_t* a_indices,
                                const int32_t* b_indptr, int32_t* counts,
                                int32_t* offsets, int64_t* scan_ws,

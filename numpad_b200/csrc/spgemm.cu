@@ -187,6 +187,26 @@ k_sg_init(int64_t m, int32_t* __restrict__ cnt, int32_t* __restrict__ tstart) {
     if (i < m) { cnt[i] = 0; tstart[i] = 0x7fffffff; }
 }
 
+// out row r = in row r with every column c replaced by map[c], re-sorted by the new column
+// (insertion sort by one thread per row: for the short rows of a symmetric permutation
+// P A P^T, whose rows are almost sorted already).  map must be injective on each row.
+__global__ void __launch_bounds__(256)
+k_relabel_sort_rows(int64_t m, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                    const double* __restrict__ dat, const int32_t* __restrict__ map,
+                    int32_t* __restrict__ oidx, double* __restrict__ odat) {
+    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= m) return;
+    const int32_t s = ptr[r], e = ptr[r + 1];
+    for (int32_t k = s; k < e; ++k) {
+        const int32_t c = map[idx[k]];
+        const double v = dat[k];
+        int32_t p = k;
+        while (p > s && oidx[p - 1] > c) { oidx[p] = oidx[p - 1]; odat[p] = odat[p - 1]; --p; }
+        oidx[p] = c;
+        odat[p] = v;
+    }
+}
+
 }  // namespace
 
 #define ST(s) ((cudaStream_t)(s))
@@ -256,6 +276,19 @@ int npb_spgemm_rows_indptr(int64_t m, const int32_t* cnt, int32_t* c_indptr, int
         NPB_COUNT_LAUNCH();
     }
     return npb_scan_launch(cnt, c_indptr, m, scan_ws, stats, ST(stream));
+}
+
+// column relabel by an injective map with per-row re-sort (see k_relabel_sort_rows); the row
+// pointers are shared with the input
+int npb_csr_relabel_sort_rows(int64_t m, const int32_t* indptr, const int32_t* indices,
+                              const double* data, const int32_t* map, int32_t* indices_out,
+                              double* data_out, void* stream) {
+    if (m <= 0) return NPB_OK;
+    k_relabel_sort_rows<<<npb_blocks(m, 256), 256, 0, ST(stream)>>>(m, indptr, indices, data, map,
+                                                                   indices_out, data_out);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_relabel_sort_rows");
+    return NPB_OK;
 }
 
 // phase 3 (after npb_spgemm_rows_indptr and the allocation of C)

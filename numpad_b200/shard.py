@@ -351,6 +351,24 @@ class ShardedLsc:
         self.c_ctx = ctypes.addressof(s)
 
 
+def permuted(J, perm, inv):
+    """Pi J Pi^T for new index i = old index perm[i] (inv = inverse map): rows gathered in the
+    new order, columns relabelled and every row re-sorted in place (short rows), instead of a
+    device-wide sort of all entries"""
+    from ._dev import coo_to_csr, sel_jac, _sel_times_csr, _empty, _call, DevCsr
+    J = J.materialized()
+    if J.max_row > 64:
+        rows = inv[J.rows().long()].to(torch.int32)
+        cols = inv[J.indices.long()].to(torch.int32)
+        return coo_to_csr(J.shape, rows, cols, J.data, prune=False)
+    Jr = _sel_times_csr(sel_jac(perm.to(torch.int32), J.shape[0], full=True, monotone=False), J)
+    Jr = Jr.materialized()
+    idx, dat = _empty(Jr.nnz, torch.int32), _empty(Jr.nnz, torch.float64)
+    _call('npb_csr_relabel_sort_rows', Jr.shape[0], Jr.indptr, Jr.indices, Jr.data,
+          inv.to(torch.int32), idx, dat)
+    return DevCsr(J.shape, Jr.indptr, idx, dat, (), Jr.nnz, Jr.max_row, True)
+
+
 last_info = {}
 
 
@@ -374,9 +392,7 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
     owner = torch.as_tensor(owner).to(dev)
     perm, inv, cuts = strip_permutation(owner, world)
     # J' = Pi J Pi^T (strip-major), replicated
-    rows = inv[J.rows().long()].to(torch.int32)
-    cols = inv[J.indices.long()].to(torch.int32)
-    Jp = coo_to_csr(J.shape, rows, cols, J.data, prune=False)
+    Jp = permuted(J, perm, inv)
     bp = b.reshape(-1)[perm].contiguous()
     torch.cuda.synchronize(); t1 = time.perf_counter()
     M = amg.LscPreconditioner(Jp, **(lsc_options or {}))

@@ -20,7 +20,7 @@ J = npd.diff_dev(res, u).materialized()
 handle = shard.init()
 torch.manual_seed(0)
 perm, inv, cuts = shard.strip_permutation(torch.from_numpy(P.partition(world)).cuda(), world)
-Jp = coo_to_csr(J.shape, inv[J.rows().long()].to(torch.int32), inv[J.indices.long()].to(torch.int32), J.data, prune=False)
+Jp = shard.permuted(J, perm, inv)
 M = amg.LscPreconditioner(Jp)
 shard._heap_reset()
 S = shard.ShardedLsc(M, cuts)
