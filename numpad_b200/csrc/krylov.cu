@@ -37,7 +37,9 @@ struct spmv_epi {
     int32_t n_own;
 };
 
+template <bool HALO>
 __device__ __forceinline__ double ldx(const double* x, const spmv_epi& e, int32_t c) {
+    if (!HALO) return __ldg(x + c);
     return c < e.n_own ? __ldg(x + c) : __ldg(e.xh + (c - e.n_own));
 }
 
@@ -64,7 +66,7 @@ constexpr int SP_TILE = 3072;       // 24 KB of products -> 8 CTAs / SM
 // ROWS rows per CTA, TPR = 256 / ROWS threads cooperate on the sum of one row.
 // ROWS = 256 for the big operators (least overhead per row); 64 / 32 for the
 // small multigrid levels so that their grids still cover the 148 SMs.
-template <int ROWS>
+template <int ROWS, bool HALO>
 __global__ void __launch_bounds__(SP_THREADS)
 k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
               const int32_t* __restrict__ idx, const double* __restrict__ dat,
@@ -86,7 +88,7 @@ k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
         const int32_t lim = min(base + SP_TILE, k1);
 #pragma unroll 4
         for (int32_t k = base + tid; k < lim; k += SP_THREADS)
-            sprod[k - base] = dat[k] * ldx(x, epi, idx[k]);
+            sprod[k - base] = dat[k] * ldx<HALO>(x, epi, idx[k]);
         __syncthreads();
         const int32_t s = max(rs, base), e = min(re, lim);
         for (int32_t k = s + sub; k < e; k += TPR) acc += sprod[k - base];
@@ -108,7 +110,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 
-template <int ROWS>
+template <int ROWS, bool HALO>
 __global__ void __launch_bounds__(SP_THREADS)
 k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
                     const int32_t* __restrict__ idx, const double* __restrict__ dat,
@@ -144,7 +146,7 @@ k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
         const int32_t lo = max(base, k0);
 #pragma unroll 4
         for (int32_t k = lo + tid; k < lim; k += SP_THREADS)
-            sdat[k - base] *= ldx(x, epi, sidx[k - base]);
+            sdat[k - base] *= ldx<HALO>(x, epi, sidx[k - base]);
         __syncthreads();
         const int32_t s = max(rs, base), e = min(re, lim);
         for (int32_t k = s + sub; k < e; k += TPR) acc += sdat[k - base];
@@ -162,7 +164,7 @@ k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
 // and 4 values (2 x double2) per round and three rounds are in flight at once
 // (144 B per thread outstanding instead of 48).  Needs 16-byte aligned idx /
 // dat base pointers (checked by the launcher).
-template <int ROWS>
+template <int ROWS, bool HALO>
 __global__ void __launch_bounds__(SP_THREADS)
 k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
                  const int32_t* __restrict__ idx, const double* __restrict__ dat,
@@ -208,10 +210,10 @@ k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
             const int32_t k = base + (j * SP_THREADS + tid) * 4;
             if (k < lim) {
                 double2 p0, p1;
-                p0.x = da[j].x * ldx(x, epi, iv[j].x);
-                p0.y = da[j].y * ldx(x, epi, iv[j].y);
-                p1.x = db[j].x * ldx(x, epi, iv[j].z);
-                p1.y = db[j].y * ldx(x, epi, iv[j].w);
+                p0.x = da[j].x * ldx<HALO>(x, epi, iv[j].x);
+                p0.y = da[j].y * ldx<HALO>(x, epi, iv[j].y);
+                p1.x = db[j].x * ldx<HALO>(x, epi, iv[j].z);
+                p1.y = db[j].y * ldx<HALO>(x, epi, iv[j].w);
                 *reinterpret_cast<double2*>(sprod + (k - base)) = p0;
                 *reinterpret_cast<double2*>(sprod + (k - base) + 2) = p1;
             }
@@ -231,7 +233,7 @@ k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
 #include "spmv_tma.cuh"
 
 // (b) "vector" kernel for long rows: G lanes cooperate on one row.
-template <int G>
+template <int G, bool HALO>
 __global__ void __launch_bounds__(TPB)
 k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
        const int32_t* __restrict__ idx, const double* __restrict__ dat,
@@ -242,7 +244,7 @@ k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
     if (r < nrows) {
         const int32_t e = ptr[r + 1];
         for (int32_t k = ptr[r] + lane; k < e; k += G)
-            s = fma(dat[k], ldx(x, epi, idx[k]), s);
+            s = fma(dat[k], ldx<HALO>(x, epi, idx[k]), s);
     }
 #pragma unroll
     for (int d = G >> 1; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -407,6 +409,31 @@ int grid_for(int64_t n) {
 // 1: the auto dispatch prefers the TMA pipeline kernel (npb_spmv_set_default_tma)
 static int npb_spmv_default_tma = 1;
 
+// the non-persistent kernels (operators too small for the TMA pipeline, forced variants)
+template <bool HALO>
+static void spmv_small_dispatch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                                const double* dat, const double* x, const spmv_epi& e, double* y,
+                                int variant, double mean, bool aligned, cudaStream_t st) {
+    if ((variant == 4 || (variant == 0 && nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)) && aligned) {
+        k_spmv_stream_v4<256, HALO><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
+    } else if (variant == 3 && aligned) {
+        k_spmv_stream_async<256, HALO><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
+    } else if (variant == 1 || variant == 3 || variant == 4 || (variant == 0 && mean <= 96.0)) {
+        // rows per CTA: as many as keep >= ~4 CTAs per SM in flight and the
+        // row block inside a few shared-memory tiles
+        if (nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)
+            k_spmv_stream<256, HALO><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+        else if (nrows >= 64 * NPB_NUM_SMS * 4 && mean <= 64.0)
+            k_spmv_stream<64, HALO><<<npb_blocks(nrows, 64), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+        else
+            k_spmv_stream<32, HALO><<<npb_blocks(nrows, 32), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    } else if (mean <= 48.0) {
+        k_spmv<16, HALO><<<npb_blocks(nrows * 16, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    } else {
+        k_spmv<32, HALO><<<npb_blocks(nrows * 32, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    }
+}
+
 // ------------------------------------------------------------- internal API
 // y = epilogue(A x); see spmv_epi.  `variant`: 0 auto, 1 stream, 2 vector, 3 stream + cp.async
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
@@ -423,23 +450,10 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
                                     nrows >= tma_min_rows(mean)))) {
         int rc = spmv_tma_dispatch(nrows, nnz, ptr, idx, dat, x, e, y, st);
         if (rc) return rc;
-    } else if ((variant == 4 || (variant == 0 && nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)) && aligned) {
-        k_spmv_stream_v4<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
-    } else if (variant == 3 && aligned) {
-        k_spmv_stream_async<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, nnz, ptr, idx, dat, x, e, y);
-    } else if (variant == 1 || variant == 3 || variant == 4 || (variant == 0 && mean <= 96.0)) {
-        // rows per CTA: as many as keep >= ~4 CTAs per SM in flight and the
-        // row block inside a few shared-memory tiles
-        if (nrows >= 256 * NPB_NUM_SMS * 4 && mean <= 24.0)
-            k_spmv_stream<256><<<npb_blocks(nrows, 256), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
-        else if (nrows >= 64 * NPB_NUM_SMS * 4 && mean <= 64.0)
-            k_spmv_stream<64><<<npb_blocks(nrows, 64), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
-        else
-            k_spmv_stream<32><<<npb_blocks(nrows, 32), SP_THREADS, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
-    } else if (mean <= 48.0) {
-        k_spmv<16><<<npb_blocks(nrows * 16, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+    } else if (e.xh) {
+        spmv_small_dispatch<true>(nrows, nnz, ptr, idx, dat, x, e, y, variant, mean, aligned, st);
     } else {
-        k_spmv<32><<<npb_blocks(nrows * 32, TPB), TPB, 0, st>>>(nrows, ptr, idx, dat, x, e, y);
+        spmv_small_dispatch<false>(nrows, nnz, ptr, idx, dat, x, e, y, variant, mean, aligned, st);
     }
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("spmv");

@@ -70,7 +70,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-template <int ROWS, int RPT, class G>
+template <int ROWS, int RPT, class G, bool HALO>
 __global__ void __launch_bounds__(TM_THREADS, G::CTAS)
 k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict__ ptr,
            const int32_t* __restrict__ idx, const double* __restrict__ dat,
@@ -217,7 +217,7 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
 #pragma unroll
                     for (int g = 0; g < GB; ++g) {
                         const int32_t k = kk[j] + g * TPR;
-                        xv[j][g] = (k < ee[j]) ? ldx(x, epi, si[k]) : 0.0;
+                        xv[j][g] = (k < ee[j]) ? ldx<HALO>(x, epi, si[k]) : 0.0;
                     }
                 more = false;
 #pragma unroll
@@ -296,22 +296,32 @@ static inline int64_t tma_min_rows(double mean) {
     return (int64_t)s.rows * s.rpt * NPB_NUM_SMS * tma_ctas(g) * 2;
 }
 
-template <int ROWS, int RPT, class G>
-static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+template <int ROWS, int RPT, class G, bool HALO>
+static int launch_spmv_tma_h(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                            const double* dat, const double* x, const spmv_epi& e, double* y,
                            cudaStream_t st) {
     static bool configured = false;
     const size_t sh = sizeof(tm_smem<G>) + 128;
     if (!configured) {
-        NPB_CUDA(cudaFuncSetAttribute(k_spmv_tma<ROWS, RPT, G>,
+        NPB_CUDA(cudaFuncSetAttribute(k_spmv_tma<ROWS, RPT, G, HALO>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         configured = true;
     }
     const int64_t nunits = (nrows + ROWS * RPT - 1) / (ROWS * RPT);
     const int64_t cap = (int64_t)NPB_NUM_SMS * G::CTAS;
     const int grid = (int)(nunits < cap ? nunits : cap);
-    k_spmv_tma<ROWS, RPT, G><<<grid, TM_THREADS, sh, st>>>(nrows, nnz, nunits, ptr, idx, dat, x, e, y);
+    k_spmv_tma<ROWS, RPT, G, HALO><<<grid, TM_THREADS, sh, st>>>(nrows, nnz, nunits, ptr, idx, dat, x, e, y);
     return NPB_OK;
+}
+
+// the halo-aware instantiation only for row-sharded operators: the extra compare / select per
+// gather costs the single-GPU kernel 6 % (measured)
+template <int ROWS, int RPT, class G>
+static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                           const double* dat, const double* x, const spmv_epi& e, double* y,
+                           cudaStream_t st) {
+    return e.xh ? launch_spmv_tma_h<ROWS, RPT, G, true>(nrows, nnz, ptr, idx, dat, x, e, y, st)
+                : launch_spmv_tma_h<ROWS, RPT, G, false>(nrows, nnz, ptr, idx, dat, x, e, y, st);
 }
 
 template <class G>
