@@ -448,6 +448,45 @@ def _vstack(blocks, shape):
 
 
 USE_SPGEMM_ROWS = True
+# (rank, world, min_rows) while shard.solve builds its hierarchies: the large general products
+# are computed by row blocks, one per rank, and all-gathered (bit-identical to the local product)
+SPGEMM_SHARD = None
+
+
+def _csr_times_csr_sharded(A, B):
+    """rows [m q / world, m (q+1) / world) of A B on rank q, then an all-gather of the pieces;
+    None when a row has too many partial products on any rank (all ranks take the same path)"""
+    import torch.distributed as dist
+    rank, world, _ = SPGEMM_SHARD
+    m = A.shape[0]
+    cuts = [m * q // world for q in range(world + 1)]
+    A = A.materialized()
+    C = _csr_times_csr_rows(_row_block(A, cuts[rank], cuts[rank + 1]), B)
+    meta = torch.tensor([C.nnz if C is not None else -1, C.max_row if C is not None else 0],
+                        dtype=torch.int64, device=device())
+    allm = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(allm, meta)
+    allm = torch.stack(allm).tolist()
+    if any(a[0] < 0 for a in allm):
+        return None
+    nnzs = [int(a[0]) for a in allm]
+    koff = [0]
+    for v in nnzs:
+        koff.append(koff[-1] + v)
+    idx, dat = _empty(koff[-1], torch.int32), _empty(koff[-1], torch.float64)
+    cnt = _empty(m, torch.int32)
+    idx[koff[rank]:koff[rank + 1]] = C.indices
+    dat[koff[rank]:koff[rank + 1]] = C.data
+    cnt[cuts[rank]:cuts[rank + 1]] = C.indptr[1:] - C.indptr[:-1]
+    for q in range(world):
+        if cuts[q + 1] > cuts[q]:
+            dist.broadcast(cnt[cuts[q]:cuts[q + 1]], q)
+        if nnzs[q]:
+            dist.broadcast(idx[koff[q]:koff[q + 1]], q)
+            dist.broadcast(dat[koff[q]:koff[q + 1]], q)
+    ptr = torch.zeros(m + 1, dtype=torch.int32, device=device())
+    ptr[1:] = torch.cumsum(cnt, 0)
+    return DevCsr((m, B.shape[1]), ptr, idx, dat, (), koff[-1], max(int(a[1]) for a in allm), True)
 
 
 def _csr_times_csr_rows(A, B):
@@ -485,7 +524,10 @@ def _csr_times_csr(A, B):
     if A.nnz == 0 or B.nnz == 0:
         return DevCsr.empty(shape)
     if USE_SPGEMM_ROWS:
-        C = _csr_times_csr_rows(A, B)
+        if SPGEMM_SHARD is not None and A.shape[0] >= SPGEMM_SHARD[2] and not A.scales and not B.scales:
+            C = _csr_times_csr_sharded(A, B)
+        else:
+            C = _csr_times_csr_rows(A, B)
         if C is not None:
             return C
     cnt, off = _empty(A.nnz, torch.int32), _empty(A.nnz + 1, torch.int32)

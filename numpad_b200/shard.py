@@ -30,6 +30,10 @@ import torch
 # levels with fewer rows than this are replicated instead of sharded
 REPLICATE_BELOW = 120000
 
+# general products of the (otherwise replicated) multigrid setup with at least this many rows
+# are computed by row blocks across the ranks and all-gathered (0: never)
+SHARD_PRODUCTS_ABOVE = 500000
+
 # bytes of the symmetric heap for direct-store exchanges (0 / NPB_DIST_P2P=0: NCCL only)
 HEAP_BYTES = 64 << 20
 
@@ -395,7 +399,13 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
     Jp = permuted(J, perm, inv)
     bp = b.reshape(-1)[perm].contiguous()
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    M = amg.LscPreconditioner(Jp, **(lsc_options or {}))
+    from . import _dev
+    # the large Galerkin products of the setup are computed by row blocks, one per rank
+    _dev.SPGEMM_SHARD = (rank, world, SHARD_PRODUCTS_ABOVE) if world > 1 and SHARD_PRODUCTS_ABOVE else None
+    try:
+        M = amg.LscPreconditioner(Jp, **(lsc_options or {}))
+    finally:
+        _dev.SPGEMM_SHARD = None
     torch.cuda.synchronize(); t2 = time.perf_counter()
     _heap_reset()
     S = ShardedLsc(M, cuts)
