@@ -326,7 +326,7 @@ def run_ours(args):
                          'frac_of_nominal_8TBs': achieved / 8000.0},
             'phases': phases, 'clocks': clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # rank 0 at N = 1 only
             line['cpu_baseline'] = cpu_baseline(args.grid, args.sample_grid)
         print(json.dumps(line))
     if world > 1:

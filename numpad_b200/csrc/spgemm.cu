@@ -13,6 +13,7 @@
 // Algorithmic bytes: bytes(A) + (rows of B as referenced, mostly L2 hits) + bytes(C).
 // Rows whose products do not fit (ub > CAP / 2) make the caller fall back to coo.cu.
 #include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
 
 #include "common.cuh"
@@ -74,7 +75,9 @@ struct sg_smem {
     union {
         typename cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>::TempStorage sort;
         typename cub::BlockScan<int, SG_THREADS>::TempStorage scan;
+        typename cub::BlockReduce<int, SG_THREADS>::TempStorage red;
     } tmp;
+    int cmin, cmax;
     unsigned long long key[SG_CAP + 1];
     double val[SG_CAP];
     int32_t rptr[SG_CAP + 1];
@@ -109,6 +112,7 @@ k_sg_numeric(const int32_t* __restrict__ brow, const int32_t* __restrict__ aptr,
     __syncthreads();
     for (int p = total + tid; p < SG_CAP + 1; p += SG_THREADS) S.key[p] = ~0ull;
     // 2. expansion into shared memory: key = (row - r0) << 32 | column
+    int cmin = 0x7fffffff, cmax = 0;
 #pragma unroll
     for (int j = 0; j < SG_ITEMS; ++j) {
         const int e = tid * SG_ITEMS + j;
@@ -120,21 +124,47 @@ k_sg_numeric(const int32_t* __restrict__ brow, const int32_t* __restrict__ aptr,
         const double a = npb_apply(sa, adat[e0 + e]);
         const int32_t b0 = bptr[k];
         for (int t = 0; t < len[j]; ++t) {
-            S.key[off[j] + t] = rk | (unsigned long long)(uint32_t)bidx[b0 + t];
+            const int32_t c = bidx[b0 + t];
+            cmin = min(cmin, c);
+            cmax = max(cmax, c);
+            S.key[off[j] + t] = rk | (unsigned long long)(uint32_t)c;
             S.val[off[j] + t] = __dmul_rn(a, npb_apply(sb, bdat[b0 + t]));
         }
     }
+    // 3. stable sort by (row, column).  Keys are compressed to (row << cb) | (column - cmin)
+    // with cb = bits of the batch's column range: a batch of a stencil-like product spans a
+    // few thousand columns, so the radix sort runs over ~20 bits instead of 44
+    cmin = cub::BlockReduce<int, SG_THREADS>(S.tmp.red).Reduce(cmin, cub::Min());
     __syncthreads();
-    // 3. stable sort by (row, column)
+    cmax = cub::BlockReduce<int, SG_THREADS>(S.tmp.red).Reduce(cmax, cub::Max());
+    if (tid == 0) { S.cmin = cmin; S.cmax = cmax; }
+    __syncthreads();
+    cmin = S.cmin;
+    const unsigned span = total > 0 ? (unsigned)(S.cmax - cmin) : 0u;
+    const int cb = span ? 32 - __clz(span) : 1;
+    const int rbits = 32 - __clz((unsigned)nr);            // rows 0 .. nr-1, padding row nr
+    const unsigned long long cmask = (1ull << cb) - 1ull;
+    (void)key_bits;
     unsigned long long k8[SG_ITEMS];
     double v8[SG_ITEMS];
 #pragma unroll
-    for (int j = 0; j < SG_ITEMS; ++j) { k8[j] = S.key[tid * SG_ITEMS + j]; v8[j] = S.val[tid * SG_ITEMS + j]; }
+    for (int j = 0; j < SG_ITEMS; ++j) {
+        const int p = tid * SG_ITEMS + j;
+        const unsigned long long k = S.key[p];
+        k8[j] = p < total ? (((k >> 32) << cb) | (unsigned long long)((uint32_t)k - (uint32_t)cmin))
+                          : ((unsigned long long)nr << cb);
+        v8[j] = S.val[p];
+    }
     __syncthreads();
-    cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>(S.tmp.sort).Sort(k8, v8, 0, key_bits);
+    cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>(S.tmp.sort).Sort(k8, v8, 0, cb + rbits);
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < SG_ITEMS; ++j) { S.key[tid * SG_ITEMS + j] = k8[j]; S.val[tid * SG_ITEMS + j] = v8[j]; }
+    for (int j = 0; j < SG_ITEMS; ++j) {
+        // back to (row << 32) | column for the run sums below
+        k8[j] = ((k8[j] >> cb) << 32) | (unsigned long long)((uint32_t)(k8[j] & cmask) + (uint32_t)cmin);
+        S.key[tid * SG_ITEMS + j] = k8[j];
+        S.val[tid * SG_ITEMS + j] = v8[j];
+    }
     __syncthreads();
     // 4. heads of equal-key runs: sum the run in order, decide survival, rank the survivors
     double sum[SG_ITEMS];
