@@ -149,6 +149,13 @@ int npb_spgemm_rows_indptr(int64_t m, const int32_t* cnt, int32_t* c_indptr, int
 int npb_spgemm_rows_compact(int64_t m, const int32_t* cnt, const int32_t* tstart,
                             const int32_t* c_indptr, const int32_t* tidx, const double* tval,
                             int32_t* c_indices, double* c_data, void* stream);
+/* A times a selection with a non-monotone column map (map[c] < 0 drops column c, optional
+ * weights): per-row relabel + stable sort + duplicate sums in scratch (nnz(A) entries), then
+ * npb_spgemm_rows_indptr on cnt and npb_spgemm_rows_compact */
+int npb_csr_relabel_merge_rows(int64_t m, const int32_t* indptr, const int32_t* indices,
+                               const double* data, const npb_scales* scales, const int32_t* map,
+                               const double* weights, int prune, int32_t* tidx, double* tval,
+                               int32_t* cnt, int32_t* tstart, void* stream);
 /* columns relabelled by an injective map, every (short) row re-sorted: the column half of a
  * symmetric permutation P A P^T (shard.py); indptr is shared with the input */
 int npb_csr_relabel_sort_rows(int64_t m, const int32_t* indptr, const int32_t* indices,

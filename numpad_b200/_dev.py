@@ -390,6 +390,20 @@ def _csr_times_sel(A, S):
             _call('npb_csr_relabel_numeric', m, A.indptr, A.indices, A.data, sc, S.map, S.w,
                   ptr, idx, dat, zc)
             return _finish(DevCsr(shape, ptr, idx, dat, (), nnz, max_row), zc)
+    if A.max_row <= 48 and USE_SPGEMM_ROWS:
+        # non-monotone map, short rows: relabel + per-row sort + duplicate sums, no device-wide sort
+        m = A.shape[0]
+        tidx, tval = _empty(A.nnz, torch.int32), _empty(A.nnz, torch.float64)
+        cnt, tstart = _empty(m, torch.int32), _empty(m, torch.int32)
+        _call('npb_csr_relabel_merge_rows', m, A.indptr, A.indices, A.data, make_scales(A.scales),
+              S.map, S.w, 1, tidx, tval, cnt, tstart)
+        ptr = _empty(m + 1, torch.int32)
+        stats = _empty(2, torch.int64)
+        _call('npb_spgemm_rows_indptr', m, cnt, ptr, _scan_ws(m), stats)
+        nnz, max_row = _read_stats(stats)
+        idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+        _call('npb_spgemm_rows_compact', m, cnt, tstart, ptr, tidx, tval, idx, dat)
+        return DevCsr(shape, ptr, idx, dat, (), nnz, max_row, True)
     # general: relabel in COO form, drop, sort, merge duplicates, prune
     Am = A.materialized()
     cols = S.map[Am.indices.long()]

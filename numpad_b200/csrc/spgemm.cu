@@ -237,6 +237,45 @@ k_relabel_sort_rows(int64_t m, const int32_t* __restrict__ ptr, const int32_t* _
     }
 }
 
+// row r of A S for a selection S given as a column map (map[c] < 0: column dropped) with
+// optional weights w[c]: columns relabelled, the row re-sorted (stable insertion sort, one
+// thread per row), equal columns summed in input order, exact zeros dropped when prune.
+// Works in the scratch segment [ptr[r], ptr[r+1]) of tidx / tval; cnt[r] = entries kept.
+__global__ void __launch_bounds__(256)
+k_relabel_merge_rows(int64_t m, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                     const double* __restrict__ dat, npb_scales sc, const int32_t* __restrict__ map,
+                     const double* __restrict__ w, int prune, int32_t* __restrict__ tidx,
+                     double* __restrict__ tval, int32_t* __restrict__ cnt,
+                     int32_t* __restrict__ tstart) {
+    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= m) return;
+    const int32_t s = ptr[r], e = ptr[r + 1];
+    int32_t n = 0;
+    for (int32_t k = s; k < e; ++k) {
+        const int32_t c0 = idx[k];
+        const int32_t c = map[c0];
+        if (c < 0) continue;
+        double v = npb_apply(sc, dat[k]);
+        if (w) v = __dmul_rn(v, w[c0]);
+        int32_t p = s + n;
+        while (p > s && tidx[p - 1] > c) { tidx[p] = tidx[p - 1]; tval[p] = tval[p - 1]; --p; }
+        tidx[p] = c;
+        tval[p] = v;
+        ++n;
+    }
+    int32_t o = s;
+    for (int32_t k = s; k < s + n;) {
+        const int32_t c = tidx[k];
+        double sum = tval[k];
+        int32_t q = k + 1;
+        for (; q < s + n && tidx[q] == c; ++q) sum = __dadd_rn(sum, tval[q]);
+        if (!prune || sum != 0.0) { tidx[o] = c; tval[o] = sum; ++o; }
+        k = q;
+    }
+    cnt[r] = o - s;
+    tstart[r] = s;
+}
+
 }  // namespace
 
 #define ST(s) ((cudaStream_t)(s))
@@ -306,6 +345,21 @@ int npb_spgemm_rows_indptr(int64_t m, const int32_t* cnt, int32_t* c_indptr, int
         NPB_COUNT_LAUNCH();
     }
     return npb_scan_launch(cnt, c_indptr, m, scan_ws, stats, ST(stream));
+}
+
+// A times a selection with a non-monotone column map (aggregation maps, scatters): see
+// k_relabel_merge_rows.  tidx / tval: nnz(A) entries of scratch; then npb_spgemm_rows_indptr
+// on cnt and npb_spgemm_rows_compact.  For short rows (the sort is quadratic in the row length).
+int npb_csr_relabel_merge_rows(int64_t m, const int32_t* indptr, const int32_t* indices,
+                               const double* data, const npb_scales* scales, const int32_t* map,
+                               const double* weights, int prune, int32_t* tidx, double* tval,
+                               int32_t* cnt, int32_t* tstart, void* stream) {
+    if (m <= 0) return NPB_OK;
+    k_relabel_merge_rows<<<npb_blocks(m, 256), 256, 0, ST(stream)>>>(m, indptr, indices, data, *scales, map,
+                                                                    weights, prune, tidx, tval, cnt, tstart);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_relabel_merge_rows");
+    return NPB_OK;
 }
 
 // column relabel by an injective map with per-row re-sort (see k_relabel_sort_rows); the row
