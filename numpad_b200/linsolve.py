@@ -20,7 +20,12 @@ from ._dev import DevCsr, device, stream_ptr, _empty
 
 # knobs (also settable through solve(..., linear_options={...}))
 DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=60, maxiter=600, precond='auto',
-                verbose=False)
+                verbose=False,
+                # multi-GPU: owner[i] = rank of unknown i.  When set and torch.distributed runs
+                # with more than one rank, saddle-point systems too large for the direct solver
+                # are solved row-sharded over the ranks (shard.py); every rank calls solve()
+                # with the same replicated A and b and gets the same x back.
+                shard_owner=None)
 
 last_info = {}      # filled by every solve: iterations, residuals, method
 _hints = {'robust': False}
@@ -126,6 +131,30 @@ def _now():
     return time.perf_counter()
 
 
+def _solve_sharded(A, b, o):
+    """the row-sharded path of solve(); None when it does not apply or did not converge (every
+    rank takes the same decision: all of them see the same matrix and the same iteration)"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    from . import precond as _pc, amg, shard
+    if _pc.direct_feasible(A) or not bool((amg.diagonal(A) == 0).any()):
+        return None
+    try:
+        x = shard.solve(A, b, owner=o['shard_owner'], rtol=o['rtol'], restart=max(o['restart'], 100),
+                        maxiter=2 * max(o['restart'], 100))
+    except LinearSolveError:
+        _hints['robust'] = True        # convection-dominated: the replicated robust solver takes over
+        return None
+    last_info.clear()
+    last_info.update(shard.last_info)
+    if o['verbose']:
+        print('    linear solve [%s]: %d its, |r|/|b| = %.2e' %
+              (last_info['method'], last_info['iters'],
+               last_info['rnorm'] / max(last_info['bnorm'], 1e-300)))
+    return x
+
+
 def solve(A, b, transpose=False, **opts):
     """x = A^{-1} b (or A^{-T} b) for a DevCsr A and a device vector b."""
     o = dict(DEFAULTS)
@@ -136,6 +165,10 @@ def solve(A, b, transpose=False, **opts):
     n = A.shape[0]
     b = b.reshape(-1).contiguous()
     from . import precond as _pc
+    if o['shard_owner'] is not None and not _hints['robust'] and o['precond'] in ('auto', 'lsc'):
+        x = _solve_sharded(A, b, o)
+        if x is not None:
+            return x
     t0 = _now()
     if o['precond'] == 'lsc' and _hints['robust']:
         o['precond'] = 'lsc-robust'
