@@ -27,7 +27,7 @@ int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, 
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                 const double* dat, const double* x, int mode, const double* b,
                 const double* dinv, double omega, double* y, int variant, cudaStream_t st,
-                const npb_halo* halo);
+                const npb_halo* halo, const npb_wait* wait);
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st);
 
@@ -507,14 +507,15 @@ static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* 
     if (M.halo.dist) {
         npb_halo h = M.halo;
         const double* xh = nullptr;
-        int rc = npb_dist_halo_exchange(M.halo, x, st, &xh);
+        npb_wait w;
+        int rc = npb_dist_halo_exchange(M.halo, x, st, &xh, &w);   // publish; the SpMV waits
         if (rc) return rc;
         h.recv = const_cast<double*>(xh);
         return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y,
-                           0, st, &h);
+                           0, st, &h, &w);
     }
     return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y, 0,
-                       st, nullptr);
+                       st, nullptr, nullptr);
 }
 
 struct npb_amg_level {
@@ -680,7 +681,7 @@ int npb_mat_matvec_cb(void* ctx, const double* x, double* y, void* stream) {
 int npb_mat_halo_exchange(void* ctx, const double* x, void* stream) {
     const npb_csr_mat& M = *(const npb_csr_mat*)ctx;
     const double* xh = nullptr;
-    return M.halo.dist ? npb_dist_halo_exchange(M.halo, x, ST(stream), &xh) : NPB_OK;
+    return M.halo.dist ? npb_dist_halo_exchange(M.halo, x, ST(stream), &xh, nullptr) : NPB_OK;
 }
 
 // y = k V-cycles applied to x: usable directly as an npb_apply_fn

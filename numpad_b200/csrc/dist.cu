@@ -118,7 +118,7 @@ __device__ __forceinline__ void wait_peers(const unsigned long long* flags, int 
 __global__ void __launch_bounds__(1024)
 k_push_halo(int n, const int32_t* __restrict__ idx, const double* __restrict__ x, peer_ptrs pp,
             int64_t data_off, int64_t flag_off, int64_t slot, int world, int rank,
-            unsigned long long seq) {
+            unsigned long long seq, int wait) {
     for (int i = threadIdx.x; i < n; i += 1024) {
         const double v = x[idx[i]];
         for (int q = 0; q < world; ++q)
@@ -128,7 +128,8 @@ k_push_halo(int n, const int32_t* __restrict__ idx, const double* __restrict__ x
     __syncthreads();
     if (threadIdx.x < world && threadIdx.x != rank)
         st_release_sys(reinterpret_cast<unsigned long long*>(pp.base[threadIdx.x] + flag_off) + rank, seq);
-    wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
+    if (wait)
+        wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
 }
 
 // one CTA: the slice [off, off + n) of this rank's copy of a replicated vector -> the same
@@ -181,7 +182,9 @@ static inline peer_ptrs make_peers(const npb_dist* d) {
 }  // namespace
 
 // ---- internal API (dist.cuh) ------------------------------------------------------
-int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, const double** xh) {
+int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, const double** xh,
+                           npb_wait* wait) {
+    if (wait) wait->flags = nullptr;
     // boundary values of x -> this rank's slot of the gather buffer -> every rank
     const npb_dist* d = (const npb_dist*)h.dist;
     if (h.p2p_data >= 0 && d->heap[d->rank]) {
@@ -190,8 +193,14 @@ int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, 
         if (h.maxb > 0) {
             k_push_halo<<<1, 1024, 0, st>>>(h.n_send, h.send_idx, x, make_peers(d), h.p2p_data,
                                             h.p2p_flags, parity_off + (int64_t)d->rank * h.maxb,
-                                            d->world, d->rank, seq);
+                                            d->world, d->rank, seq, wait ? 0 : 1);
             NPB_COUNT_LAUNCH();
+            if (wait) {
+                wait->flags = reinterpret_cast<const unsigned long long*>(d->heap[d->rank] + h.p2p_flags);
+                wait->seq = seq;
+                wait->world = d->world;
+                wait->rank = d->rank;
+            }
         }
         *xh = reinterpret_cast<const double*>(d->heap[d->rank] + h.p2p_data) + parity_off;
         return NPB_OK;

@@ -33,8 +33,39 @@ struct npb_halo {
     unsigned long long* seq;
 };
 
-// publishes / fetches the boundary values of x; *xh = where the SpMV reads them
-int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, const double** xh);
+// what the consumer of a direct-store exchange still has to wait for: the arrival counters
+// flags[q] (q != rank) of this rank reaching seq.  flags == NULL: nothing (already waited).
+struct npb_wait {
+    const unsigned long long* flags;
+    unsigned long long seq;
+    int world, rank;
+};
+
+__device__ __forceinline__ unsigned long long npb_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// prologue of a kernel that reads a halo: threads 0 .. world-1 each watch one peer's arrival
+// counter (in LOCAL memory), then the CTA synchronises.  Call from ALL threads of the CTA.
+__device__ __forceinline__ void npb_wait_peers(const npb_wait& w) {
+    if (w.flags) {
+        const int q = threadIdx.x;
+        if (q < w.world && q != w.rank) {
+            unsigned long long spins = 0;
+            while (npb_ld_acquire_sys(w.flags + q) < w.seq)
+                if (++spins > (1ull << 31)) __trap();      // a dead peer must not hang the GPU
+        }
+        __syncthreads();
+    }
+}
+
+// publishes / fetches the boundary values of x; *xh = where the SpMV reads them.  With
+// `wait` != NULL a direct-store exchange only PUBLISHES and leaves the wait for the peers'
+// values to the consumer kernel (overlaps the NVLink latency with that kernel's launch).
+int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, const double** xh,
+                           npb_wait* wait);
 int npb_dist_allreduce_sum(const npb_dist* d, double* buf, int count, cudaStream_t st);
 int npb_dist_allgatherv(const npb_dist* d, const double* mine, double* full,
                         const int64_t* offsets, cudaStream_t st);

@@ -35,6 +35,7 @@ struct spmv_epi {
     // other ranks, gathered into xh; a single-GPU operator has n_own = INT32_MAX
     const double* xh;
     int32_t n_own;
+    npb_wait wait;      // HALO kernels: arrival counters to wait for before the first gather
 };
 
 template <bool HALO>
@@ -74,6 +75,7 @@ k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
     constexpr int TPR = SP_THREADS / ROWS;
     __shared__ int32_t sptr[ROWS + 1];
     __shared__ double sprod[SP_TILE];
+    if (HALO) npb_wait_peers(epi.wait);
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS;
     const int nr = (int)min((int64_t)ROWS, nrows - r0);
@@ -119,6 +121,7 @@ k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
     __shared__ int32_t sptr[ROWS + 1];
     __shared__ __align__(16) int32_t sidx[SP_TILE];
     __shared__ __align__(16) double sdat[SP_TILE];
+    if (HALO) npb_wait_peers(epi.wait);
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS;
     const int nr = (int)min((int64_t)ROWS, nrows - r0);
@@ -173,6 +176,7 @@ k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
     constexpr int ROUNDS = SP_TILE / (SP_THREADS * 4);
     __shared__ int32_t sptr[ROWS + 1];
     __shared__ __align__(16) double sprod[SP_TILE];
+    if (HALO) npb_wait_peers(epi.wait);
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS;
     const int nr = (int)min((int64_t)ROWS, nrows - r0);
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(TPB)
 k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
        const int32_t* __restrict__ idx, const double* __restrict__ dat,
        const double* x, spmv_epi epi, double* y) {
+    if (HALO) npb_wait_peers(epi.wait);
     const int lane = threadIdx.x & (G - 1);
     const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
     double s = 0.0;
@@ -439,10 +444,11 @@ static void spmv_small_dispatch(int64_t nrows, int64_t nnz, const int32_t* ptr, 
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                 const double* dat, const double* x, int mode, const double* b,
                 const double* dinv, double omega, double* y, int variant, cudaStream_t st,
-                const npb_halo* halo) {
+                const npb_halo* halo, const npb_wait* wait) {
     if (nrows <= 0) return NPB_OK;
-    spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff};
+    spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
     if (halo && halo->dist) { e.xh = halo->recv; e.n_own = (int32_t)halo->n_own; }
+    if (wait && e.xh) e.wait = *wait;
     const double mean = (double)nnz / (double)nrows;
     const bool aligned = (((uintptr_t)idx | (uintptr_t)dat) & 15) == 0;
     const bool tma_ok = aligned && nnz < (int64_t)0x7fffffff - 2 * TM_CAP_MAX;
@@ -463,7 +469,7 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
 int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                     const double* dat, const double* x, const double* b, double* y,
                     int mode, cudaStream_t st) {
-    return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st, nullptr);
+    return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st, nullptr, nullptr);
 }
 
 // scratch: RED_BLOCKS*KC doubles of partials followed by one uint ticket
@@ -540,7 +546,7 @@ int npb_spmv_set_tma_geometry(int g) {
 int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                      const double* data, const double* x, double* y, int variant, void* stream) {
     return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, 0, nullptr, nullptr, 0.0, y, variant,
-                       ST(stream), nullptr);
+                       ST(stream), nullptr, nullptr);
 }
 
 // y = epilogue(A x) with a forced kernel variant (0 = auto):
@@ -553,7 +559,7 @@ int npb_spmv_epilogue(int64_t nrows, int64_t nnz, const int32_t* indptr, const i
         return NPB_ERR_ARG;
     }
     return npb_spmv_ex(nrows, nnz, indptr, indices, data, x, mode, b, dinv, omega, y, variant,
-                       ST(stream), nullptr);
+                       ST(stream), nullptr, nullptr);
 }
 
 // y = b - A x
