@@ -318,7 +318,7 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'Newton iters/sec', 'h2d_bytes_per_step': 16 * n,
                     'd2h_bytes_per_step': 8 * n, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_spmv_tma (persistent TMA-pipelined CSR SpMV, here of the Jacobian; all its instances together: 51 % of the device time of a step, profiles/)',
+            'roofline': {'bound': 'hbm', 'kernel': 'k_spmv_tma (persistent TMA-pipelined CSR SpMV, here of the Jacobian; all its instances together: 56 % of the device time of a step, profiles/r1_launches_cavity2048_newton_step.txt)',
                          'achieved': achieved, 'peak': peak,
                          'peak_source': 'measured' if peaks else 'fallback',
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
