@@ -327,7 +327,8 @@ typedef struct npb_lsc {            /* [host] ctx of npb_lsc_apply_cb */
     const double* a_dinv;
     const npb_amg* amg_a;
     const npb_amg* amg_l;
-    int32_t cycles_a, cycles_l;     /* A: stationary V-cycles; L: V-cycle-preconditioned CG steps */
+    int32_t cycles_a, cycles_l;     /* A: stationary V-cycles; L: V-cycle-preconditioned CG steps
+                                     * (first solve in the low 16 bits, second in the high 16; 0: same) */
     double* wv[5];
     double* wp[8];
     double* scal;                   /* 4 device doubles */

@@ -341,6 +341,8 @@ class LscPreconditioner:
         s.a_gmres = self.a_gmres
         if self.a_gmres > 0:
             s.a_work, s.a_work_bytes = self.a_work.data_ptr(), self.a_work.numel()
+        if isinstance(cycles_l, (tuple, list)):      # (first L-solve, second L-solve)
+            cycles_l = int(cycles_l[0]) | (int(cycles_l[1]) << 16)
         s.cycles_a, s.cycles_l = int(cycles_a), int(cycles_l)
         for k in range(5):
             s.wv[k] = self.wv[k].data_ptr()

@@ -766,13 +766,17 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
         k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, rp);
         NPB_COUNT_LAUNCH();
         // p1 = L^-1 r_P            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
-        if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, rp, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
+        // cycles_l: CG steps of the first L-solve in the low 16 bits, of the second one in
+        // the high 16 bits (0: the same)
+        const int cl1 = c->cycles_l & 0xffff;
+        const int cl2 = (c->cycles_l >> 16) ? (c->cycles_l >> 16) : cl1;
+        if ((rc = amg_pcg(c->amg_l, c->Lm, cl1, rp, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         // q = D A G p1
         if ((rc = spmv_mat(c->G, p1, nullptr, t1, 0, st))) return rc;
         if ((rc = spmv_mat(c->A, t1, nullptr, t2, 0, st))) return rc;
         if ((rc = spmv_mat(c->D, t2, nullptr, q, 0, st))) return rc;
         // p = -L^-1 q
-        if ((rc = amg_pcg(c->amg_l, c->Lm, c->cycles_l, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
+        if ((rc = amg_pcg(c->amg_l, c->Lm, cl2, q, p1, s1, s2, s3, s4, c->scal, c->red, st))) return rc;
         if ((rc = npb_axpby_launch(np, 0.0, p1, -1.0, p1, st))) return rc;
         // r_V <- r_V - G p
         if ((rc = spmv_mat(c->G, p1, rv, rv, 1, st))) return rc;

@@ -17,6 +17,7 @@ for cfg in a.configs.split(';'):
     agl = vals[7] if len(vals) > 7 else 'mis1'
     aga = vals[8] if len(vals) > 8 else 'mis1'
     nua = int(vals[9]) if len(vals) > 9 else 2
+    vals[1] = str(int(vals[1].split('+')[0]) | (int(vals[1].split('+')[1]) << 16)) if '+' in vals[1] else vals[1]
     ca, cl, nul, sm, ap_, apa = ([int(v) for v in vals[:6]] + [1, 1])[:6]
     torch.cuda.synchronize(); t0 = time.perf_counter()
     M = amg.LscPreconditioner(J, cycles_a=ca, cycles_l=cl, nu_l=nul, smooth_a=bool(sm), agg_passes=ap_, agg_passes_a=apa, p_trunc=ptr_, agg_l=agl, agg_a=aga, nu_a=nua)
@@ -24,5 +25,5 @@ for cfg in a.configs.split(';'):
     x, info = linsolve.fgmres(J, b, precond=M, rtol=1e-10, restart=60, maxiter=600)
     torch.cuda.synchronize(); t2 = time.perf_counter()
     print('agg %s/%s nu_a=%d ' % (agl, aga, nua), end='')
-    print('grid %d cycles_a=%d pcg_l=%d nu_l=%d smooth_a=%d passes(L,A)=%d,%d trunc=%.2f: its %d status %d setup %.0f ms krylov %.0f ms | %s'
+    print('grid %d cycles_a=%d pcg_l=%x nu_l=%d smooth_a=%d passes(L,A)=%d,%d trunc=%.2f: its %d status %d setup %.0f ms krylov %.0f ms | %s'
           % (a.grid, ca, cl, nul, sm, ap_, apa, ptr_, info['iters'], info['status'], 1e3*(t1-t0), 1e3*(t2-t1), M.describe()), flush=True)
