@@ -272,7 +272,7 @@ def _submatrix(J, rows, colmap, ncols):
 class LscPreconditioner:
     """Block preconditioner for J = [[A, G], [D, 0]] split by zero diagonal."""
 
-    def __init__(self, J, cycles_a=1, cycles_l=4, theta_a=0.25, nu_a=4, nu_l=1, smooth_a=True,
+    def __init__(self, J, cycles_a=1, cycles_l=(3, 4), theta_a=0.25, nu_a=4, nu_l=1, smooth_a=True,
                  reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None, p_trunc=0.1,
                  agg_l='mis1', agg_a='mis2'):
         J = J.materialized()
