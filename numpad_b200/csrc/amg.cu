@@ -721,6 +721,12 @@ struct npb_lsc {
     int64_t a_work_bytes;
 };
 
+// the host structs above are declared a second time in include/numpad_b200.h (and mirrored
+// with ctypes, tests/test_abi.py): a one-sided edit must not compile
+static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 112, "npb_csr_mat layout");
+static_assert(sizeof(npb_amg_level) == 416 && sizeof(npb_amg) == 48, "npb_amg layout");
+static_assert(sizeof(npb_amg_precond) == 144 && sizeof(npb_lsc) == 664, "npb_lsc layout");
+
 // y = d .* x as an npb_apply_fn (Jacobi preconditioner; ctx = npb_diag_ctx)
 struct npb_diag_ctx { int64_t n; const double* d; };
 typedef npb_diag_ctx diag_ctx;

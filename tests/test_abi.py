@@ -74,3 +74,33 @@ def test_rcm_host():
     q = reverse_cuthill_mckee(A, symmetric_mode=True)
     C = A[q][:, q].tocoo()
     assert bw[0] <= 1.5 * (C.row - C.col).max()
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """the ctypes mirrors of the host structs (amg.py, _lib.py) have the size and the field
+    offsets the C header gives them: compile a probe against include/numpad_b200.h with gcc"""
+    import shutil
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc unavailable')
+    from numpad_b200 import amg
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [('npb_halo', amg.Halo), ('npb_csr_mat', amg.CsrMat), ('npb_amg_level', amg.AmgLevel),
+             ('npb_amg', amg.AmgStruct), ('npb_amg_precond', amg.AmgPrecondStruct),
+             ('npb_lsc', amg.LscStruct), ('npb_csr_view', _lib.CsrView),
+             ('npb_krylov_ops', _lib.KrylovOps), ('npb_krylov_info', _lib.KrylovInfo),
+             ('npb_scales', _lib.Scales)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "numpad_b200.h"', 'int main(void) {']
+    for name, cls in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ['return 0; }']
+    src = tmp_path / 'probe.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'probe'
+    subprocess.check_call(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, cls in pairs:
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for fname, _ in cls._fields_:
+            assert int(got['%s.%s' % (name, fname)]) == getattr(cls, fname).offset, (name, fname)
