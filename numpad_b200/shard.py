@@ -16,10 +16,13 @@ so iteration counts do not depend on the number of GPUs -- unlike the block-Jaco
 preconditioner of the reference's MpiJacobian.approx_solve (admpisolve.py:167-172),
 which the saddle-point structure of the cavity Jacobian does not tolerate.
 
-This round the SETUP is replicated: every rank builds the same global hierarchies
-(deterministic kernels) and slices its rows out.  The slicing logic (`localize`) is
-plain torch and is tested on CPU; the halo numbering it produces is what
-`npb_halo` (include/numpad_b200.h) documents.
+This round most of the SETUP is replicated: every rank builds the same global hierarchies
+(deterministic kernels) and slices its rows out; only the large general products of the
+Galerkin operators are computed by row blocks, one per rank, and all-gathered
+(`_dev._csr_times_csr_sharded`, bit-identical to the local product).  The slicing logic
+(`localize`) is plain torch and is tested on CPU; the halo numbering it produces is what
+`npb_halo` (include/numpad_b200.h) documents.  Exchanges go by direct stores into NVLink peer
+memory through a symmetric CUDA-IPC heap when the ranks share a node (<= 8), else NCCL.
 """
 import ctypes
 import os
