@@ -323,6 +323,60 @@ k_dot_multi(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
     }
 }
 
+// same for few vectors (kc <= KS: the CG inner products and norms, the first Gram-Schmidt
+// steps): the general kernel keeps only kc + 1 eight-byte loads in flight per thread, which
+// leaves a one- or two-vector product latency-bound; here every thread moves two elements
+// with 128-bit loads and two such pairs per round.  n even, V / w / ld 16-byte aligned.
+template <int KS>
+__global__ void __launch_bounds__(TPB)
+k_dot_few(int64_t n2, int kc, const double* __restrict__ V, int64_t ld,
+          const double* __restrict__ w, double* __restrict__ partial,
+          unsigned int* __restrict__ ticket, double* __restrict__ out) {
+    __shared__ double smem[(TPB / 32) * KS];
+    double acc[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) acc[j] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n2; i += 2 * stride) {
+        const int64_t i1 = i + stride;
+        const bool two = i1 < n2;
+        const double2 wa = w2[i];
+        const double2 wb = two ? w2[i1] : make_double2(0.0, 0.0);
+        double2 va[KS], vb[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            va[j] = vb[j] = make_double2(0.0, 0.0);
+            if (j < kc) {
+                const double2* v2 = reinterpret_cast<const double2*>(V + (int64_t)j * ld);
+                va[j] = v2[i];
+                if (two) vb[j] = v2[i1];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            acc[j] = fma(va[j].x, wa.x, acc[j]);
+            acc[j] = fma(va[j].y, wa.y, acc[j]);
+            acc[j] = fma(vb[j].x, wb.x, acc[j]);
+            acc[j] = fma(vb[j].y, wb.y, acc[j]);
+        }
+    }
+    block_sum<KS>(acc, smem);
+    if (threadIdx.x < kc) partial[(int64_t)blockIdx.x * KC + threadIdx.x] = smem[threadIdx.x];
+    if (last_block(ticket)) {
+        __threadfence();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int j = warp; j < kc; j += TPB / 32) {
+            double t = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += partial[(int64_t)b * KC + j];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (lane == 0) out[j] = t;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
 // w += sum_j hs[j] V_j (j < k, hs = sign * h), and out_norm2 = ||w_new||^2.
 // Two elements per thread (128-bit loads) and four basis vectors per round: 8 x 16 B
 // in flight per thread -- the kernel streams (k + 2) vectors and has nothing to hide
@@ -480,11 +534,19 @@ static inline unsigned int* red_ticket(void* scratch) {
 
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st) {
+    const bool vec = (n % 2 == 0) && ((((uintptr_t)V | (uintptr_t)w) & 15) == 0) && (ld % 2 == 0 || k <= 1);
     for (int j0 = 0; j0 < k; j0 += KC) {
         int kc = k - j0 < KC ? k - j0 : KC;
-        k_dot_multi<<<grid_for(n), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
-                                                 red_partial(scratch), red_ticket(scratch),
-                                                 out + j0);
+        if (vec && kc <= 2 && n >= 4096)
+            k_dot_few<2><<<grid_for(n / 4), TPB, 0, st>>>(n / 2, kc, V + (int64_t)j0 * ld, ld, w,
+                                                        red_partial(scratch), red_ticket(scratch), out + j0);
+        else if (vec && kc <= 6 && n >= 4096)
+            k_dot_few<6><<<grid_for(n / 4), TPB, 0, st>>>(n / 2, kc, V + (int64_t)j0 * ld, ld, w,
+                                                        red_partial(scratch), red_ticket(scratch), out + j0);
+        else
+            k_dot_multi<<<grid_for(n), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
+                                                     red_partial(scratch), red_ticket(scratch),
+                                                     out + j0);
         NPB_COUNT_LAUNCH();
     }
     NPB_CHECK_LAUNCH("dot_multi");
