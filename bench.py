@@ -274,8 +274,14 @@ def run_ours(args):
     L = _lib.lib().cdll
     with Clocks(local) as clk:
         L.npb_launch_count_reset()
+        L.npb_profile_matvec(1)            # events around the Jacobian SpMV inside the timed steps
         ms = timed(step_resident, args.steps)
         launches = int(L.npb_launch_count())
+        L.npb_profile_matvec(0)
+        import ctypes
+        tot_ms, cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
+        L.npb_profile_matvec_read(ctypes.byref(tot_ms), ctypes.byref(cnt))
+        ms_spmv_insitu = tot_ms.value / cnt.value if cnt.value else None
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
         # ---- roofline of the dominant Krylov building block: CSR SpMV of J
@@ -294,7 +300,14 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
-    achieved = spmv_bytes / (ms_spmv * 1e-3) / 1e9
+    standalone = spmv_bytes / (ms_spmv * 1e-3) / 1e9
+    # headline: the launch as it ran inside the timed Newton steps; the back-to-back loop
+    # after the region (same kernel, same matrix) is reported beside it
+    if ms_spmv_insitu:
+        achieved, ms_roof, how = spmv_bytes / (ms_spmv_insitu * 1e-3) / 1e9, ms_spmv_insitu, \
+            'CUDA events around each Jacobian SpMV launch of the Krylov loop inside the timed steps (%d launches)' % cnt.value
+    else:
+        achieved, ms_roof, how = standalone, ms_spmv, 'back-to-back loop of 50 launches after the timed steps'
     # DRAM traffic of this kernel from the committed `ncu --set full` capture
     # (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch)
     traffic = None
@@ -322,7 +335,9 @@ def run_ours(args):
                          'achieved': achieved, 'peak': peak,
                          'peak_source': 'measured' if peaks else 'fallback',
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'bytes_per_launch': spmv_bytes, 'us_per_launch': 1e3 * ms_spmv,
+                         'bytes_per_launch': spmv_bytes, 'us_per_launch': 1e3 * ms_roof,
+                         'measured': how, 'standalone_gbs': standalone,
+                         'standalone_us_per_launch': 1e3 * ms_spmv,
                          'frac_of_nominal_8TBs': achieved / 8000.0},
             'phases': phases, 'clocks': clocks,
         }

@@ -260,6 +260,10 @@ typedef struct npb_krylov_info {         /* [host] */
 } npb_krylov_info;
 
 int npb_csr_matvec_cb(void* ctx, const double* x, double* y, void* stream);
+/* in-situ timing of npb_csr_matvec_cb launches (CUDA events on the launching stream):
+ * npb_profile_matvec(1) starts / resets, (0) stops; _read synchronises and sums */
+int npb_profile_matvec(int on);
+int npb_profile_matvec_read(double* total_ms, int64_t* count);
 int64_t npb_fgmres_workspace_bytes(int64_t n, int restart, int flexible);
 int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
                int restart, int maxiter, double rtol, double atol, int flexible,

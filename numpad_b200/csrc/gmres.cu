@@ -61,10 +61,47 @@ struct npb_krylov_info {
     double bnorm, rnorm0, rnorm; // ||b||, initial and final TRUE residual norms
 };
 
+// In-situ timing of the operator SpMV of the Krylov loop (bench.py's roofline: the average
+// duration of this launch INSIDE the timed steps): CUDA events around the launch, on the
+// launching stream, from a pool created on first use; read back after the region.
+static int g_prof_on = 0;
+static std::vector<cudaEvent_t> g_prof_ev;
+static size_t g_prof_used = 0;
+
+int npb_profile_matvec(int on) {
+    if (on && g_prof_ev.empty()) {
+        g_prof_ev.resize(2 * 4096);
+        for (auto& e : g_prof_ev)
+            if (cudaEventCreate(&e) != cudaSuccess) { g_prof_ev.clear(); return NPB_ERR_CUDA; }
+    }
+    if (on) g_prof_used = 0;
+    g_prof_on = on ? 1 : 0;
+    return NPB_OK;
+}
+
+// total milliseconds and number of timed launches since npb_profile_matvec(1); synchronises
+int npb_profile_matvec_read(double* total_ms, int64_t* count) {
+    double t = 0.0;
+    for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_prof_ev[i + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms, g_prof_ev[i], g_prof_ev[i + 1]) != cudaSuccess)
+            return NPB_ERR_CUDA;
+        t += ms;
+    }
+    *total_ms = t;
+    *count = (int64_t)(g_prof_used / 2);
+    return NPB_OK;
+}
+
 int npb_csr_matvec_cb(void* ctx, const double* x, double* y, void* stream) {
     const npb_csr_view* A = (const npb_csr_view*)ctx;
-    return npb_spmv_launch(A->nrows, A->nnz, A->indptr, A->indices, A->data, x, nullptr, y, 0,
-                           (cudaStream_t)stream);
+    const bool prof = g_prof_on && g_prof_used + 2 <= g_prof_ev.size();
+    if (prof) cudaEventRecord(g_prof_ev[g_prof_used], (cudaStream_t)stream);
+    int rc = npb_spmv_launch(A->nrows, A->nnz, A->indptr, A->indices, A->data, x, nullptr, y, 0,
+                             (cudaStream_t)stream);
+    if (prof) { cudaEventRecord(g_prof_ev[g_prof_used + 1], (cudaStream_t)stream); g_prof_used += 2; }
+    return rc;
 }
 
 int64_t npb_fgmres_workspace_bytes(int64_t n, int restart, int flexible) {
