@@ -104,6 +104,61 @@ def aggregate(A, theta, max_rounds=12, kind='mis1', with_roots=False):
     return (agg, n_agg, root_id) if with_roots else (agg, n_agg)
 
 
+def merge_small_aggregates(indptr, indices, data, agg, n_agg, root_id, max_small=2, max_size=6):
+    """Merge the aggregates of at most `max_small` nodes into their most strongly connected
+    neighbouring aggregate: the distance-1 independent set leaves many singletons and pairs
+    (2.75 nodes per aggregate on a 5-point stencil); merged, aggregates hold ~4.5 nodes and the
+    operator complexity of the hierarchy drops from ~2.5 to ~1.8 at the same convergence
+    (tools/proto_lsc.py).  Pure torch (setup code, runs on whatever device the inputs are on).
+
+    Rules (no chains: a merge target never merges itself): a small aggregate goes to its
+    strongest neighbour if that one is large; two small ones that choose each other pair up
+    (the lower id survives); a small one whose choice is a small one that stays joins it.
+    -> (agg, n_agg, root_id) with ids in the order of the surviving roots."""
+    dev = agg.device
+    n = agg.numel()
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), (indptr[1:] - indptr[:-1]).long())
+    a, b = agg.long()[rows], agg.long()[indices.long()]
+    off = a != b
+    key = a[off] * n_agg + b[off]
+    w = data[off].abs()
+    ukey, inv = torch.unique(key, return_inverse=True)
+    wsum = torch.zeros(ukey.numel(), dtype=w.dtype, device=dev).scatter_add_(0, inv, w)
+    ga, gb = ukey // n_agg, ukey % n_agg
+    size = torch.bincount(agg.long(), minlength=n_agg)
+    small = size <= max_small
+    ok = small[ga] & (size[ga] + size[gb] <= max_size)
+    ga, gb, wsum = ga[ok], gb[ok], wsum[ok]
+    best_w = torch.zeros(n_agg, dtype=w.dtype, device=dev).scatter_reduce_(0, ga, wsum, 'amax', include_self=True)
+    is_best = wsum == best_w[ga]
+    best = torch.full((n_agg,), n_agg, dtype=torch.long, device=dev)
+    best.scatter_reduce_(0, ga[is_best], gb[is_best], 'amin', include_self=True)
+    has = best < n_agg                                    # small aggregates with a candidate
+    ids = torch.arange(n_agg, device=dev)
+    tgt = torch.where(has, best, ids)
+    tgt_c = tgt.clamp(max=n_agg - 1)
+    to_large = has & ~small[tgt_c]
+    mutual = has & small[tgt_c] & (tgt[tgt_c] == ids)
+    loser = mutual & (ids > tgt)                          # the higher id of a pair merges
+    merging = to_large | loser
+    stays = ~merging
+    to_staying_small = has & ~merging & ~mutual & small[tgt_c] & stays[tgt_c] & ~has[tgt_c].logical_and(merging[tgt_c])
+    # a target chosen in the last rule must not be merging itself (it is not: stays[tgt])
+    merging = merging | to_staying_small
+    final = torch.where(merging, tgt, ids)
+    # the rule above can only point at aggregates that stay; assert the no-chain property cheaply
+    final = torch.where(merging[final.clamp(max=n_agg - 1)], ids, final)
+    survive = final == ids
+    new_id = torch.cumsum(survive.long(), 0) - 1
+    agg_new = new_id[final[agg.long()]].to(torch.int32)
+    n_new = int(survive.sum().item())
+    flag = (root_id[1:] - root_id[:-1]).long()            # 1 at the root node of each old aggregate
+    flag = flag * survive[agg.long()].long()
+    rid = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    rid[1:] = torch.cumsum(flag, 0).to(torch.int32)
+    return agg_new.contiguous(), n_new, rid
+
+
 def filtered(A, theta):
     """A with its weak off-diagonal entries lumped onto the diagonal"""
     m = A.shape[0]
@@ -148,9 +203,13 @@ class Hierarchy:
             levels.append(lev)
             if n <= coarse_max or len(levels) >= max_levels:
                 break
-            agg, n_agg, root_id = aggregate(cur, theta, kind=agg_kind, with_roots=True)
+            base_kind = 'mis1' if agg_kind == 'mis1m' else agg_kind
+            agg, n_agg, root_id = aggregate(cur, theta, kind=base_kind, with_roots=True)
             if n_agg > 0.6 * n and theta > 0:      # filtered graph too sparse down here
-                agg, n_agg, root_id = aggregate(cur, 0.0, kind=agg_kind, with_roots=True)
+                agg, n_agg, root_id = aggregate(cur, 0.0, kind=base_kind, with_roots=True)
+            if agg_kind == 'mis1m' and 0 < n_agg < 0.9 * n:
+                agg, n_agg, root_id = merge_small_aggregates(cur.indptr, cur.indices, cur.data, agg,
+                                                             n_agg, root_id)
             if n_agg >= 0.9 * n or n_agg == 0:
                 break
             for _ in range(1, agg_passes):

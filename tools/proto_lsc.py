@@ -94,6 +94,61 @@ def aggregate(A, theta, kind, rng):
     return agg, int(agg.max() + 1)
 
 
+def merge_small(A, agg, na, theta, max_small=2, max_size=6):
+    """merge aggregates of <= max_small nodes into their most strongly connected neighbouring
+    aggregate (greedy, sequential): aggregates of ~4-5 nodes instead of the 2.75 of MIS-1"""
+    S = strength(A, theta).tocoo()
+    G = sp.csr_matrix((S.data, (agg[S.row], agg[S.col])), shape=(na, na))
+    G.sum_duplicates()
+    G.setdiag(0)
+    G.eliminate_zeros()
+    G = G.tocsr()
+    size = np.bincount(agg, minlength=na).astype(np.int64)
+    target = np.arange(na)
+    order = np.argsort(size, kind='stable')
+    for a in order:
+        if size[a] > max_small or target[a] != a:
+            continue
+        nb, w = G.indices[G.indptr[a]:G.indptr[a + 1]], G.data[G.indptr[a]:G.indptr[a + 1]]
+        best, bw = -1, 0.0
+        for b, wb in zip(nb, w):
+            r = b
+            while target[r] != r:
+                r = target[r]
+            if r != a and size[r] + size[a] <= max_size and wb > bw:
+                best, bw = r, wb
+        if best >= 0:
+            target[a] = best
+            size[best] += size[a]
+            size[a] = 0
+    root = target.copy()
+    for _ in range(20):
+        root = root[root]
+    ids = np.unique(root, return_inverse=True)[1]
+    return ids[agg], int(ids.max() + 1)
+
+
+def merge_small_parallel(A, agg, na):
+    """the product's merge rule (numpad_b200/amg.py: merge_small_aggregates, pure torch)"""
+    import torch
+    from numpad_b200 import amg
+    A = A.tocsr()
+    first = np.full(na, A.shape[0])
+    np.minimum.at(first, agg, np.arange(A.shape[0]))
+    order = np.argsort(first)
+    ren = np.empty(na, np.int64)
+    ren[order] = np.arange(na)
+    agg = ren[agg]
+    flag = np.zeros(A.shape[0], np.int64)
+    flag[first[order]] = 1
+    rid = np.concatenate([[0], np.cumsum(flag)]).astype(np.int32)
+    t = lambda v, dt: torch.from_numpy(np.ascontiguousarray(v)).to(dt)
+    a2, n2, _ = amg.merge_small_aggregates(t(A.indptr, torch.int32), t(A.indices, torch.int32),
+                                           t(A.data, torch.float64), t(agg, torch.int32), na,
+                                           t(rid, torch.int32))
+    return a2.numpy().astype(np.int64), n2
+
+
 def filtered(A, theta):
     A = A.tocsr()
     d = A.diagonal()
@@ -144,9 +199,14 @@ class Hier:
             self.levels.append(lev)
             if n <= coarse_max or len(self.levels) >= max_levels:
                 break
-            ag, na = aggregate(cur, theta, agg, rng)
+            kind = 'mis1' if agg in ('mis1m', 'mis1p') else agg
+            ag, na = aggregate(cur, theta, kind, rng)
             if na > 0.6 * n and theta > 0:
-                ag, na = aggregate(cur, 0.0, agg, rng)
+                ag, na = aggregate(cur, 0.0, kind, rng)
+            if agg == 'mis1m':
+                ag, na = merge_small(cur, ag, na, theta)
+            if agg == 'mis1p':
+                ag, na = merge_small_parallel(cur, ag, na)
             if na >= 0.9 * n:
                 break
             T = sp.csr_matrix((np.ones(n), (np.arange(n), ag)), shape=(n, na))
@@ -310,6 +370,10 @@ VARIANTS = {
     'A4lev': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=4), 4, 1),
     'A3lev_mis2': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=3, agg='mis2'), 4, 1),
     'A2lev_mis2': (dict(theta=0.0, nu=1), dict(theta=0.25, nu=2, max_levels=2, agg='mis2'), 4, 1),
+    'mis1mL': (dict(theta=0.0, nu=1, agg='mis1m'), dict(theta=0.25, nu=2), 4, 1),
+    'mis1mL_c3': (dict(theta=0.0, nu=1, agg='mis1m'), dict(theta=0.25, nu=2), 3, 1),
+    'mis1pL': (dict(theta=0.0, nu=1, agg='mis1p'), dict(theta=0.25, nu=2), 4, 1),
+    'mis1pL_34': (dict(theta=0.0, nu=1, agg='mis1p'), dict(theta=0.25, nu=2), 4, 1),
     'mis2_t0': (dict(theta=0.0, nu=1, agg='mis2', p_trunc=0.0), dict(theta=0.25, nu=2, agg='mis2', p_trunc=0.0), 4, 1),
 }
 
