@@ -177,12 +177,15 @@ def truncate(P, theta):
 
 class Hier:
     def __init__(self, A, theta=0.0, nu=1, omega=0.67, omega_p=0.67, coarse_max=600, agg='mis1',
-                 p_trunc=0.1, smoother='jacobi', seed=0, cheb_deg=2, filt=True, gal='full', omega_c=None, max_levels=20, coarse_sweeps=None):
+                 p_trunc=0.1, smoother='jacobi', seed=0, cheb_deg=2, filt=True, gal='full', omega_c=None, max_levels=20, coarse_sweeps=None,
+                 gamma=1, gamma_from=1, psmooth=1, nu_post=None):
         rng = np.random.RandomState(seed)
         self.levels = []
         cur = A.tocsr()
         self.nu, self.omega, self.smoother, self.cheb_deg = nu, omega, smoother, cheb_deg
         self.coarse_sweeps = coarse_sweeps
+        self.gamma, self.gamma_from = gamma, gamma_from
+        self.nu_post = nu if nu_post is None else nu_post
         while True:
             n = cur.shape[0]
             d = cur.diagonal()
@@ -214,6 +217,8 @@ class Hier:
             dF = AF.diagonal()
             dFinv = np.where(dF != 0, 1.0 / np.where(dF != 0, dF, 1), 1.0)
             P = (T - sp.diags(omega_p * dFinv) @ (AF @ T)).tocsr()
+            for _ in range(1, psmooth):
+                P = (P - sp.diags(omega_p * dFinv) @ (AF @ P)).tocsr()
             if p_trunc > 0:
                 P = truncate(P, p_trunc)
             lev['P'] = P.tocsr()
@@ -269,11 +274,13 @@ class Hier:
                 return self.cinv @ b
             return self.smooth(l, b, None, self.coarse_sweeps or (2 * self.nu + 6))
         x = self.smooth(l, b, None, self.nu)
-        r = b - mv(L['A'], x)
-        bc = mv(L['R'], r)
-        xc = self.vcycle(bc, l + 1)
-        x = x + mv(L['P'], xc)
-        return self.smooth(l, b, x, self.nu)
+        reps = self.gamma if (l + 1 >= self.gamma_from and l + 2 < len(self.levels)) else 1
+        for _ in range(reps):
+            r = b - mv(L['A'], x)
+            bc = mv(L['R'], r)
+            xc = self.vcycle(bc, l + 1)
+            x = x + mv(L['P'], xc)
+        return self.smooth(l, b, x, self.nu_post)
 
 
 def pcg(h, A, b, k):
@@ -374,6 +381,12 @@ VARIANTS = {
     'mis1mL_c3': (dict(theta=0.0, nu=1, agg='mis1m'), dict(theta=0.25, nu=2), 3, 1),
     'mis1pL': (dict(theta=0.0, nu=1, agg='mis1p'), dict(theta=0.25, nu=2), 4, 1),
     'mis1pL_34': (dict(theta=0.0, nu=1, agg='mis1p'), dict(theta=0.25, nu=2), 4, 1),
+    'mis2L_W': (dict(theta=0.0, nu=1, agg='mis2', gamma=2), dict(theta=0.25, nu=2), 4, 1),
+    'mis2L_W2': (dict(theta=0.0, nu=1, agg='mis2', gamma=2, gamma_from=2), dict(theta=0.25, nu=2), 4, 1),
+    'mis2L_ps2': (dict(theta=0.0, nu=1, agg='mis2', psmooth=2), dict(theta=0.25, nu=2), 4, 1),
+    'mis2L_v12': (dict(theta=0.0, nu=1, agg='mis2', nu_post=2), dict(theta=0.25, nu=2), 4, 1),
+    'mis1pL_W2': (dict(theta=0.0, nu=1, agg='mis1p', gamma=2, gamma_from=2), dict(theta=0.25, nu=2), 4, 1),
+    'base_W2': (dict(theta=0.0, nu=1, gamma=2, gamma_from=2), dict(theta=0.25, nu=2), 4, 1),
     'mis2_t0': (dict(theta=0.0, nu=1, agg='mis2', p_trunc=0.0), dict(theta=0.25, nu=2, agg='mis2', p_trunc=0.0), 4, 1),
 }
 
