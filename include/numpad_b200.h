@@ -53,6 +53,10 @@ int npb_version(void);
 int npb_device_check(void);
 unsigned long long npb_launch_count(void);
 void npb_launch_count_reset(void);
+/* algorithmic bytes (each operand once) of the SpMV-shaped and vector kernels of the solve
+ * phase launched since the last reset (bench.py: whole-Krylov-phase roofline) */
+double npb_bytes_count(void);
+void npb_bytes_count_reset(void);
 int64_t npb_scan_workspace_elems(int64_t n);      /* int64 elements of scan_ws */
 
 /* ---- S1: number * csr (scipy _mul_scalar): materialise a scale chain --- */

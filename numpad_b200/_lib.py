@@ -55,7 +55,7 @@ def parse_header(path=HEADER_PATH):
     src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
     src = re.sub(r'//[^\n]*', ' ', src)
     protos = {}
-    pat = re.compile(r'(?:^|;|\})\s*((?:const\s+)?(?:unsigned long long|int64_t|int|void|char)\s*\*?)\s*'
+    pat = re.compile(r'(?:^|;|\})\s*((?:const\s+)?(?:unsigned long long|int64_t|int|void|char|double)\s*\*?)\s*'
                      r'(npb_\w+)\s*\(([^()]*)\)\s*(?=;)', re.S)
     for m in pat.finditer(src):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()

@@ -4,7 +4,9 @@ Same public surface as the reference's adarray.py (names, argument meaning,
 error behaviour -- SURVEY.md section 8b / Appendix A), different substance:
 
   * `_dev` is a float64 CUDA tensor (torch is the allocator / view machinery);
-    `_value` is a read-only host snapshot of it, assignable to upload.
+    `_value` is a WRITABLE host mirror of it (`_HostMirror`): in-place edits
+    (`u._value -= step`, reference adsolve.py:198; `a._value[i] = x`) mark the
+    array dirty and are uploaded before the next device use.
   * every operation records its local Jacobian as a number, a `dia_jac`
     (device vector), a `sel_jac` (device int32 gather/scatter map -- what the
     reference builds as a unit-data csr_jac) or a general `csr_jac`.
@@ -15,6 +17,7 @@ error behaviour -- SURVEY.md section 8b / Appendix A), different substance:
 reference: adarray.py:112-900.
 """
 import numbers
+import weakref
 
 import numpy as np
 import scipy.sparse as sp
@@ -104,6 +107,49 @@ def _flat(t):
     return t.reshape(-1)
 
 
+class _HostMirror(np.ndarray):
+    """Host mirror of an adarray's values.  The reference's `_value` is the
+    array's own mutable ndarray (mutated in place at adsolve.py:198); here the
+    values live in HBM, so writes into the mirror (item assignment, in-place
+    operators, ufuncs with `out=`) flag the owning adarray, which uploads the
+    mirror before its next device use.  Views of the mirror carry the same
+    owner; everything computed FROM a mirror is a plain ndarray."""
+    _owner = None          # (weakref to the adarray, mirror generation)
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, '_owner', None)
+
+    def _touch(self):
+        if self._owner is not None:
+            ref, gen = self._owner
+            o = ref()
+            if o is not None and o._mirror_gen == gen:
+                o._mirror_dirty = True
+
+    def __setitem__(self, key, val):
+        self._touch()
+        np.ndarray.__setitem__(self, key, val)
+
+    def fill(self, v):
+        self._touch()
+        np.ndarray.fill(self, v)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kw):
+        plain = lambda a: a.view(np.ndarray) if isinstance(a, _HostMirror) else a
+        if out is not None:
+            for o in out:
+                if isinstance(o, _HostMirror):
+                    o._touch()
+            kw['out'] = tuple(plain(o) for o in out)
+        res = getattr(ufunc, method)(*[plain(a) for a in inputs], **kw)
+        if out is not None and len(out) == 1 and isinstance(out[0], _HostMirror):
+            return out[0]              # x += y keeps x bound to the mirror
+        return res
+
+    def __reduce__(self):              # pickles / copies as a plain array
+        return np.ndarray.__reduce__(self.view(np.ndarray))
+
+
 # --------------------------------------------------------------------------- #
 # the array class                                  (reference adarray.py:467-807)
 # --------------------------------------------------------------------------- #
@@ -119,20 +165,44 @@ class adarray:
             t = array.to(device=device(), dtype=torch.float64)
         else:
             t = torch.from_numpy(np.asarray(value(array), np.float64)).to(device())
-        self._dev = t
+        self._mirror, self._mirror_dirty, self._mirror_gen = None, False, 0
+        self._devt = t
         self._dind_cache = None
         self._current_state = InitialState(self)
+
+    # -- device values: `_dev` uploads a host mirror that was written to ------ #
+    @property
+    def _dev(self):
+        if self._mirror_dirty:
+            self._mirror_dirty = False
+            self._devt.copy_(torch.from_numpy(self._mirror.view(np.ndarray)))
+        return self._devt
+
+    @_dev.setter
+    def _dev(self, t):
+        self._devt = t
+        self._drop_mirror()
+
+    def _drop_mirror(self):
+        """the device values changed: an outstanding host mirror is stale (and detached)"""
+        self._mirror, self._mirror_dirty = None, False
+        self._mirror_gen += 1
 
     # -- host views ---------------------------------------------------------- #
     @property
     def _value(self):
-        v = self._dev.detach().cpu().numpy()
-        v.setflags(write=False)       # a snapshot: writes would be lost silently
-        return v
+        if self._mirror is None:
+            v = self._devt.detach().cpu().numpy()
+            if not (v.flags.writeable and v.flags.owndata):
+                v = np.array(v)
+            m = v.view(_HostMirror)
+            m._owner = (weakref.ref(self), self._mirror_gen)
+            self._mirror = m
+        return self._mirror
 
     @_value.setter
     def _value(self, v):
-        self._dev = torch.from_numpy(np.asarray(v, np.float64)).to(device())
+        self._dev = torch.from_numpy(np.array(v, np.float64)).to(device())
         self._dind_cache = None
 
     @property
@@ -208,6 +278,7 @@ class adarray:
             raise NotImplementedError('in-place sort of multi-dimensional adarrays')
         vals, order = torch.sort(self._dev, stable=True)
         self._dev.copy_(vals)
+        self._drop_mirror()
         self.next_state(sel_jac(order.to(torch.int32), self.size, full=True), op_name='sort')
 
     # -- arithmetic (reference adarray.py:580-757) --------------------------- #
@@ -351,6 +422,8 @@ class adarray:
         keep[i.long()] = 0
         self.next_state(dia_jac(keep), op_name='[]=0')
         # assign the values (numpy broadcasting rules)
+        self._dev                      # (uploads a dirty mirror first)
+        self._drop_mirror()
         if basic:
             self._dev[_basic(ind)] = a._dev
             tshape = tuple(self._dev[_basic(ind)].shape)
@@ -433,6 +506,7 @@ def _unary(fn, dfn, name):
             out = adarray(fn(x._dev))
         else:
             out._dev.copy_(fn(x._dev))
+            out._drop_mirror()
             out.next_state(0, op_name='0')
         out.next_state(dia_jac(dfn(_flat(x._dev))), x, name)
         return out

@@ -10,8 +10,18 @@ non-convergence).  What changed underneath:
   * `J = res.diff(u)` is assembled in HBM (adstate sweeps -> CUDA kernels);
   * `spsolve(J, res)` (SuperLU)  -> linsolve.solve (preconditioned FGMRES);
   * `factorized(J^T)(g)` row by row on densified operands (adsolve.py:74-82,
-    137-145) -> one Krylov solve per row/column on the transposed / plain
-    device CSR; the diagonal-Jacobian shortcut (:60-73,:122-136) is kept.
+    137-145) -> block solves of all rows/columns at once on the transposed /
+    plain device CSR (linsolve.solve_multi: one preconditioner setup, operands
+    kept sparse on the device); the diagonal-Jacobian shortcut
+    (:60-73,:122-136) is kept.
+  * `adsolution` assembles its Jacobian lazily (first differentiation through
+    the solution) instead of at construction (adsolve.py:155-156).
+
+Provenance: the control flow of `solve`, `psuedo_time_continuation` and the
+state-class protocol (`ResidualState`, `SolutionState`) deliberately restate
+the reference's (qiqi/numpad adsolve.py, GPLv3 -- see /root/reference/LICENSE)
+because tolerances, guards, printed messages and `_n_Newton` semantics are
+API-visible to user scripts; all arithmetic underneath is new.
 """
 import numbers
 import sys
@@ -108,14 +118,31 @@ class SolutionState(IntermediateState):
         assert residual_state.size == self.size
         residual_state.solution = weakref.ref(self)
         self.residual = residual_state
-        if not isinstance(jacobian, numbers.Number):
+        if not callable(jacobian) and not isinstance(jacobian, numbers.Number):
             assert jacobian.shape == (self.size, self.size)
-        self.jacobian = jacobian
+        self._jacobian = jacobian
+
+    @property
+    def jacobian(self):
+        """d residual / d solution.  The reference assembles it when the adsolution is
+        built (adsolve.py:155-156), i.e. once per solve() whether or not anybody ever
+        differentiates through the solution; here a thunk is stored and the assembly
+        runs on first use (the residual's tape is alive for as long as this state is,
+        exactly as in the reference)."""
+        if callable(self._jacobian):
+            self._jacobian = self._jacobian()
+            if not isinstance(self._jacobian, numbers.Number):
+                assert self._jacobian.shape == (self.size, self.size)
+        return self._jacobian
+
+    @jacobian.setter
+    def jacobian(self, j):
+        self._jacobian = j
 
     def obliviate(self):
         IntermediateState.obliviate(self)
         self.residual = None
-        self.jacobian = None
+        self._jacobian = None
 
     def froms(self):
         if hasattr(self, 'residual') and self.residual:
@@ -150,10 +177,27 @@ class adsolution(adarray):
     def __init__(self, solution, residual, n_Newton):
         assert isinstance(solution, adarray)
         assert isinstance(residual, adarray)
-        residual._current_state = ResidualState(residual._current_state)
+        res_state = residual._current_state = ResidualState(residual._current_state)
+        u_state = solution._initial_state
         adarray.__init__(self, solution._dev)
-        self._current_state = SolutionState(self, residual._current_state,
-                                            diff_dev(residual, solution))
+
+        def assemble():
+            # the tape as it was when the solution was built: the residual state does not
+            # yet lead on to the solution
+            link, res_state.solution = getattr(res_state, 'solution', None), (lambda: None)
+            try:
+                from .adstate import diff_adjoint, diff_tangent
+                if u_state.size < res_state.size:
+                    return diff_tangent(res_state, u_state)
+                return diff_adjoint(res_state, u_state)
+            finally:
+                if link is None:
+                    del res_state.solution
+                else:
+                    res_state.solution = link
+
+        self._current_state = SolutionState(self, res_state,
+                                            assemble if lazy_jacobian else assemble())
         self._n_Newton = n_Newton
         self._res_norm = float(torch.linalg.vector_norm(residual._dev.reshape(-1)))
 
@@ -161,6 +205,11 @@ class adsolution(adarray):
         adarray.obliviate(self)
         del self._n_Newton
         del self._res_norm
+
+
+# adsolution assembles d residual / d solution on first use (True) or at construction like the
+# reference (False)
+lazy_jacobian = True
 
 
 # optional hook for tests / benchmarks: trace(i_newton, u_dev, J_dev, rhs_dev, minus_du_dev)
@@ -195,7 +244,15 @@ def solve_newton_with_dt(func, u0, args, kargs, dt, max_iter, abs_tol, rel_tol, 
         if res.size > 1:
             if _is0(J):
                 raise ZeroDivisionError('residual does not depend on the unknown')
-            minus_du = linsolve.solve(_to_devcsr(J), rhs, **linear_options)
+            try:
+                minus_du = linsolve.solve(_to_devcsr(J), rhs, **linear_options)
+            except (linsolve.LinearSolveError, np.linalg.LinAlgError) as e:
+                # the reference never raises on a hard step (spsolve returns garbage and the
+                # divergence guard trips): report non-convergence, so that solve() falls back
+                # to pseudo-time continuation, whose 1/dt shift is what rescues such Jacobians
+                if verbose:
+                    print('     linear solve failed:', e)
+                break
         else:
             minus_du = rhs / float(_to_devcsr(J).toscipy().toarray()[0, 0])
         if newton_trace is not None:

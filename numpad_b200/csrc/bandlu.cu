@@ -35,6 +35,7 @@ k_band_fill(int64_t n, const int32_t* __restrict__ ptr, const int32_t* __restric
     const int pi = inv[r];
     for (int32_t k = ptr[r] + lane, e = ptr[r + 1]; k < e; k += 8) {
         const int pj = inv[idx[k]];
+        if (pi - pj > kl || pj - pi > ku) continue;     // outside the band: caller's ordering is stale
         AB[(int64_t)(kl + ku + pi - pj) + (int64_t)pj * ldab] = dat[k];
     }
 }

@@ -6,6 +6,7 @@
 
 static char g_err[512] = "";
 extern "C" unsigned long long npb_launch_counter = 0;
+extern "C" double npb_bytes_counter = 0.0;
 
 void npb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -23,6 +24,8 @@ int npb_version(void) { return 100; }
 // number of kernels launched through this library since load / last reset
 unsigned long long npb_launch_count(void) { return npb_launch_counter; }
 void npb_launch_count_reset(void) { npb_launch_counter = 0; }
+double npb_bytes_count(void) { return npb_bytes_counter; }
+void npb_bytes_count_reset(void) { npb_bytes_counter = 0.0; }
 
 // 0 when a CUDA device is usable; the Python layer refuses to run without it
 int npb_device_check(void) {

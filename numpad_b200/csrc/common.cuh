@@ -72,5 +72,10 @@ extern "C" {
 // bumped by every kernel launch issued through the C-ABI (bench.py reports it
 // as gpu_launches)
 extern unsigned long long npb_launch_counter;
+// algorithmic bytes (every operand once) of the SpMV-shaped and vector
+// kernels of the solve phase launched since the last reset: bench.py divides it by the
+// Krylov phase time for the whole-phase roofline
+extern double npb_bytes_counter;
 }
 #define NPB_COUNT_LAUNCH() (++npb_launch_counter)
+#define NPB_COUNT_BYTES(b) (npb_bytes_counter += (double)(b))

@@ -41,7 +41,9 @@ struct spmv_epi {
 template <bool HALO>
 __device__ __forceinline__ double ldx(const double* x, const spmv_epi& e, int32_t c) {
     if (!HALO) return __ldg(x + c);
-    return c < e.n_own ? __ldg(x + c) : __ldg(e.xh + (c - e.n_own));
+    // halo slots are written by PEER GPUs while this kernel may already run (the arrival
+    // wait sits in the prologue): they must not go through the non-coherent path
+    return c < e.n_own ? __ldg(x + c) : __ldcg(e.xh + (c - e.n_own));
 }
 
 __device__ __forceinline__ double spmv_finish(const spmv_epi& e, int64_t r, double s,
@@ -516,6 +518,8 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
         spmv_small_dispatch<false>(nrows, nnz, ptr, idx, dat, x, e, y, variant, mean, aligned, st);
     }
     NPB_COUNT_LAUNCH();
+    // CSR once + x + y (+ b, + dinv and x[row] for the Jacobi epilogue); x counted with the row count
+    NPB_COUNT_BYTES(12.0 * nnz + 4.0 * (nrows + 1) + 8.0 * nrows * (2 + (mode >= 1) + 2 * (mode == 3)));
     NPB_CHECK_LAUNCH("spmv");
     return NPB_OK;
 }
@@ -549,6 +553,7 @@ int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const do
                                                      out + j0);
         NPB_COUNT_LAUNCH();
     }
+    NPB_COUNT_BYTES(8.0 * n * (k + 1));
     NPB_CHECK_LAUNCH("dot_multi");
     return NPB_OK;
 }
@@ -565,6 +570,7 @@ int npb_axpy_multi_launch(int64_t n, int k, const double* V, int64_t ld, const d
         k_axpy_multi<false><<<grid_for(n), TPB, sh, st>>>(n, k, V, ld, h, sign, w, red_partial(scratch),
                                                          red_ticket(scratch), out_norm2);
     NPB_COUNT_LAUNCH();
+    NPB_COUNT_BYTES(8.0 * n * (k + 2));
     NPB_CHECK_LAUNCH("axpy_multi");
     return NPB_OK;
 }
@@ -573,6 +579,7 @@ int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, 
     if (n <= 0) return NPB_OK;
     k_axpby<<<grid_for(n), TPB, 0, st>>>(n, a, x, b, y);
     NPB_COUNT_LAUNCH();
+    NPB_COUNT_BYTES(8.0 * n * (b == 0.0 ? 2 : 3));
     NPB_CHECK_LAUNCH("axpby");
     return NPB_OK;
 }

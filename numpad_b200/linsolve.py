@@ -19,7 +19,7 @@ from ._lib import KrylovOps, CsrView, KrylovInfo
 from ._dev import DevCsr, device, stream_ptr, _empty
 
 # knobs (also settable through solve(..., linear_options={...}))
-DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=60, maxiter=600, precond='auto',
+DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=100, maxiter=600, precond='auto',
                 verbose=False,
                 # multi-GPU: owner[i] = rank of unknown i.  When set and torch.distributed runs
                 # with more than one rank, saddle-point systems too large for the direct solver

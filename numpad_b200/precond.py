@@ -41,7 +41,11 @@ def rcm(A):
     key = _pattern_key(A)
     hit = _rcm_cache.get(key)
     if hit is not None:
-        return hit
+        # the hash only selects a candidate: the cached pattern itself is compared, so a
+        # collision can never hand BandLU a stale ordering / bandwidth
+        ptr0, idx0, out = hit
+        if torch.equal(ptr0, A.indptr) and torch.equal(idx0, A.indices):
+            return out
     n = A.shape[0]
     ptr = np.ascontiguousarray(A.indptr.cpu().numpy())
     idx = np.ascontiguousarray(A.indices.cpu().numpy())
@@ -57,7 +61,7 @@ def rcm(A):
            int(bw[0]), int(bw[1]))
     if len(_rcm_cache) > 8:
         _rcm_cache.clear()
-    _rcm_cache[key] = out
+    _rcm_cache[key] = (A.indptr.clone(), A.indices.clone(), out)
     return out
 
 
@@ -124,6 +128,12 @@ def direct_feasible(A):
 
 
 _last = {'lsc': None}
+
+
+def forget():
+    """drop the preconditioner carried over from the previous solve (its pressure hierarchy is
+    reused while the constraint blocks stay bit-identical, see LscPreconditioner)"""
+    _last['lsc'] = None
 
 
 def build(A, kind='auto'):

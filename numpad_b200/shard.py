@@ -377,6 +377,29 @@ def permuted(J, perm, inv):
 
 
 last_info = {}
+# True: last_info['lsc_digests'] holds checksums of the replicated operators (LSC blocks and
+# every multigrid level) so that a multi-rank test can assert they are bit-identical everywhere
+DIGESTS = False
+
+
+def _digest(t):
+    v = t.reshape(-1)
+    v = v.view(torch.int64) if v.dtype == torch.float64 else v.to(torch.int64)
+    w = torch.arange(1, v.numel() + 1, device=v.device, dtype=torch.int64)
+    return int(((v * (w % 1000003 + 1)).sum() % 9223372036854775783).item())
+
+
+def _lsc_digests(M):
+    out = []
+    mats = [M.A, M.G, M.D, M.Lm]
+    for h in (M.amg_a, M.amg_l):
+        for lev in h.levels:
+            mats.append(lev['A'])
+            if 'P' in lev:
+                mats.append(lev['P'])
+    for m in mats:
+        out += [_digest(m.indptr), _digest(m.indices), _digest(m.data)]
+    return out
 
 
 def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=None):
@@ -439,6 +462,8 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
                first_replicated_level=(S.amg_a.first_rep, S.amg_l.first_rep),
                halo=(Jl.maxb, S.A.maxb, S.Lm.maxb),
                exchange='direct stores into NVLink peer memory' if _handle['p2p'] else 'NCCL all-gather')
+    if DIGESTS:
+        res['lsc_digests'] = _lsc_digests(M)
     last_info.clear()
     last_info.update(res)
     if res['status'] != 0:

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
-                          '--steps', '1', '--warmup', '0', '--sample-grid', '40', '--grid', '1024'],
+                          '--steps', '1', '--warmup', '0', '--sample-grid', '40', '--trend-grid', '56', '--grid', '1024'],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
@@ -21,7 +21,10 @@ def test_reference_arm_json_line():
               'cpu_baseline', 'e2e'):
         assert k in d, k
     assert d['impl'] == 'reference' and d['dtype'] == 'f64' and d['vs_baseline'] is None
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] == 1
+    kind = 'reference' if os.path.exists(os.path.join(ROOT, 'baseline', '_ref', 'numpad', 'adarray.py')) else 'port'
+    assert d['cpu_baseline']['kind'] == kind and d['cpu_baseline']['cores'] == 1
+    assert d['loaded_engine_modules'] == []      # the CPU arm never imports the engine
+    assert len(d['cpu_baseline']['trend']) == 2 and d['cpu_baseline']['trend_extrapolation']
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     assert 'workload' in d['config'] and d['value'] > 0
 
@@ -35,7 +38,7 @@ def test_reference_arm_under_torchrun_prints_once():
                           '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                           '--master-port', str(port), os.path.join(ROOT, 'bench.py'),
                           '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0',
-                          '--sample-grid', '32', '--grid', '1024'],
+                          '--sample-grid', '32', '--trend-grid', '0', '--grid', '1024'],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]

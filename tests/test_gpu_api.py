@@ -1,0 +1,86 @@
+"""Drop-in behaviours of the Python surface that scripts rely on:
+writable `_value`, `adsolution` with a lazily assembled Jacobian, and `solve()`
+surviving a failing linear solve through pseudo-time continuation."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def npd():
+    import numpad_b200
+    from numpad_b200 import _dev
+    _dev.device()
+    return numpad_b200
+
+
+def test_value_is_a_writable_mirror(npd):
+    a = npd.array(np.arange(6.0))
+    v = a._value
+    assert v.flags.writeable
+    v -= 1.0                                    # reference adsolve.py:198 mutates _value in place
+    np.testing.assert_array_equal((a * 2)._value, 2 * (np.arange(6.0) - 1))
+    a._value[2] = 10.0                          # item assignment through a fresh handle
+    a._value[4:] = [7.0, 8.0]                   # ... and through a view
+    np.testing.assert_array_equal(a._dev.cpu().numpy(), [-1, 0, 10, 2, 7, 8])
+    np.multiply(a._value, 2.0, out=a._value)    # ufunc with out=
+    np.testing.assert_array_equal(a._dev.cpu().numpy(), [-2, 0, 20, 4, 14, 16])
+    # arithmetic on the mirror yields plain arrays; reading does not dirty anything
+    assert type(a._value * 2) is np.ndarray and type(np.linalg.norm(a._value)) is not type(v)
+    # device-side changes invalidate the mirror: the next read sees them
+    a[0] = 5.0
+    assert a._value[0] == 5.0
+    # a stale handle from before the device change is detached: writing it changes nothing
+    v[1] = 99.0
+    assert a._value[1] == 0.0
+    a._value = np.ones(6)
+    np.testing.assert_array_equal(a._dev.cpu().numpy(), np.ones(6))
+
+
+def test_lazy_jacobian_matches_eager(npd):
+    from numpad_b200 import adsolve
+    N = 30
+    dx = 1.0 / (N + 1)
+
+    def residual(u, f):
+        w = npd.hstack([0, u, 0])
+        return (w[2:] + w[:-2] - 2 * w[1:-1]) / dx ** 2 + f * npd.exp(-u)
+    out = {}
+    for lazy in (True, False):
+        adsolve.lazy_jacobian = lazy
+        try:
+            f = npd.ones(N)
+            u = npd.solve(residual, npd.zeros(N), args=(f,), verbose=False)
+            J = npd.sum(u ** 2).diff(f)
+            out[lazy] = (np.asarray(u._value).copy(), np.asarray(J.todense()),
+                         u._current_state.jacobian.toscipy().toarray())
+        finally:
+            adsolve.lazy_jacobian = True
+    np.testing.assert_array_equal(out[True][0], out[False][0])
+    np.testing.assert_array_equal(out[True][2], out[False][2])
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-13, atol=1e-15)
+
+
+def test_failed_linear_solve_falls_back_to_continuation(npd, monkeypatch):
+    """a LinearSolveError inside Newton must not leave solve(); the step counts as
+    not converged (`_n_Newton = inf`) and pseudo-time continuation, whose 1/dt shift changes the
+    matrix, takes over -- the reference's contract (adsolve.py:225-264)."""
+    from numpad_b200 import linsolve, adsolve
+    real = linsolve.solve
+    calls = {'failed': 0}
+
+    def flaky(A, b, **kw):
+        if calls['failed'] < 1:           # the first system (plain Newton, dt = inf) stagnates
+            calls['failed'] += 1
+            raise linsolve.LinearSolveError('synthetic stagnation')
+        return real(A, b, **kw)
+    monkeypatch.setattr(adsolve.linsolve, 'solve', flaky)
+
+    def residual(u):
+        return u ** 3 + 2 * u - 1.0
+    u = npd.solve(residual, npd.zeros(5), verbose=False)
+    assert calls['failed'] >= 1
+    assert np.isfinite(u._n_Newton)
+    r = np.asarray(u._value)
+    np.testing.assert_allclose(r ** 3 + 2 * r - 1.0, 0.0, atol=1e-5)
