@@ -241,6 +241,29 @@ int npb_band_lu_factor(int n, int kl, int ku, double* AB, int ldab, int32_t* ipi
 int npb_band_lu_solve(int n, int kl, int ku, const double* AB, int ldab,
                       const int32_t* ipiv, double* b, void* stream);
 
+/* Block-tridiagonal direct solver over the level sets of the matrix graph (csrc/blocktri.cu;
+ * replaces spsolve, adsolve.py:193-195, where preconditioned Krylov fails: convection-
+ * dominated saddle points, compressible-flow Jacobians at the scripts' time steps).  The
+ * caller owns the dense blocks; "window" = rows [r0, r1) x columns [c0, c1) of a CSR matrix. */
+int npb_bfs_levels_host(int64_t n, const int32_t* indptr /*[host]*/, const int32_t* indices /*[host]*/,
+                        const int32_t* indptr_t /*[host] pattern of A^T, may be NULL*/,
+                        const int32_t* indices_t /*[host]*/, int32_t* level /*[host] out*/,
+                        int32_t* nlevels /*[host] out*/);
+int npb_bt_window_to_dense(const int32_t* indptr, const int32_t* indices, const double* data,
+                           int64_t r0, int64_t r1, int64_t c0, int64_t c1, double alpha,
+                           double* out, int64_t ld, void* stream);
+int npb_bt_window_spmm(const int32_t* indptr, const int32_t* indices, const double* data,
+                       int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double* B,
+                       int64_t ldb, int64_t ncols, double alpha, double beta, double* C,
+                       int64_t ldc, void* stream);
+int npb_bt_window_spmv(const int32_t* indptr, const int32_t* indices, const double* data,
+                       int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double* x,
+                       double alpha, double beta, double* y, void* stream);
+int64_t npb_bt_gemv_scratch_doubles(int64_t m);
+int npb_bt_gemv(int64_t m, const double* M, int64_t ld, const double* x, double alpha,
+                double beta, const double* y0, double* y, int trans, double* scratch,
+                void* stream);
+
 /* ---- S3: the linear solve (replaces spsolve / factorized / _lgmres) ---- */
 typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
 typedef int (*npb_allreduce_fn)(void* ctx, double* buf, int count, void* stream);

@@ -223,7 +223,7 @@ def solve_newton_with_dt(func, u0, args, kargs, dt, max_iter, abs_tol, rel_tol, 
     u0v = u0._dev if isinstance(u0, adarray) else \
         torch.from_numpy(np.asarray(value(u0), np.float64)).to(device())
     u = adarray(u0v.clone())
-    linsolve.reset_hints()
+    linsolve.reset_hints(hard=False)
     for i_Newton in range(max_iter):
         if dt == np.inf:
             res = func(u, *args, **kargs)

@@ -28,13 +28,21 @@ DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=100, maxiter=600, precond='auto',
                 shard_owner=None)
 
 last_info = {}      # filled by every solve: iterations, residuals, method
-_hints = {'robust': False}
+# 'robust': the multigrid-preconditioned solve failed on a matrix of signature 'sig' = (n, nnz):
+# later systems of the same signature (the next Newton iterations and time steps of the same
+# run) go straight to the robust solver instead of failing first
+_hints = {'robust': False, 'sig': None}
+_stale = {'btlu': None, 'sig': None}     # last block-tridiagonal factorisation (reused as a
+                                         # preconditioner while the Jacobian has not moved far)
 
 
-def reset_hints():
-    """called at the start of every Newton solve: forget that the previous
-    sequence of Jacobians needed the robust inner solver"""
-    _hints['robust'] = False
+def reset_hints(hard=True):
+    """forget that earlier Jacobians needed the robust solver.  The Newton loop calls this
+    softly (hard=False) at the start of every solve: the hint then survives as long as the
+    systems keep their signature."""
+    if hard:
+        _hints['robust'], _hints['sig'] = False, None
+        _stale['btlu'], _stale['sig'] = None, None
 
 
 class LinearSolveError(RuntimeError):
@@ -155,6 +163,56 @@ def _solve_sharded(A, b, o):
     return x
 
 
+def _solve_btlu(A, b, o, t0):
+    """block-tridiagonal direct solve + FGMRES refinement to the requested tolerance; a
+    factorisation of an earlier Jacobian of the same pattern is first tried as the
+    preconditioner (Newton iterates move little: a handful of iterations instead of a new
+    factorisation).  None: not applicable (caller falls back)."""
+    from . import blocktri, precond as _pc
+    import numpy as np
+    sig = (A.shape[0], A.nnz)
+    info = {}
+    M = _stale['btlu'] if _stale['sig'] == sig else None
+    if M is not None and o.get('btlu_reuse', True):
+        x, res = fgmres(A, b, precond=M.apply, rtol=o['rtol'], atol=o['atol'], restart=30, maxiter=30)
+        if res['status'] == 0:
+            res.update(method='btlu (reused factorisation)', setup_ms=0.0, krylov_ms=1e3 * (_now() - t0),
+                       precond=M.describe())
+            last_info.clear()
+            last_info.update(res)
+            if o['verbose']:
+                print('    linear solve [%s]: %d its, |r|/|b| = %.2e' % (res['method'], res['iters'],
+                      res['rnorm'] / max(res['bnorm'], 1e-300)))
+            return x
+        info['stale_iters'] = res['iters']
+    _stale['btlu'] = M = None            # free the old inverses before building new ones
+    if not blocktri.feasible(A):
+        return None
+    try:
+        M = blocktri.BlockTriLU(A)
+    except np.linalg.LinAlgError:
+        return None
+    t_setup = _now() - t0
+    t1 = _now()
+    x0 = M.solve(b)
+    x, res = fgmres(A, b, x0=x0, precond=M.apply, rtol=o['rtol'], atol=o['atol'], restart=20, maxiter=40)
+    res.update(info, method='btlu', setup_ms=1e3 * t_setup, krylov_ms=1e3 * (_now() - t1),
+               precond=M.describe())
+    last_info.clear()
+    last_info.update(res)
+    if _cb_error:
+        e = _cb_error.pop()
+        _cb_error.clear()
+        raise e
+    if o['verbose']:
+        print('    linear solve [btlu]: factor %.0f ms, %d refinement its, |r|/|b| = %.2e' %
+              (res['setup_ms'], res['iters'], res['rnorm'] / max(res['bnorm'], 1e-300)))
+    if res['status'] != 0:
+        return None
+    _stale['btlu'], _stale['sig'] = M, sig
+    return x
+
+
 def solve(A, b, transpose=False, **opts):
     """x = A^{-1} b (or A^{-T} b) for a DevCsr A and a device vector b."""
     o = dict(DEFAULTS)
@@ -170,11 +228,17 @@ def solve(A, b, transpose=False, **opts):
         if x is not None:
             return x
     t0 = _now()
-    if o['precond'] == 'lsc' and _hints['robust']:
-        o['precond'] = 'lsc-robust'
+    sig = (n, A.nnz)
+    if _hints['robust'] and _hints['sig'] != sig:
+        reset_hints()
+    if o['precond'] in ('auto', 'lsc', 'amg') and _hints['robust'] and not _pc.direct_feasible(A):
+        o['precond'] = _pc.robust_kind(A)
+    if o['precond'] == 'btlu':
+        x = _solve_btlu(A, b, o, t0)
+        if x is not None:
+            return x
+        o['precond'] = 'lsc-robust' if bool((_pc.diagonal(A) == 0).any()) else 'jacobi'
     M, method = _pc.build(A, o['precond'])
-    if method == 'fgmres+lsc' and _hints['robust']:
-        M, method = _pc.build(A, 'lsc-robust')
     first_try = method in ('fgmres+lsc', 'fgmres+amg')
     t_setup = _now() - t0
     if method == 'direct':
@@ -212,16 +276,16 @@ def solve(A, b, transpose=False, **opts):
     if o['verbose']:
         print('    linear solve [%s]: %d its, |r|/|b| = %.2e' %
               (method, res['iters'], res['rnorm'] / max(res['bnorm'], 1e-300)))
-    if res['status'] != 0 and method == 'fgmres+lsc':
-        # multigrid on a convection-dominated momentum block can diverge: retry
-        # with the Krylov inner solve, and keep using it for the rest of this
-        # Newton sequence
-        _hints['robust'] = True
-        return solve(A, b, **dict(o, precond='lsc-robust'))
-    if res['status'] != 0 and method == 'fgmres+amg':
-        # multigrid on a non-elliptic (e.g. compressible-flow) Jacobian: fall back
-        # to the Jacobi-preconditioned Krylov solve
-        return solve(A, b, **dict(o, precond='jacobi', maxiter=max(o['maxiter'], 1000)))
+    if res['status'] != 0 and method in ('fgmres+lsc', 'fgmres+amg'):
+        # multigrid on a convection-dominated momentum block / a non-elliptic (compressible-
+        # flow) Jacobian can stagnate or diverge: retry with the robust solver -- the block-
+        # tridiagonal direct solve when its dense blocks fit in HBM, else the Krylov inner
+        # solve (saddle points) or Jacobi-GMRES -- and keep using it for the systems that follow
+        _hints['robust'], _hints['sig'] = True, sig
+        del M
+        kind = _pc.robust_kind(A)
+        return solve(A, b, **dict(o, precond=kind,
+                                  maxiter=max(o['maxiter'], 1000) if kind == 'jacobi' else o['maxiter']))
     if res['status'] != 0 and method != 'direct' and _pc.direct_feasible(A):
         # robust fallback: pivoted banded LU (+ refinement through the front door)
         return solve(A, b, **dict(o, precond='direct'))

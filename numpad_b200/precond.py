@@ -10,7 +10,10 @@ build(A, kind) -> (M, method):
              complement with multigrid sub-solves
   'lsc-robust': same, the momentum block solved by Jacobi-GMRES instead of a
              V-cycle; the automatic retry when 'lsc' stagnates or diverges
-             (convection-dominated Jacobians, where Jacobi smoothing diverges)
+             (convection-dominated Jacobians, where Jacobi smoothing diverges) when the
+             block-tridiagonal direct solve does not fit
+  'btlu'   : block-tridiagonal direct solve over the level sets of the matrix graph
+             (blocktri.py): the robust retry whenever its dense blocks fit in HBM
   'auto'   : picks from the size and structure of A
 """
 import ctypes
@@ -128,6 +131,19 @@ def direct_feasible(A):
 
 
 _last = {'lsc': None}
+
+
+def diagonal(A):
+    from . import amg
+    return amg.diagonal(A)
+
+
+def robust_kind(A):
+    """the solver for systems on which multigrid-preconditioned Krylov failed"""
+    from . import blocktri
+    if blocktri.feasible(A):
+        return 'btlu'
+    return 'lsc-robust' if bool((diagonal(A) == 0).any()) else 'jacobi'
 
 
 def forget():
