@@ -209,6 +209,10 @@ int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      void* stream);
 int npb_spmv_set_tma_geometry(int g);   /* tuning: shared-memory ring geometry -1 (auto) or 0..3; returns old */
 int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA kernel; returns old */
+/* same epilogues for an operator whose values are stored in fp32 (vectors and sums fp64) */
+int npb_spmv_f32(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                 const float* data32, const double* x, int mode, const double* b,
+                 const double* dinv, double omega, double* y, void* stream);
 int npb_spmv_residual(int64_t nrows, int64_t nnz, const int32_t* indptr,
                       const int32_t* indices, const double* data,
                       const double* x, const double* b, double* y,
@@ -323,6 +327,8 @@ typedef struct npb_csr_mat {
     const int32_t* indices;
     const double* data;
     npb_halo halo;
+    const float* data32;            /* != NULL: the same values in fp32 (preconditioner operators; the
+                                       SpMV then reads 8 instead of 12 bytes per entry) */
 } npb_csr_mat;
 
 typedef struct npb_amg_level {      /* [host] */
@@ -364,7 +370,9 @@ typedef struct npb_lsc {            /* [host] ctx of npb_lsc_apply_cb */
     double* wp[8];
     double* scal;                   /* 4 device doubles */
     void* red;                      /* npb_reduce_scratch_bytes(), zeroed */
-    int32_t a_gmres, pad;           /* > 0: A-solve = that many Jacobi-GMRES steps */
+    int32_t a_gmres;                /* > 0: A-solve = that many Jacobi-GMRES steps */
+    int32_t graph_id;               /* > 0 (unique per preconditioner): npb_lsc_apply_cb may replay its
+                                       launch sequence as a CUDA graph; release with npb_lsc_graph_release */
     void* a_work;                   /* npb_fgmres_workspace_bytes(nv, a_gmres, 0) */
     int64_t a_work_bytes;
 } npb_lsc;
@@ -434,6 +442,10 @@ int npb_diag_apply_cb(void* ctx, const double* x, double* y, void* stream);  /* 
 int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream);
 int npb_amg_apply_cb(void* ctx, const double* x, double* y, void* stream);
 int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream);
+/* CUDA-graph replay of the preconditioner's launch sequence (single GPU, multigrid momentum
+ * solve): global switch (returns the old value) and release of a preconditioner's graph */
+int npb_lsc_graphs_enable(int on);
+int npb_lsc_graph_release(int graph_id);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,11 @@ from .adarray import (np, sp, value, array, diff, diff_dev, adarray, sum, exp, s
 from .adsolve import (solve, solve_newton_with_dt, psuedo_time_continuation,  # noqa: F401,E402
                       adsolution, ResidualState, SolutionState)
 from .adstate import _add_ops, _multiply_ops  # noqa: F401,E402
+from .adtools import interp  # noqa: F401,E402
+from . import adrandom as random  # noqa: F401,E402      (reference __init__.py:4-7)
+from . import advisual as visual  # noqa: F401,E402
+from . import adlinalg as linalg  # noqa: F401,E402
+from . import adsparse as sparse  # noqa: F401,E402
 
 
 def launch_count():

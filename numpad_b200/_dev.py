@@ -124,6 +124,11 @@ class DevCsr:
                       int(lens.max()) if lens.size else 0,
                       clean=bool(np.count_nonzero(m.data) == m.nnz))
 
+    @staticmethod
+    def from_coo(shape, rows, cols, vals):
+        """device COO triplets (duplicates summed, explicit zeros kept) -> canonical CSR"""
+        return coo_to_csr(shape, _as_dev_i32(rows), _as_dev_i32(cols), _as_dev_f64(vals), prune=False)
+
     def scaled(self, a):
         if len(self.scales) >= MAX_SCALES:
             return self.materialized().scaled(a)

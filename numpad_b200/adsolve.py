@@ -61,11 +61,32 @@ def _diagonal_of(jac):
     return None
 
 
-def _dense_rows(m):
-    """host dense copy of a (small) derivative block, one row per entry of f"""
-    if isinstance(m, (DevCsr, DevEye)):
-        return np.asarray(m.toscipy().todense())
-    return np.asarray(sp.csr_matrix(m).todense())
+# the implicit tangent / adjoint densify one operand (as the reference does, adsolve.py:75,138);
+# refuse shapes whose dense image cannot sit in HBM beside the solver
+MAX_DENSE_BYTES = 32e9
+
+
+def _dense_on_device(m, transpose=False):
+    """dense image (rows x cols, or its transpose) of a device CSR block, built on the device"""
+    m = _to_devcsr(m).materialized()
+    r, c = m.shape
+    if 8.0 * r * c > MAX_DENSE_BYTES:
+        raise MemoryError('implicit derivative: a %d x %d operand would be densified' % (r, c))
+    out = torch.zeros((c, r) if transpose else (r, c), dtype=torch.float64, device=device())
+    rows, cols = m.rows().long(), m.indices.long()
+    if transpose:
+        out[cols, rows] = m.data
+    else:
+        out[rows, cols] = m.data
+    return out
+
+
+def _sparse_from_dense(d):
+    """device CSR of a dense device matrix without its exact zeros (what sp.csr_matrix(dense)
+    keeps in the reference, adsolve.py:82,145)"""
+    nz = torch.nonzero(d)
+    return DevCsr.from_coo(tuple(d.shape), nz[:, 0].to(torch.int32), nz[:, 1].to(torch.int32),
+                           d[nz[:, 0], nz[:, 1]])
 
 
 class ResidualState(IntermediateState):
@@ -95,16 +116,11 @@ class ResidualState(IntermediateState):
                     from ._dev import _csr_times_diag, dia_jac
                     f_diff_self = _csr_times_diag(f_diff_soln, dia_jac(-1.0 / d))
                 else:
-                    # one transposed solve J^T lambda = g^T per row of f_diff_soln
-                    g = _dense_rows(f_diff_soln)
-                    J = _to_devcsr(jac)
-                    Jt = J.transpose()
-                    rows = []
-                    for b in g:
-                        bd = torch.from_numpy(np.ascontiguousarray(b)).to(device())
-                        rows.append(-linsolve.solve(Jt, bd).cpu().numpy())
-                    f_diff_self = DevCsr.from_scipy(sp.csr_matrix(
-                        np.array(rows).reshape(g.shape)))
+                    # transposed solves J^T lambda_k = g_k^T, one per row of f_diff_soln: the
+                    # solver is set up once for all rows, operands never leave the device
+                    g = _dense_on_device(f_diff_soln)
+                    lam = linsolve.solve_multi(_to_devcsr(jac), g, transpose=True, **linear_options)
+                    f_diff_self = _sparse_from_dense(-lam)
         return _add_ops(f_diff_self, IntermediateState.diff_adjoint(self, it))
 
 
@@ -160,14 +176,10 @@ class SolutionState(IntermediateState):
         if d is not None:
             from ._dev import _diag_times_csr, dia_jac
             return _diag_times_csr(dia_jac(-1.0 / d), resid_diff_u)
-        # one solve J du = -dR/dp per column
-        cols = _dense_rows(resid_diff_u)
-        J = _to_devcsr(self.jacobian)
-        out = []
-        for b in cols.T:
-            bd = torch.from_numpy(np.ascontiguousarray(b)).to(device())
-            out.append(-linsolve.solve(J, bd).cpu().numpy())
-        return DevCsr.from_scipy(sp.csr_matrix(np.transpose(out).reshape(cols.shape)))
+        # solves J du_k = -dR/dp_k, one per column: one solver set-up for all of them
+        cols_t = _dense_on_device(resid_diff_u, transpose=True)       # (n_p x n): row k = column k
+        du = linsolve.solve_multi(_to_devcsr(self.jacobian), cols_t, **linear_options)
+        return _sparse_from_dense(-du.t().contiguous())
 
 
 class adsolution(adarray):

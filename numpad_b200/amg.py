@@ -28,7 +28,7 @@ class Halo(ctypes.Structure):            # npb_halo: filled by shard.py for row-
 class CsrMat(ctypes.Structure):
     _fields_ = [('nrows', ctypes.c_int64), ('ncols', ctypes.c_int64), ('nnz', ctypes.c_int64),
                 ('indptr', ctypes.c_void_p), ('indices', ctypes.c_void_p),
-                ('data', ctypes.c_void_p), ('halo', Halo)]
+                ('data', ctypes.c_void_p), ('halo', Halo), ('data32', ctypes.c_void_p)]
 
 
 class AmgLevel(ctypes.Structure):
@@ -59,14 +59,47 @@ class LscStruct(ctypes.Structure):
                 ('amg_l', ctypes.c_void_p), ('cycles_a', ctypes.c_int32),
                 ('cycles_l', ctypes.c_int32), ('wv', ctypes.c_void_p * 5),
                 ('wp', ctypes.c_void_p * 8), ('scal', ctypes.c_void_p),
-                ('red', ctypes.c_void_p), ('a_gmres', ctypes.c_int32), ('pad', ctypes.c_int32),
+                ('red', ctypes.c_void_p), ('a_gmres', ctypes.c_int32), ('graph_id', ctypes.c_int32),
                 ('a_work', ctypes.c_void_p), ('a_work_bytes', ctypes.c_int64)]
 
 
-def csr_mat(A):
+# Operators of the preconditioner with at least this many rows are ALSO stored with fp32
+# values and applied from those (csrc/spmv_tma.cuh, value type float): the preconditioner is
+# an approximation anyway (a few multigrid cycles inside flexible GMRES, whose Krylov basis,
+# operator and residuals stay fp64), and its SpMVs are HBM-bound at 12 bytes per entry, 8 of
+# them the value.  0 disables.
+F32_MIN_ROWS = 200000
+_f32_cache = {}
+
+
+def f32_values(A):
+    """fp32 copy of A.data for large operators (None otherwise); cached per data tensor so that
+    the LSC blocks and the finest multigrid level share one copy"""
+    if not F32_MIN_ROWS or A.shape[0] < F32_MIN_ROWS or A.nnz == 0 or A.nnz / A.shape[0] > 96:
+        return None
+    key = (A.data.data_ptr(), A.nnz)
+    hit = _f32_cache.get(key)
+    if hit is not None and hit[0]() is A.data:
+        return hit[1]
+    import weakref
+    v = A.data.to(torch.float32)
+    if len(_f32_cache) > 64:
+        _f32_cache.clear()
+    _f32_cache[key] = (weakref.ref(A.data), v)
+    return v
+
+
+def csr_mat(A, keep=None):
+    """descriptor of a device CSR matrix; with `keep` (a list that outlives the descriptor) large
+    operators also get their fp32 values (see F32_MIN_ROWS)"""
     m = CsrMat()
     m.nrows, m.ncols, m.nnz = A.shape[0], A.shape[1], A.nnz
     m.indptr, m.indices, m.data = A.indptr.data_ptr(), A.indices.data_ptr(), A.data.data_ptr()
+    if keep is not None:
+        v = f32_values(A)
+        if v is not None:
+            keep.append(v)
+            m.data32 = v.data_ptr()
     return m
 
 
@@ -256,9 +289,9 @@ class Hierarchy:
         for l, lev in enumerate(levels):
             n = lev['A'].shape[0]
             L = self.arr[l]
-            L.A = csr_mat(lev['A'])
+            L.A = csr_mat(lev['A'], self.keep)
             if 'P' in lev:
-                L.P, L.R = csr_mat(lev['P']), csr_mat(lev['R'])
+                L.P, L.R = csr_mat(lev['P'], self.keep), csr_mat(lev['R'], self.keep)
             L.dinv = lev['dinv'].data_ptr()
             lev['work'] = [torch.zeros(n, dtype=torch.float64, device=device()) for _ in range(4)]
             L.x, L.x2, L.b, L.r = [w.data_ptr() for w in lev['work']]
@@ -393,11 +426,16 @@ class LscPreconditioner:
         s = self.struct = LscStruct()
         s.n, s.nv, s.np = n, nv, np_
         s.vset, s.pset = vset.data_ptr(), pset.data_ptr()
-        s.A, s.G, s.D, s.Lm = csr_mat(self.A), csr_mat(self.G), csr_mat(self.D), csr_mat(self.Lm)
+        self.keep = []
+        s.A, s.G, s.D, s.Lm = (csr_mat(m, self.keep) for m in (self.A, self.G, self.D, self.Lm))
         s.a_dinv = self.a_dinv.data_ptr()
         s.amg_a = self.amg_a.addr if self.amg_a is not None else None
         s.amg_l = self.amg_l.addr
         s.a_gmres = self.a_gmres
+        # the apply's launch sequence is fixed (device-resident CG scalars): csrc/amg.cu replays
+        # it as a CUDA graph under this id
+        LscPreconditioner._next_graph_id += 1
+        s.graph_id = self.graph_id = LscPreconditioner._next_graph_id
         if self.a_gmres > 0:
             s.a_work, s.a_work_bytes = self.a_work.data_ptr(), self.a_work.numel()
         if isinstance(cycles_l, (tuple, list)):      # (first L-solve, second L-solve)
@@ -410,6 +448,14 @@ class LscPreconditioner:
         s.scal, s.red = self.scal.data_ptr(), self.red.data_ptr()
         self.c_apply = ctypes.cast(_lib.lib().cdll.npb_lsc_apply_cb, ctypes.c_void_p).value
         self.c_ctx = ctypes.addressof(s)
+
+    _next_graph_id = 0
+
+    def __del__(self):
+        try:
+            _lib.lib().cdll.npb_lsc_graph_release(int(self.graph_id))
+        except Exception:
+            pass
 
     def apply(self, r, z):
         rc = _lib.lib().cdll.npb_lsc_apply_cb(self.c_ctx, r.data_ptr(), z.data_ptr(), stream_ptr())

@@ -113,8 +113,10 @@ class BlockTriLU:
         for k in range(K):
             r0, r1 = off[k], off[k + 1]
             m = r1 - r0
+            # S^T is assembled (not S): the library inverse comes back column-major, and the
+            # column-major image of (S^T)^-1 IS the row-major S^-1 the kernels read
             if k == 0:
-                S = torch.zeros((m, m), dtype=torch.float64, device=dev)
+                St = torch.zeros((m, m), dtype=torch.float64, device=dev)
             else:
                 q0, mp = off[k - 1], r0 - off[k - 1]
                 # Y = L_k S_{k-1}^-1   (m x mp): each row combines the few rows of S^-1 that
@@ -122,17 +124,17 @@ class BlockTriLU:
                 Y = torch.empty((m, mp), dtype=torch.float64, device=dev)
                 _call('npb_bt_window_spmm', Ap.indptr, Ap.indices, Ap.data, r0, r1, q0, r0,
                       self.Sinv[k - 1], mp, mp, 1.0, 0.0, Y, mp)
-                # W^T = U_{k-1}^T Y^T  (m x m): rows of A^T in level k, columns in level k-1
+                # -W^T = -U_{k-1}^T Y^T  (m x m): rows of A^T in level k, columns in level k-1
                 Yt = Y.t().contiguous()
-                Wt = torch.empty((m, m), dtype=torch.float64, device=dev)
+                St = torch.empty((m, m), dtype=torch.float64, device=dev)
                 _call('npb_bt_window_spmm', At.indptr, At.indices, At.data, r0, r1, q0, r0,
-                      Yt, m, m, -1.0, 0.0, Wt, m)
-                S = Wt.t().contiguous()                  # = -W
-                del Y, Yt, Wt
-            _call('npb_bt_window_to_dense', Ap.indptr, Ap.indices, Ap.data, r0, r1, r0, r1, 1.0, S, m)
-            Si, info = torch.linalg.inv_ex(S)
-            del S
-            self.Sinv.append(Si)
+                      Yt, m, m, -1.0, 0.0, St, m)
+                del Y, Yt
+            _call('npb_bt_window_to_dense', At.indptr, At.indices, At.data, r0, r1, r0, r1, 1.0, St, m)
+            Ri, info = torch.linalg.inv_ex(St)
+            del St
+            Si = Ri.t()
+            self.Sinv.append(Si if Si.is_contiguous() else Si.contiguous())
             infos.append(info)
         bad = torch.stack(infos).ne(0).nonzero().reshape(-1)
         if bad.numel():

@@ -16,6 +16,8 @@
 // Krylov loop).
 #include <math.h>
 
+#include <map>
+
 #include "common.cuh"
 #include "dist.cuh"
 #include "scan.cuh"
@@ -27,7 +29,7 @@ int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, 
 int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                 const double* dat, const double* x, int mode, const double* b,
                 const double* dinv, double omega, double* y, int variant, cudaStream_t st,
-                const npb_halo* halo, const npb_wait* wait);
+                const npb_halo* halo, const npb_wait* wait, const float* dat32);
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st);
 
@@ -497,6 +499,8 @@ struct npb_csr_mat {
     const int32_t* indices;
     const double* data;
     npb_halo halo;         // halo.dist != NULL: rows of a row-sharded operator (dist.cuh)
+    const float* data32;   // != NULL: the values rounded to fp32 (preconditioner operators:
+                           // 8 instead of 12 bytes per entry; sums, x and y stay fp64)
 };
 
 // y = epilogue(M x): 0: Mx  1: b - Mx  2: b + Mx  3: x + omega dinv (b - Mx); a sharded
@@ -512,10 +516,10 @@ static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* 
         if (rc) return rc;
         h.recv = const_cast<double*>(xh);
         return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y,
-                           0, st, &h, &w);
+                           0, st, &h, &w, nullptr);
     }
     return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y, 0,
-                       st, nullptr, nullptr);
+                       st, nullptr, nullptr, M.data32);
 }
 
 struct npb_amg_level {
@@ -559,65 +563,72 @@ static int jacobi_sweep(const npb_amg_level& L, double omega, const double* b, c
 int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
     cudaStream_t st = ST(stream);
     const int nl = h->nlevels;
+    if (nl > 64) { npb_set_error("amg_vcycle: more than 64 levels"); return NPB_ERR_ARG; }
+    // which of the two ping-pong buffers of a level holds its iterate: kept in locals, the
+    // level descriptors are never modified, so the launch sequence of a cycle (buffers
+    // included) is the same on every call -- a captured CUDA graph of it can be replayed
+    double* X[64];
+    double* X2[64];
+    double* CB[64];          // right-hand side of level l (l >= 1)
+    for (int l = 0; l < nl; ++l) { X[l] = h->levels[l].x; X2[l] = h->levels[l].x2; CB[l] = h->levels[l].b; }
     // downward
     for (int l = 0; l < nl; ++l) {
         npb_amg_level& L = h->levels[l];
         const int64_t n = L.A.nrows;
-        const double* bl = (l == 0) ? b : L.b;
+        const double* bl = (l == 0) ? b : CB[l];
         if (l == nl - 1 && h->coarse_n > 0) {
-            double* xl = (l == 0) ? x : L.x;
+            double* xl = (l == 0) ? x : X[l];
             k_dense_mv<<<npb_blocks((int64_t)h->coarse_n * 32, TPB), TPB, 0, st>>>(h->coarse_n, h->coarse_inv, bl, xl);
             NPB_COUNT_LAUNCH();
             break;
         }
         // pre-smoothing from zero: x = omega dinv b, then nu_pre-1 sweeps
-        double* cur = L.x;
-        double* oth = L.x2;
+        double* cur = X[l];
+        double* oth = X2[l];
         k_jacobi0<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, L.dinv, h->omega, bl, cur);
         NPB_COUNT_LAUNCH();
+        NPB_COUNT_BYTES(24.0 * n);
         const int extra = (l == nl - 1) ? (h->nu_pre + h->nu_post + 6) : (h->nu_pre - 1);
         for (int s = 0; s < extra; ++s) {
             jacobi_sweep(L, h->omega, bl, cur, oth, st);
             double* t = cur; cur = oth; oth = t;
         }
-        if (cur != L.x) { double* t = L.x; L.x = L.x2; L.x2 = t; }   // keep the iterate in L.x
+        X[l] = cur; X2[l] = oth;                      // the iterate is in X[l]
         if (l == nl - 1) {
-            if (l == 0) NPB_CUDA(cudaMemcpyAsync(x, L.x, n * 8, cudaMemcpyDeviceToDevice, st));
+            if (l == 0) NPB_CUDA(cudaMemcpyAsync(x, X[l], n * 8, cudaMemcpyDeviceToDevice, st));
             break;
         }
         // r = b - A x ; b_{l+1} = R r
-        int rc = spmv_mat(L.A, L.x, bl, L.r, 1, st);
+        int rc = spmv_mat(L.A, X[l], bl, L.r, 1, st);
         if (rc) return rc;
-        npb_amg_level& C = h->levels[l + 1];
         if (L.gather) {
             const npb_dist* d = (const npb_dist*)h->dist;
             if (L.g_data >= 0 && npb_dist_heap_ptr(d, 0)) {
                 const unsigned long long seq = ++(*L.g_seq);
                 const int64_t elem_off = (int64_t)(seq & 1) * L.offsets[d->world];
-                C.b = npb_dist_heap_ptr(d, L.g_data) + elem_off;
-                rc = spmv_mat(L.R, L.r, nullptr, C.b + L.offsets[d->rank], 0, st);
+                CB[l + 1] = npb_dist_heap_ptr(d, L.g_data) + elem_off;
+                rc = spmv_mat(L.R, L.r, nullptr, CB[l + 1] + L.offsets[d->rank], 0, st);
                 if (!rc) rc = npb_dist_push_slice(d, L.g_data, L.g_flags, elem_off, L.offsets, seq, st);
             } else {
-                double* mine = C.b + L.offsets[d->rank];
+                double* mine = CB[l + 1] + L.offsets[d->rank];
                 rc = spmv_mat(L.R, L.r, nullptr, mine, 0, st);
-                if (!rc) rc = npb_dist_allgatherv(d, mine, C.b, L.offsets, st);
+                if (!rc) rc = npb_dist_allgatherv(d, mine, CB[l + 1], L.offsets, st);
             }
         } else {
-            rc = spmv_mat(L.R, L.r, nullptr, C.b, 0, st);
+            rc = spmv_mat(L.R, L.r, nullptr, CB[l + 1], 0, st);
         }
         if (rc) return rc;
     }
     // upward
     for (int l = nl - 2; l >= 0; --l) {
         npb_amg_level& L = h->levels[l];
-        npb_amg_level& C = h->levels[l + 1];
         const int64_t n = L.A.nrows;
-        const double* bl = (l == 0) ? b : L.b;
+        const double* bl = (l == 0) ? b : CB[l];
         // x += P x_{l+1}
-        int rc = spmv_mat(L.P, C.x, L.x, L.x, 2, st);
+        int rc = spmv_mat(L.P, X[l + 1], X[l], X[l], 2, st);
         if (rc) return rc;
-        double* cur = L.x;
-        double* oth = L.x2;
+        double* cur = X[l];
+        double* oth = X2[l];
         for (int s = 0; s < h->nu_post; ++s) {
             double* out = (l == 0 && s == h->nu_post - 1) ? x : oth;
             jacobi_sweep(L, h->omega, bl, cur, out, st);
@@ -626,8 +637,8 @@ int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
         }
         if (l == 0) {
             if (cur != x) NPB_CUDA(cudaMemcpyAsync(x, cur, n * 8, cudaMemcpyDeviceToDevice, st));
-        } else if (cur != L.x) {
-            double* t = L.x; L.x = L.x2; L.x2 = t;
+        } else {
+            X[l] = cur; X2[l] = oth;
         }
     }
     NPB_CHECK_LAUNCH("amg_vcycle");
@@ -716,16 +727,17 @@ struct npb_lsc {
     // robust mode for convection-dominated momentum blocks (a_gmres > 0): the
     // A-solve is a_gmres steps of Jacobi-preconditioned GMRES (cannot diverge,
     // unlike a Jacobi-smoothed V-cycle on a matrix without diagonal dominance)
-    int32_t a_gmres, pad;
+    int32_t a_gmres;
+    int32_t graph_id;          // > 0: the launch sequence may be replayed as a CUDA graph (unique id)
     void* a_work;              // npb_fgmres_workspace_bytes(nv, a_gmres, 0)
     int64_t a_work_bytes;
 };
 
 // the host structs above are declared a second time in include/numpad_b200.h (and mirrored
 // with ctypes, tests/test_abi.py): a one-sided edit must not compile
-static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 112, "npb_csr_mat layout");
-static_assert(sizeof(npb_amg_level) == 416 && sizeof(npb_amg) == 48, "npb_amg layout");
-static_assert(sizeof(npb_amg_precond) == 144 && sizeof(npb_lsc) == 664, "npb_lsc layout");
+static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 120, "npb_csr_mat layout");
+static_assert(sizeof(npb_amg_level) == 440 && sizeof(npb_amg) == 48, "npb_amg layout");
+static_assert(sizeof(npb_amg_precond) == 152 && sizeof(npb_lsc) == 696, "npb_lsc layout");
 
 // y = d .* x as an npb_apply_fn (Jacobi preconditioner; ctx = npb_diag_ctx)
 struct npb_diag_ctx { int64_t n; const double* d; };
@@ -757,20 +769,16 @@ static int lsc_solve_a(const npb_lsc* c, const double* b, double* x, double* r, 
 }
 
 
-int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
+// the launch sequence between the gathers of r and the scatters into z: fixed buffers, device-
+// resident scalars, no host decision -- capturable
+static int lsc_core(const npb_lsc* c, cudaStream_t st) {
     // block upper-triangular form:  p = S~^-1 r_P ;  u = A~^-1 (r_V - G p)
-    const npb_lsc* c = (const npb_lsc*)ctx;
-    cudaStream_t st = ST(stream);
-    const int64_t nv = c->nv, np = c->np;
+    const int64_t np = c->np;
     double *rv = c->wv[0], *us = c->wv[1], *t1 = c->wv[2], *t2 = c->wv[3];
     double *rp = c->wp[0], *q = c->wp[1], *p1 = c->wp[2], *s1 = c->wp[3], *s2 = c->wp[4];
     double *s3 = c->wp[5], *s4 = c->wp[6];
     int rc;
-    k_gather<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, r, rv);
-    NPB_COUNT_LAUNCH();
     if (np > 0) {
-        k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, rp);
-        NPB_COUNT_LAUNCH();
         // p1 = L^-1 r_P            (L = -DG, so S^-1 ~ -L^-1 (D A G) L^-1)
         // cycles_l: CG steps of the first L-solve in the low 16 bits, of the second one in
         // the high 16 bits (0: the same)
@@ -786,12 +794,98 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
         if ((rc = npb_axpby_launch(np, 0.0, p1, -1.0, p1, st))) return rc;
         // r_V <- r_V - G p
         if ((rc = spmv_mat(c->G, p1, rv, rv, 1, st))) return rc;
-        k_scatter<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, p1, z);
-        NPB_COUNT_LAUNCH();
     }
     // u = A~^-1 (r_V - G p)
-    if ((rc = lsc_solve_a(c, rv, us, t1, t2, st))) return rc;
-    k_scatter<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, us, z);
+    return lsc_solve_a(c, rv, us, t1, t2, st);
+}
+
+// CUDA graphs of lsc_core, one per preconditioner (npb_lsc::graph_id > 0, unique for the
+// lifetime of the process; released by npb_lsc_graph_release).  The first application runs
+// eagerly (lazy kernel attributes settle), the second is captured on an internal stream and
+// instantiated, later ones are ONE cudaGraphLaunch instead of ~300 kernel launches: the
+// coarse-level kernels of the two multigrid hierarchies are shorter than their launch cost.
+struct lsc_graph {
+    int calls = 0;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long launches = 0;
+    double bytes = 0.0;
+    bool failed = false;
+};
+static std::map<int, lsc_graph> g_lsc_graphs;
+static cudaStream_t g_capture_stream = nullptr;
+static int g_graphs_enabled = 1;
+
+int npb_lsc_graphs_enable(int on) { const int old = g_graphs_enabled; g_graphs_enabled = on ? 1 : 0; return old; }
+
+int npb_lsc_graph_release(int graph_id) {
+    auto it = g_lsc_graphs.find(graph_id);
+    if (it == g_lsc_graphs.end()) return NPB_OK;
+    if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+    g_lsc_graphs.erase(it);
+    return NPB_OK;
+}
+
+int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
+    const npb_lsc* c = (const npb_lsc*)ctx;
+    cudaStream_t st = ST(stream);
+    const int64_t nv = c->nv, np = c->np;
+    int rc = NPB_OK;
+    k_gather<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, r, c->wv[0]);
+    NPB_COUNT_LAUNCH();
+    if (np > 0) {
+        k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, c->wp[0]);
+        NPB_COUNT_LAUNCH();
+    }
+    const bool graphable = g_graphs_enabled && c->graph_id > 0 && c->a_gmres <= 0 && !c->A.halo.dist &&
+                           !c->Lm.halo.dist && !(c->amg_a && c->amg_a->dist) && !c->amg_l->dist;
+    lsc_graph* g = graphable ? &g_lsc_graphs[c->graph_id] : nullptr;
+    if (g && !g->failed && g->exec) {
+        if (cudaGraphLaunch(g->exec, st) != cudaSuccess) {
+            npb_set_error("lsc_apply: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return NPB_ERR_CUDA;
+        }
+        npb_launch_counter += g->launches;
+        npb_bytes_counter += g->bytes;
+    } else if (g && !g->failed && g->calls >= 1) {
+        // capture on an internal stream (the caller's may be the legacy default stream, which
+        // cannot be captured); nothing executes during capture
+        if (!g_capture_stream) NPB_CUDA(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+        const unsigned long long l0 = npb_launch_counter;
+        const double b0 = npb_bytes_counter;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            rc = lsc_core(c, g_capture_stream);
+            ok = (cudaStreamEndCapture(g_capture_stream, &graph) == cudaSuccess) && rc == NPB_OK && graph;
+        }
+        if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        g->launches = npb_launch_counter - l0;
+        g->bytes = npb_bytes_counter - b0;
+        npb_launch_counter = l0;
+        npb_bytes_counter = b0;
+        if (!ok) {                       // fall back to eager launches for this preconditioner
+            cudaGetLastError();
+            g->failed = true;
+            g->exec = nullptr;
+            if ((rc = lsc_core(c, st))) return rc;
+        } else {
+            if (cudaGraphLaunch(g->exec, st) != cudaSuccess) {
+                npb_set_error("lsc_apply: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return NPB_ERR_CUDA;
+            }
+            npb_launch_counter += g->launches;
+            npb_bytes_counter += g->bytes;
+        }
+    } else {
+        if ((rc = lsc_core(c, st))) return rc;
+    }
+    if (g) g->calls++;
+    if (np > 0) {
+        k_scatter<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, c->wp[2], z);
+        NPB_COUNT_LAUNCH();
+    }
+    k_scatter<<<npb_blocks(nv, TPB), TPB, 0, st>>>(nv, c->vset, c->wv[1], z);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("lsc_apply");
     return NPB_OK;

@@ -29,9 +29,9 @@ struct tm_geom {
     static constexpr int CAP = CAP_, STAGES = STAGES_, CTAS = CTAS_;
 };
 
-template <class G>
+template <class G, class T>
 struct tm_smem {
-    alignas(128) double val[G::STAGES][G::CAP];
+    alignas(128) T val[G::STAGES][G::CAP];
     alignas(128) int32_t idx[G::STAGES][G::CAP];
     alignas(8) unsigned long long full[G::STAGES];
     unsigned long long empty[G::STAGES];
@@ -70,10 +70,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-template <int ROWS, int RPT, class G, bool HALO>
+// T = value type of the stored matrix: double, or float for the operators of the multigrid
+// preconditioner (8 instead of 12 bytes per entry; x, y and the sums stay fp64)
+template <int ROWS, int RPT, class G, bool HALO, class T>
 __global__ void __launch_bounds__(TM_THREADS, G::CTAS)
 k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict__ ptr,
-           const int32_t* __restrict__ idx, const double* __restrict__ dat,
+           const int32_t* __restrict__ idx, const T* __restrict__ dat,
            const double* x, spmv_epi epi, double* y) {
     constexpr int TPR = TM_CONSUMERS / ROWS;
     constexpr int UROWS = ROWS * RPT;            // rows per unit
@@ -81,7 +83,7 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
     static_assert(RPT == 1 || TPR == 1, "several rows per thread only with one thread per row");
     constexpr int TM_CAP = G::CAP, TM_STAGES = G::STAGES;
     extern __shared__ __align__(128) unsigned char tm_raw[];
-    tm_smem<G>& S = *reinterpret_cast<tm_smem<G>*>(
+    tm_smem<G, T>& S = *reinterpret_cast<tm_smem<G, T>*>(
         (reinterpret_cast<uintptr_t>(tm_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x;
     if (HALO) npb_wait_peers(epi.wait);
@@ -132,9 +134,9 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
                     S.val[stage][k - lo] = dat[k];
                 }
                 if (ne > 0) {
-                    mbar_arrive_tx(&S.full[stage], (unsigned)ne * 12u);
+                    mbar_arrive_tx(&S.full[stage], (unsigned)ne * (4u + (unsigned)sizeof(T)));
                     bulk_g2s(&S.idx[stage][0], idx + lo, (unsigned)ne * 4u, &S.full[stage], policy);
-                    bulk_g2s(&S.val[stage][0], dat + lo, (unsigned)ne * 8u, &S.full[stage], policy);
+                    bulk_g2s(&S.val[stage][0], dat + lo, (unsigned)ne * (unsigned)sizeof(T), &S.full[stage], policy);
                 } else {
                     mbar_arrive(&S.full[stage]);
                 }
@@ -200,7 +202,7 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
             const int32_t hi = min(lo + TM_CAP, k1);
             mbar_wait(&S.full[stage], phase);
             const int32_t* si = &S.idx[stage][0];
-            const double* sv = &S.val[stage][0];
+            const T* sv = &S.val[stage][0];
             // gathers of all RPT rows are issued GB at a time before any of them is
             // used: one memory latency per batch instead of one per row / per 4 entries
             int32_t kk[RPT], ee[RPT];
@@ -227,7 +229,7 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
 #pragma unroll
                     for (int g = 0; g < GB; ++g) {
                         const int32_t k = kk[j] + g * TPR;
-                        if (k < ee[j]) a_ = fma(sv[k], xv[j][g], a_);
+                        if (k < ee[j]) a_ = fma((double)sv[k], xv[j][g], a_);
                     }
                     acc[j] = a_;
                     kk[j] += GB * TPR;
@@ -297,21 +299,21 @@ static inline int64_t tma_min_rows(double mean) {
     return (int64_t)s.rows * s.rpt * NPB_NUM_SMS * tma_ctas(g) * 2;
 }
 
-template <int ROWS, int RPT, class G, bool HALO>
+template <int ROWS, int RPT, class G, bool HALO, class T>
 static int launch_spmv_tma_h(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
-                           const double* dat, const double* x, const spmv_epi& e, double* y,
+                           const T* dat, const double* x, const spmv_epi& e, double* y,
                            cudaStream_t st) {
     static bool configured = false;
-    const size_t sh = sizeof(tm_smem<G>) + 128;
+    const size_t sh = sizeof(tm_smem<G, T>) + 128;
     if (!configured) {
-        NPB_CUDA(cudaFuncSetAttribute(k_spmv_tma<ROWS, RPT, G, HALO>,
+        NPB_CUDA(cudaFuncSetAttribute(k_spmv_tma<ROWS, RPT, G, HALO, T>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         configured = true;
     }
     const int64_t nunits = (nrows + ROWS * RPT - 1) / (ROWS * RPT);
     const int64_t cap = (int64_t)NPB_NUM_SMS * G::CTAS;
     const int grid = (int)(nunits < cap ? nunits : cap);
-    k_spmv_tma<ROWS, RPT, G, HALO><<<grid, TM_THREADS, sh, st>>>(nrows, nnz, nunits, ptr, idx, dat, x, e, y);
+    k_spmv_tma<ROWS, RPT, G, HALO, T><<<grid, TM_THREADS, sh, st>>>(nrows, nnz, nunits, ptr, idx, dat, x, e, y);
     return NPB_OK;
 }
 
@@ -321,13 +323,20 @@ template <int ROWS, int RPT, class G>
 static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                            const double* dat, const double* x, const spmv_epi& e, double* y,
                            cudaStream_t st) {
-    return e.xh ? launch_spmv_tma_h<ROWS, RPT, G, true>(nrows, nnz, ptr, idx, dat, x, e, y, st)
-                : launch_spmv_tma_h<ROWS, RPT, G, false>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+    return e.xh ? launch_spmv_tma_h<ROWS, RPT, G, true, double>(nrows, nnz, ptr, idx, dat, x, e, y, st)
+                : launch_spmv_tma_h<ROWS, RPT, G, false, double>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+}
+// fp32-stored operators: single-GPU only (the sharded hierarchy keeps fp64 values)
+template <int ROWS, int RPT, class G>
+static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                           const float* dat, const double* x, const spmv_epi& e, double* y,
+                           cudaStream_t st) {
+    return launch_spmv_tma_h<ROWS, RPT, G, false, float>(nrows, nnz, ptr, idx, dat, x, e, y, st);
 }
 
-template <class G>
+template <class G, class T>
 static int spmv_tma_dispatch_g(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
-                               const double* dat, const double* x, const spmv_epi& e, double* y,
+                               const T* dat, const double* x, const spmv_epi& e, double* y,
                                cudaStream_t st) {
     const tma_shape s = tma_shape_for((double)nnz / (double)nrows, G::CAP);
     if (s.rpt == 4) return launch_spmv_tma<256, 4, G>(nrows, nnz, ptr, idx, dat, x, e, y, st);
@@ -340,14 +349,15 @@ static int spmv_tma_dispatch_g(int64_t nrows, int64_t nnz, const int32_t* ptr, c
     }
 }
 
+template <class T>
 static int spmv_tma_dispatch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
-                             const double* dat, const double* x, const spmv_epi& e, double* y,
+                             const T* dat, const double* x, const spmv_epi& e, double* y,
                              cudaStream_t st) {
     switch (tma_geometry_for((double)nnz / (double)nrows)) {
-        case 1: return spmv_tma_dispatch_g<tm_geom<2304, 3, 2>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        case 2: return spmv_tma_dispatch_g<tm_geom<2304, 2, 3>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        case 3: return spmv_tma_dispatch_g<tm_geom<1536, 3, 4>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        default: return spmv_tma_dispatch_g<tm_geom<3072, 3, 2>>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 1: return spmv_tma_dispatch_g<tm_geom<2304, 3, 2>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 2: return spmv_tma_dispatch_g<tm_geom<2304, 2, 3>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 3: return spmv_tma_dispatch_g<tm_geom<1536, 3, 4>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        default: return spmv_tma_dispatch_g<tm_geom<3072, 3, 2>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
     }
 }
 

@@ -32,7 +32,7 @@ last_info = {}      # filled by every solve: iterations, residuals, method
 # later systems of the same signature (the next Newton iterations and time steps of the same
 # run) go straight to the robust solver instead of failing first
 _hints = {'robust': False, 'sig': None}
-_stale = {'btlu': None, 'sig': None}     # last block-tridiagonal factorisation (reused as a
+_stale = {'btlu': None, 'sig': None, 'transposed': False}     # last block-tridiagonal factorisation (reused as a
                                          # preconditioner while the Jacobian has not moved far)
 
 
@@ -163,6 +163,21 @@ def _solve_sharded(A, b, o):
     return x
 
 
+def _btlu_refined(M, A, b, o, transposed=False):
+    """x from the block-tridiagonal factors M of A (of A^T when `transposed`: then M's
+    transposed sweeps are used) + FGMRES refinement"""
+    pc = M.apply_t if transposed else M.apply
+    x0 = M.solve(b, transpose=transposed)
+    # refinement: a few preconditioned steps towards 1e-2 of the requested tolerance (a direct
+    # solve is expected to deliver SuperLU-class residuals, and each step is one pair of sweeps);
+    # accepted at the requested tolerance
+    x, res = fgmres(A, b, x0=x0, precond=pc, rtol=max(1e-2 * o['rtol'], 2e-15), atol=o['atol'],
+                    restart=8, maxiter=8)
+    if res['rnorm'] <= max(o['rtol'] * res['bnorm'], o['atol']):
+        res['status'] = 0
+    return x, res
+
+
 def _solve_btlu(A, b, o, t0):
     """block-tridiagonal direct solve + FGMRES refinement to the requested tolerance; a
     factorisation of an earlier Jacobian of the same pattern is first tried as the
@@ -174,8 +189,13 @@ def _solve_btlu(A, b, o, t0):
     info = {}
     M = _stale['btlu'] if _stale['sig'] == sig else None
     if M is not None and o.get('btlu_reuse', True):
-        x, res = fgmres(A, b, precond=M.apply, rtol=o['rtol'], atol=o['atol'], restart=30, maxiter=30)
+        # (for A = J^T the factors of J serve through their transposed sweeps)
+        use_t = bool(o.get('_transposed')) != bool(_stale['transposed'])
+        x, res = fgmres(A, b, precond=M.apply_t if use_t else M.apply, rtol=o['rtol'],
+                        atol=o['atol'], restart=30, maxiter=30)
         if res['status'] == 0:
+            if o.get('_keep') is not None:
+                o['_keep'].update(M=M, method='btlu-stale', A=A, use_t=use_t)
             res.update(method='btlu (reused factorisation)', setup_ms=0.0, krylov_ms=1e3 * (_now() - t0),
                        precond=M.describe())
             last_info.clear()
@@ -194,8 +214,7 @@ def _solve_btlu(A, b, o, t0):
         return None
     t_setup = _now() - t0
     t1 = _now()
-    x0 = M.solve(b)
-    x, res = fgmres(A, b, x0=x0, precond=M.apply, rtol=o['rtol'], atol=o['atol'], restart=20, maxiter=40)
+    x, res = _btlu_refined(M, A, b, o)
     res.update(info, method='btlu', setup_ms=1e3 * t_setup, krylov_ms=1e3 * (_now() - t1),
                precond=M.describe())
     last_info.clear()
@@ -209,7 +228,9 @@ def _solve_btlu(A, b, o, t0):
               (res['setup_ms'], res['iters'], res['rnorm'] / max(res['bnorm'], 1e-300)))
     if res['status'] != 0:
         return None
-    _stale['btlu'], _stale['sig'] = M, sig
+    _stale['btlu'], _stale['sig'], _stale['transposed'] = M, sig, bool(o.get('_transposed'))
+    if o.get('_keep') is not None:
+        o['_keep'].update(M=M, method='btlu', A=A)
     return x
 
 
@@ -217,11 +238,15 @@ def solve(A, b, transpose=False, **opts):
     """x = A^{-1} b (or A^{-T} b) for a DevCsr A and a device vector b."""
     o = dict(DEFAULTS)
     o.update(opts)
+    keep = o.get('_keep')
+    b = b.reshape(-1).contiguous()
+    if keep is not None and 'M' in keep:
+        return _solve_again(keep, b, o)
     if transpose:
         A = A.transpose()
+        o['_transposed'] = True
     A = A.materialized()
     n = A.shape[0]
-    b = b.reshape(-1).contiguous()
     from . import precond as _pc
     if o['shard_owner'] is not None and not _hints['robust'] and o['precond'] in ('auto', 'lsc'):
         x = _solve_sharded(A, b, o)
@@ -253,6 +278,8 @@ def solve(A, b, transpose=False, **opts):
         res['setup_ms'] = 1e3 * t_setup
         last_info.clear()
         last_info.update(res)
+        if keep is not None:
+            keep.update(M=M, method=method, A=A)
         return x
     t0 = _now()
     pc = None if M is None else (M if hasattr(M, 'c_apply') else M.apply)
@@ -293,4 +320,48 @@ def solve(A, b, transpose=False, **opts):
         raise LinearSolveError('linear solve (%s) did not converge: %d iterations, '
                                '|r|/|b| = %.3e' % (method, res['iters'],
                                                   res['rnorm'] / max(res['bnorm'], 1e-300)))
+    if keep is not None:
+        keep.update(M=M, method=method, A=A, maxit=maxit)
     return x
+
+
+def _solve_again(keep, b, o):
+    """another right-hand side for the matrix of an earlier solve(..., _keep=keep): the built
+    factorisation / preconditioner is applied again, nothing is set up"""
+    M, method, A = keep['M'], keep['method'], keep['A']
+    t0 = _now()
+    if method == 'direct':
+        x = M.solve(b)
+        r = b - A.matvec(x)
+        res = dict(status=0, iters=0, rnorm=float(r.norm()), bnorm=float(b.norm()))
+        if res['rnorm'] > o['rtol'] * max(res['bnorm'], 1e-300):
+            x = x + M.solve(r)
+            res['rnorm'] = float((b - A.matvec(x)).norm())
+    elif method == 'btlu':
+        x, res = _btlu_refined(M, A, b, o)
+    elif method == 'btlu-stale':
+        x, res = fgmres(A, b, precond=M.apply_t if keep.get('use_t') else M.apply, rtol=o['rtol'],
+                        atol=o['atol'], restart=30, maxiter=60)
+    else:
+        pc = None if M is None else (M if hasattr(M, 'c_apply') else M.apply)
+        x, res = fgmres(A, b, precond=pc, rtol=o['rtol'], atol=o['atol'],
+                        restart=min(o['restart'], A.shape[0]), maxiter=keep.get('maxit', o['maxiter']))
+    res.update(method=method + ' (solver reused)', setup_ms=0.0, krylov_ms=1e3 * (_now() - t0))
+    last_info.clear()
+    last_info.update(res)
+    if res['status'] != 0:
+        raise LinearSolveError('linear solve (%s, reused) did not converge: |r|/|b| = %.3e'
+                               % (method, res['rnorm'] / max(res['bnorm'], 1e-300)))
+    return x
+
+
+def solve_multi(A, B, transpose=False, **opts):
+    """X with A X[k] = B[k] (or A^T X[k] = B[k]) for the rows of the dense device matrix B
+    (k x n): the reference loops one LU solve per row / column of a densified operand
+    (adsolve.py:74-82, 137-145); here the solver -- factorisation or preconditioner hierarchy
+    -- is built ONCE for the first right-hand side and reused for the others."""
+    keep = {}
+    X = torch.empty_like(B)
+    for k in range(B.shape[0]):
+        X[k] = solve(A, B[k], transpose=transpose, **dict(opts, _keep=keep))
+    return X

@@ -84,3 +84,38 @@ def test_failed_linear_solve_falls_back_to_continuation(npd, monkeypatch):
     assert np.isfinite(u._n_Newton)
     r = np.asarray(u._value)
     np.testing.assert_allclose(r ** 3 + 2 * r - 1.0, 0.0, atol=1e-5)
+
+
+def test_lsc_graph_replay_and_fp32_operators_do_not_change_the_solve(npd):
+    """the preconditioner's launch sequence replayed as a CUDA graph gives bit-identical
+    iterates to eager launches; storing the preconditioner's large operators in fp32 changes
+    the iteration count by at most a few and never the answer (FGMRES is fp64 outside)"""
+    import torch
+    from numpad_b200 import linsolve, precond, amg, _lib
+    from numpad_b200.workloads.cavity import CavityProblem
+    P = CavityProblem(npd, 320)             # pressure block above amg.F32_MIN_ROWS? no: force it
+    u0 = P.fixed_state()
+    u = npd.array(u0.copy())
+    res = P.residual(u, npd.array(u0), 1.0, 0)
+    J = npd.diff_dev(res, u).materialized()
+    b = res._dev.reshape(-1).contiguous()
+    L = _lib.lib().cdll
+    out = {}
+    old_min = amg.F32_MIN_ROWS
+    try:
+        for tag, graphs, f32 in (('eager64', 0, 0), ('graph64', 1, 0), ('graph32', 1, 50000)):
+            amg.F32_MIN_ROWS = f32
+            precond.forget()
+            linsolve.reset_hints()
+            L.npb_lsc_graphs_enable(graphs)
+            x = linsolve.solve(J, b, precond='lsc')
+            out[tag] = (x.clone(), linsolve.last_info['iters'],
+                        linsolve.last_info['rnorm'] / linsolve.last_info['bnorm'])
+    finally:
+        amg.F32_MIN_ROWS = old_min
+        L.npb_lsc_graphs_enable(1)
+        precond.forget()
+    assert torch.equal(out['eager64'][0], out['graph64'][0]) and out['eager64'][1] == out['graph64'][1]
+    assert out['graph32'][2] <= 1e-12 and abs(out['graph32'][1] - out['eager64'][1]) <= 4
+    ref = out['eager64'][0]
+    assert float((out['graph32'][0] - ref).norm() / ref.norm()) < 1e-9

@@ -310,6 +310,14 @@ def test_spmv_tma_pipeline(dev, nrows, ncols, per_row):
         got = y.cpu().numpy()
         tol = 1e-13 * scale * (1 + np.abs(dinv).max() if mode == 3 else 1)
         np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+        # the same operator stored with fp32 values (preconditioner SpMV): exact for the
+        # rounded matrix
+        a32 = sp.csr_matrix((a.data.astype(np.float32).astype(np.float64), idx, ptr), shape=(nrows, ncols))
+        ax32 = a32 @ x
+        want32 = [ax32, b - ax32, b + ax32, (x[:nrows] + 0.7 * dinv * (b - ax32)) if nrows == ncols else None][mode]
+        y = torch.full((nrows,), np.nan, dtype=torch.float64, device=dev.device())
+        dev._call('npb_spmv_f32', nrows, nnz, ptr_d, idx_d, t(a.data.astype(np.float32)), xd, mode, bd, dd, 0.7, y)
+        np.testing.assert_allclose(y.cpu().numpy(), want32, rtol=0, atol=tol)
 
 
 @pytest.mark.parametrize('n,k', [(1, 1), (7, 3), (1000, 1), (4097, 5), (200001, 17), (300000, 40),
