@@ -110,7 +110,17 @@ class BlockTriLU:
         self.mmax = mmax
         self.Sinv = []
         infos = []
+        import os
+        prof = os.environ.get('NPB_BT_PROFILE')
+        marks = []
+
+        def mark(tag):
+            if prof:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((tag, e))
         for k in range(K):
+            mark('start')
             r0, r1 = off[k], off[k + 1]
             m = r1 - r0
             # S^T is assembled (not S): the library inverse comes back column-major, and the
@@ -125,17 +135,29 @@ class BlockTriLU:
                 _call('npb_bt_window_spmm', Ap.indptr, Ap.indices, Ap.data, r0, r1, q0, r0,
                       self.Sinv[k - 1], mp, mp, 1.0, 0.0, Y, mp)
                 # -W^T = -U_{k-1}^T Y^T  (m x m): rows of A^T in level k, columns in level k-1
+                mark('spmm1')
                 Yt = Y.t().contiguous()
+                mark('transpose')
                 St = torch.empty((m, m), dtype=torch.float64, device=dev)
                 _call('npb_bt_window_spmm', At.indptr, At.indices, At.data, r0, r1, q0, r0,
                       Yt, m, m, -1.0, 0.0, St, m)
                 del Y, Yt
+                mark('spmm2')
             _call('npb_bt_window_to_dense', At.indptr, At.indices, At.data, r0, r1, r0, r1, 1.0, St, m)
+            mark('scatter')
             Ri, info = torch.linalg.inv_ex(St)
+            mark('inverse')
             del St
             Si = Ri.t()
             self.Sinv.append(Si if Si.is_contiguous() else Si.contiguous())
             infos.append(info)
+        if prof:
+            torch.cuda.synchronize()
+            tot = {}
+            for (t0, e0), (t1, e1) in zip(marks[:-1], marks[1:]):
+                if t1 != 'start':
+                    tot[t1] = tot.get(t1, 0.0) + e0.elapsed_time(e1)
+            print('    btlu factor profile (ms):', {k_: round(v, 1) for k_, v in tot.items()}, flush=True)
         bad = torch.stack(infos).ne(0).nonzero().reshape(-1)
         if bad.numel():
             raise np.linalg.LinAlgError('block-tridiagonal LU: singular diagonal block at level %d'
@@ -143,46 +165,42 @@ class BlockTriLU:
         self.scratch = torch.empty(int(_lib.lib().cdll.npb_bt_gemv_scratch_doubles(mmax)),
                                    dtype=torch.float64, device=dev)
         self.bytes = sum(s.numel() for s in self.Sinv) * 8
+        # host descriptors + device work buffers of the solve phase
+        self.off_h = np.asarray(off, dtype=np.int64)
+        self.sinv_h = np.asarray([s.data_ptr() for s in self.Sinv], dtype=np.uint64)
+        self.bp = torch.empty(n, dtype=torch.float64, device=dev)
+        self.z = torch.empty(n, dtype=torch.float64, device=dev)
+        self.c = torch.empty(mmax, dtype=torch.float64, device=dev)
+        BlockTriLU._next_graph_id += 1
+        self.graph_id = BlockTriLU._next_graph_id
 
     def describe(self):
         return ('block-tridiagonal LU: %d levels, largest block %d, %.1f GB of dense inverses'
                 % (self.K, self.mmax, self.bytes / 1e9))
 
+    _next_graph_id = 0
+
+    def __del__(self):
+        try:
+            _lib.lib().cdll.npb_bt_graph_release(int(self.graph_id))
+        except Exception:
+            pass
+
     def solve(self, b, transpose=False):
-        """x = A^-1 b (or A^-T b)"""
-        off, K = self.off, self.K
+        """x = A^-1 b (or A^-T b): both sweeps in ONE C call (csrc/blocktri.cu npb_bt_solve), which
+        replays them as a CUDA graph from the second call on -- the work buffers below belong to
+        the factorisation and never move"""
         M = self.At if transpose else self.Ap
-        tr = 1 if transpose else 0
-        bp = b.reshape(-1)[self.perm].contiguous()
-        z = torch.empty_like(bp)
-        c = torch.empty(self.mmax, dtype=torch.float64, device=bp.device)
-        st = stream_ptr()
-        L = _lib.lib().cdll
-        ip, ix, dat = M.indptr.data_ptr(), M.indices.data_ptr(), M.data.data_ptr()
-        zp, bpp, cp, sp_ = z.data_ptr(), bp.data_ptr(), c.data_ptr(), self.scratch.data_ptr()
-        rc = 0
-        # forward: c_k = b_k - (lower block) z_{k-1};  z_k = S_k^-1 c_k
-        for k in range(K):
-            r0, r1 = off[k], off[k + 1]
-            m = r1 - r0
-            if k == 0:
-                src = bpp + 8 * r0
-            else:
-                q0 = off[k - 1]
-                rc |= L.npb_bt_window_spmv(ip, ix, dat, r0, r1, q0, r0, zp + 8 * q0, -1.0, 0.0, cp, st)
-                rc |= L.npb_axpby(m, 1.0, bpp + 8 * r0, 1.0, cp, st)
-                src = cp
-            rc |= L.npb_bt_gemv(m, self.Sinv[k].data_ptr(), m, src, 1.0, 0.0, None, zp + 8 * r0, tr, sp_, st)
-        # backward: x_k = z_k - S_k^-1 (upper block) x_{k+1}   (in place in z)
-        for k in range(K - 2, -1, -1):
-            r0, r1 = off[k], off[k + 1]
-            m = r1 - r0
-            rc |= L.npb_bt_window_spmv(ip, ix, dat, r0, r1, r1, off[k + 2], zp + 8 * r1, 1.0, 0.0, cp, st)
-            rc |= L.npb_bt_gemv(m, self.Sinv[k].data_ptr(), m, cp, -1.0, 1.0, zp + 8 * r0, zp + 8 * r0, tr, sp_, st)
+        self.bp.copy_(b.reshape(-1)[self.perm])
+        rc = _lib.lib().cdll.npb_bt_solve(self.K, self.off_h.ctypes.data, self.sinv_h.ctypes.data,
+                                          M.indptr.data_ptr(), M.indices.data_ptr(), M.data.data_ptr(),
+                                          self.bp.data_ptr(), self.z.data_ptr(), self.c.data_ptr(),
+                                          self.scratch.data_ptr(), 1 if transpose else 0,
+                                          int(self.graph_id), stream_ptr())
         if rc:
             raise RuntimeError('block-tridiagonal solve failed: %s' % _lib.lib().last_error())
-        x = torch.empty_like(z)
-        x[self.perm] = z
+        x = torch.empty_like(self.z)
+        x[self.perm] = self.z
         return x
 
     def apply(self, r, z):

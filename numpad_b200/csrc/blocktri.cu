@@ -21,6 +21,8 @@
 
 #define ST(s) ((cudaStream_t)(s))
 
+int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st);
+
 namespace {
 
 constexpr int BT_T = 256;
@@ -269,6 +271,100 @@ int npb_bt_gemv(int64_t m, const double* M, int64_t ld, const double* x, double 
     NPB_COUNT_BYTES(8.0 * (double)m * (double)m + 24.0 * (double)m);
     NPB_CHECK_LAUNCH("bt_gemv");
     return NPB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------- solve phase in one call
+// x = A^-1 b (trans = 0) or A^-T b (trans = 1) from the stored inverses: forward sweep
+//   c_k = b_k - (lower block) z_{k-1},  z_k = S_k^-1 c_k,
+// backward sweep  z_k -= S_k^-1 (upper block) z_{k+1}.  All arrays of the sweep live in
+// buffers owned by the factorisation (bp: permuted right-hand side, z: permuted solution,
+// c / scratch: work), so the launch sequence -- ~8 K small kernels for a 1024^2 cavity -- is
+// the same on every call: after one eager call it is captured into a CUDA graph (graph_id > 0,
+// one graph per direction) and replayed; the sweeps are then bound by the 2 x (sum m_k^2) x 8
+// bytes of the inverses they stream, not by launches.
+#include <map>
+
+namespace {
+struct bt_graph { int calls = 0; cudaGraphExec_t exec = nullptr; bool failed = false; unsigned long long launches = 0; double bytes = 0.0; };
+std::map<long long, bt_graph> g_bt_graphs;
+cudaStream_t g_bt_capture = nullptr;
+
+int bt_sweeps(int K, const int64_t* off, const double* const* sinv, const int32_t* ip,
+              const int32_t* ix, const double* dat, const double* bp, double* z, double* c,
+              double* scratch, int trans, cudaStream_t st) {
+    int rc = NPB_OK;
+    for (int k = 0; k < K && !rc; ++k) {
+        const int64_t r0 = off[k], r1 = off[k + 1], m = r1 - r0;
+        const double* src = bp + r0;
+        if (k > 0) {
+            const int64_t q0 = off[k - 1];
+            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, q0, r0, z + q0, -1.0, 0.0, c, st);
+            if (!rc) rc = npb_axpby_launch(m, 1.0, bp + r0, 1.0, c, st);      // c += b_k
+            src = c;
+        }
+        if (!rc) rc = npb_bt_gemv(m, sinv[k], m, src, 1.0, 0.0, nullptr, z + r0, trans, scratch, st);
+    }
+    for (int k = K - 2; k >= 0 && !rc; --k) {
+        const int64_t r0 = off[k], r1 = off[k + 1], m = r1 - r0;
+        rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, r1, off[k + 2], z + r1, 1.0, 0.0, c, st);
+        if (!rc) rc = npb_bt_gemv(m, sinv[k], m, c, -1.0, 1.0, z + r0, z + r0, trans, scratch, st);
+    }
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int npb_bt_graph_release(int graph_id) {
+    for (int t = 0; t < 2; ++t) {
+        auto it = g_bt_graphs.find((long long)graph_id * 2 + t);
+        if (it == g_bt_graphs.end()) continue;
+        if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+        g_bt_graphs.erase(it);
+    }
+    return NPB_OK;
+}
+
+// off: [host] K + 1 level offsets; sinv: [host] K device pointers (row-major m_k x m_k);
+// (indptr, indices, data): the level-ordered matrix (its transpose when trans)
+int npb_bt_solve(int K, const int64_t* off, const double* const* sinv, const int32_t* indptr,
+                 const int32_t* indices, const double* data, const double* bp, double* z,
+                 double* c, double* scratch, int trans, int graph_id, void* stream) {
+    cudaStream_t st = ST(stream);
+    if (K <= 0) return NPB_OK;
+    bt_graph* g = graph_id > 0 ? &g_bt_graphs[(long long)graph_id * 2 + (trans ? 1 : 0)] : nullptr;
+    if (g && !g->failed && !g->exec && g->calls >= 1) {
+        if (!g_bt_capture) NPB_CUDA(cudaStreamCreateWithFlags(&g_bt_capture, cudaStreamNonBlocking));
+        const unsigned long long l0 = npb_launch_counter;
+        const double b0 = npb_bytes_counter;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(g_bt_capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        int rc = NPB_OK;
+        if (ok) {
+            rc = bt_sweeps(K, off, sinv, indptr, indices, data, bp, z, c, scratch, trans, g_bt_capture);
+            ok = (cudaStreamEndCapture(g_bt_capture, &graph) == cudaSuccess) && rc == NPB_OK && graph;
+        }
+        if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        g->launches = npb_launch_counter - l0;
+        g->bytes = npb_bytes_counter - b0;
+        npb_launch_counter = l0;
+        npb_bytes_counter = b0;
+        if (!ok) { cudaGetLastError(); g->failed = true; g->exec = nullptr; }
+    }
+    if (g) g->calls++;
+    if (g && g->exec) {
+        if (cudaGraphLaunch(g->exec, st) != cudaSuccess) {
+            npb_set_error("bt_solve: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return NPB_ERR_CUDA;
+        }
+        npb_launch_counter += g->launches;
+        npb_bytes_counter += g->bytes;
+        return NPB_OK;
+    }
+    return bt_sweeps(K, off, sinv, indptr, indices, data, bp, z, c, scratch, trans, st);
 }
 
 }  // extern "C"
