@@ -64,6 +64,119 @@ def _read_stats(stats):
     return int(total), int(max_row)
 
 
+# --------------------------------------------------------------------------- #
+# Assembly plans: trace once, replay (the reference redoes all index
+# bookkeeping on every diff(), adarray.py:470-473, 761-774)
+# --------------------------------------------------------------------------- #
+# The symbolic half of a two-pass kernel (row counts, scan, output size: one host sync each)
+# only depends on the index structure of its operands, and that is the same for every Jacobian
+# of a Newton run.  While a plan RECORDS, every such phase stores its result; while it REPLAYS,
+# the stored row pointers are handed out instead -- no count kernel, no scan, no sync -- and
+# only the numeric kernels run.  Safety does not rest on trust:
+#   * every entry carries the shapes / sizes of its operands: a different operation sequence
+#     raises PlanMismatch;
+#   * index maps that define a structure are compared ON THE DEVICE with the recorded ones;
+#   * numeric kernels count the exact zeros they produce (scipy prunes them: a value-dependent
+#     structure); a recording that saw any is not kept, a replay that sees any is discarded.
+# The comparison and zero counters are summed once at the end of the assembly (ONE sync); a
+# non-zero total raises PlanMismatch and the caller assembles again without a plan.
+class PlanMismatch(Exception):
+    pass
+
+
+class AssemblyPlan:
+    def __init__(self):
+        self.entries = []          # (kind, signature, result, guard tensors)
+        self.pos = 0
+        self.recording = True
+        self.ok = True             # the recorded structure did not depend on values
+        self.cells = None
+        self.ncell = 0
+        self.ncells_recorded = 0
+        self.checks = []
+
+    def cell(self):
+        """a fresh zero counter of this replay"""
+        if self.ncell >= self.cells.numel():
+            raise PlanMismatch('more counters than recorded')
+        c = self.cells[self.ncell:self.ncell + 1]
+        self.ncell += 1
+        return c
+
+
+_active_plan = None
+plans = {}                  # (f.size, u.size, mode) -> AssemblyPlan
+REPLAY = True               # switch (tests / tuning)
+plan_stats = {'recorded': 0, 'replayed': 0, 'mismatch': 0}
+
+
+class _PlanScope:
+    def __init__(self, plan, recording):
+        self.plan, self.recording = plan, recording
+
+    def __enter__(self):
+        global _active_plan
+        self.nested = _active_plan is not None
+        if self.nested:
+            return None                     # (a lazy Jacobian assembled inside a sweep)
+        p = self.plan
+        p.recording, p.pos, p.ncell, p.checks = self.recording, 0, 0, []
+        if not self.recording:
+            p.cells = torch.zeros(max(p.ncells_recorded, 1), dtype=torch.int64, device=device())
+        else:
+            p.ncells_recorded = 0
+        _active_plan = p
+        return p
+
+    def __exit__(self, et, ev, tb):
+        global _active_plan
+        if self.nested:
+            return False
+        p, _active_plan = _active_plan, None
+        if et is None and not self.recording:
+            if p.pos != len(p.entries):
+                raise PlanMismatch('fewer operations than recorded')
+            bad = p.cells.sum()
+            for c in p.checks:
+                bad = bad + c
+            if int(bad.item()) != 0:        # the one sync of a replayed assembly
+                raise PlanMismatch('structure changed (zeros produced or index maps differ)')
+        return False
+
+
+def recording(plan):
+    return _PlanScope(plan, True)
+
+
+def replaying(plan):
+    return _PlanScope(plan, False)
+
+
+def _symbolic(kind, sig, compute, guards=()):
+    """result of a symbolic phase: computed (and recorded), or replayed from the active plan.
+    guards: index tensors the structure depends on; compared with the recorded ones on the
+    device during a replay"""
+    p = _active_plan
+    if p is None:
+        return compute()
+    if p.recording:
+        out = compute()
+        p.entries.append((kind, sig, out, tuple(guards)))
+        return out
+    if p.pos >= len(p.entries):
+        raise PlanMismatch('more operations than recorded')
+    k, sg, out, gs = p.entries[p.pos]
+    p.pos += 1
+    if k != kind or sg != sig or len(gs) != len(guards):
+        raise PlanMismatch('%s %r != recorded %s %r' % (kind, sig, k, sg))
+    for a, b in zip(gs, guards):
+        if a is not b:
+            if a.shape != b.shape:
+                raise PlanMismatch('guard shape')
+            p.checks.append((a != b).sum())
+    return out
+
+
 class DevEye:
     """val * identity(n): the seed of a sweep and everything reached from it
     through scalar blocks only (scipy keeps those as dia_matrix)."""
@@ -159,6 +272,8 @@ class DevCsr:
         if nnz == self.nnz:
             self.clean = True
             return self
+        if _active_plan is not None:
+            _active_plan.ok = False      # value-dependent structure
         idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
         _call('npb_csr_prune_numeric', m, self.indptr, self.indices, self.data, sc, ptr, idx, dat)
         return DevCsr(self.shape, ptr, idx, dat, (), nnz, max_row, True)
@@ -300,13 +415,18 @@ class sel_jac:
     def todev(self):
         if self._dev is None:
             n = self.n_rows
-            cnt, ptr = _empty(n, torch.int32), _empty(n + 1, torch.int32)
-            stats = _empty(2, torch.int64)
-            _call('npb_sel_to_csr_symbolic', n, self.map, cnt, ptr, _scan_ws(n), stats)
-            nnz, _ = _read_stats(stats)
+
+            def symbolic():
+                cnt, ptr = _empty(n, torch.int32), _empty(n + 1, torch.int32)
+                stats = _empty(2, torch.int64)
+                _call('npb_sel_to_csr_symbolic', n, self.map, cnt, ptr, _scan_ws(n), stats)
+                return ptr, _read_stats(stats)[0]
+            ptr, nnz = _symbolic('sel_to_csr', (n, self.n_cols), symbolic, (self.map,))
             idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
             _call('npb_sel_to_csr_numeric', n, self.map, self.w, ptr, idx, dat)
-            self._dev = DevCsr(self.shape, ptr, idx, dat, (), nnz, 1 if nnz else 0)
+            # unit weights: no stored zero, nothing for pruned() to look for
+            self._dev = DevCsr(self.shape, ptr, idx, dat, (), nnz, 1 if nnz else 0,
+                               clean=self.w is None)
         return self._dev
 
     def tocsr(self):
@@ -341,13 +461,25 @@ def coo_to_csr(shape, rows, cols, vals, prune):
 
 
 def _zero_cell():
+    p = _active_plan
+    if p is not None:
+        if p.recording:
+            p.ncells_recorded += 1
+        else:
+            return p.cell()
     return _empty(1, torch.int64)
 
 
 def _finish(C, zc):
     """C was written by a product kernel that counted the zeros it produced in
     `zc`; compact them away if there are any (csr_matmat never stores a zero)"""
+    p = _active_plan
+    if zc is not None and p is not None and not p.recording:
+        C.clean = True           # verified at the end of the replay (the counters are summed there)
+        return C
     if zc is not None and int(zc.item()) > 0:
+        if p is not None:
+            p.ok = False         # value-dependent structure: this recording cannot be replayed
         C.clean = False
         return C.pruned()
     C.clean = True
@@ -385,11 +517,14 @@ def _csr_times_sel(A, S):
             return _finish(DevCsr(shape, A.indptr, idx, dat, (), A.nnz, A.max_row), zc)
         if A.max_row <= LONG_ROW:
             m = A.shape[0]
-            cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
-            stats = _empty(2, torch.int64)
-            _call('npb_csr_relabel_symbolic', m, A.indptr, A.indices, S.map, cnt, ptr,
-                  _scan_ws(m), stats)
-            nnz, max_row = _read_stats(stats)
+
+            def symbolic():
+                cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+                stats = _empty(2, torch.int64)
+                _call('npb_csr_relabel_symbolic', m, A.indptr, A.indices, S.map, cnt, ptr,
+                      _scan_ws(m), stats)
+                return (ptr,) + _read_stats(stats)
+            ptr, nnz, max_row = _symbolic('relabel', (A.shape, A.nnz, S.n_cols), symbolic, (S.map,))
             idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
             zc = _zero_cell() if S.w is not None else None
             _call('npb_csr_relabel_numeric', m, A.indptr, A.indices, A.data, sc, S.map, S.w,
@@ -431,10 +566,12 @@ def _sel_times_csr(S, B):
     """selection (m x k) times B (k x n): row gather."""
     m = S.n_rows
     shape = (m, B.shape[1])
-    cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
-    stats = _empty(2, torch.int64)
-    _call('npb_csr_gather_rows_symbolic', m, S.map, B.indptr, cnt, ptr, _scan_ws(m), stats)
-    nnz, max_row = _read_stats(stats)
+    def symbolic():
+        cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+        stats = _empty(2, torch.int64)
+        _call('npb_csr_gather_rows_symbolic', m, S.map, B.indptr, cnt, ptr, _scan_ws(m), stats)
+        return (ptr,) + _read_stats(stats)
+    ptr, nnz, max_row = _symbolic('gather_rows', (m, B.shape, B.nnz), symbolic, (S.map,))
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
     zc = _zero_cell() if S.w is not None else None
     _call('npb_csr_gather_rows_numeric', m, S.map, S.w, B.indptr, B.indices, B.data,
@@ -578,11 +715,27 @@ def _csr_plus_csr(A, B):
                           torch.cat([Am.indices, Bm.indices]),
                           torch.cat([Am.data, Bm.data]), prune=True)
     sa, sb = make_scales(A.scales), make_scales(B.scales)
-    cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
-    stats = _empty(2, torch.int64)
-    _call('npb_spadd_symbolic', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
-          B.data, sb, 1, cnt, ptr, _scan_ws(m), stats)
-    nnz, max_row = _read_stats(stats)
+
+    def symbolic(prune=1):
+        cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
+        stats = _empty(2, torch.int64)
+        _call('npb_spadd_symbolic', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
+              B.data, sb, prune, cnt, ptr, _scan_ws(m), stats)
+        return (ptr,) + _read_stats(stats)
+    p = _active_plan
+    if p is not None and not p.recording:
+        # replay: the recorded UNION structure (no sum was zero when it was recorded); the fill
+        # kernel writes every union entry and counts the zeros it meets -- verified at the end
+        ptr, nnz, max_row = _symbolic('spadd', (A.shape, A.nnz, B.nnz), None)
+        idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+        _call('npb_spadd_numeric_zc', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
+              B.data, sb, ptr, idx, dat, _zero_cell())
+        return DevCsr(A.shape, ptr, idx, dat, (), nnz, max_row, True)
+    ptr, nnz, max_row = _symbolic('spadd', (A.shape, A.nnz, B.nnz), symbolic)
+    if p is not None:
+        p.ncells_recorded += 1
+        if p.ok and symbolic(0)[1] != nnz:
+            p.ok = False                 # a sum cancelled exactly: value-dependent structure
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
     _call('npb_spadd_numeric', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
           B.data, sb, 1, ptr, idx, dat)

@@ -678,11 +678,37 @@ def diff_dev(f, u, mode='auto'):
     """d f / d u kept on the device: DevCsr, DevEye or the int 0."""
     if mode == 'auto':
         mode = 'tangent' if u.size < f.size else 'adjoint'
-    if mode == 'tangent':
-        return diff_tangent(f._current_state, u._initial_state)
-    if mode == 'adjoint':
-        return diff_adjoint(f._current_state, u._initial_state)
-    raise NotImplementedError
+    if mode not in ('tangent', 'adjoint'):
+        raise NotImplementedError
+    sweep = diff_tangent if mode == 'tangent' else diff_adjoint
+    fs, us = f._current_state, u._initial_state
+    if not _dev.REPLAY or f.size * u.size == 0:
+        return sweep(fs, us)
+    # trace once, replay: the symbolic phases of the sweep (sparsity patterns, one host sync
+    # each) are recorded the first time a tape of this shape is differentiated and reused for
+    # the Jacobians that follow (every Newton iteration records the same tape); see
+    # _dev.AssemblyPlan for what makes a replay safe
+    key = (f.size, u.size, mode)
+    plan = _dev.plans.get(key)
+    if plan is not None:
+        try:
+            with _dev.replaying(plan) as active:
+                J = sweep(fs, us)
+            if active is not None:
+                _dev.plan_stats['replayed'] += 1
+            return J
+        except _dev.PlanMismatch:
+            _dev.plan_stats['mismatch'] += 1
+            del _dev.plans[key]
+    plan = _dev.AssemblyPlan()
+    with _dev.recording(plan) as active:
+        J = sweep(fs, us)
+    if active is not None and plan.ok and plan.entries:
+        if len(_dev.plans) >= 4:
+            _dev.plans.clear()
+        _dev.plans[key] = plan
+        _dev.plan_stats['recorded'] += 1
+    return J
 
 
 def diff(f, u, mode='auto'):

@@ -516,7 +516,7 @@ static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* 
         if (rc) return rc;
         h.recv = const_cast<double*>(xh);
         return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y,
-                           0, st, &h, &w, nullptr);
+                           0, st, &h, &w, M.data32);
     }
     return npb_spmv_ex(M.nrows, M.nnz, M.indptr, M.indices, M.data, x, mode, b, dinv, omega, y, 0,
                        st, nullptr, nullptr, M.data32);

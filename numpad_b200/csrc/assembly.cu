@@ -230,9 +230,11 @@ k_spadd(int64_t nrows, const int32_t* __restrict__ ap,
         const int32_t* __restrict__ bi, const double* __restrict__ bd,
         npb_scales bs, int prune, int32_t* __restrict__ cnt,
         int64_t* __restrict__ stats, const int32_t* __restrict__ optr,
-        int32_t* __restrict__ oidx, double* __restrict__ out) {
+        int32_t* __restrict__ oidx, double* __restrict__ out,
+        int64_t* __restrict__ zero_count) {
     int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     int32_t c = 0;
+    int nz = 0;
     if (r < nrows) {
         int32_t i = ap[r], ie = ap[r + 1], j = bp[r], je = bp[r + 1];
         int32_t o = FILL ? optr[r] : 0;
@@ -254,11 +256,16 @@ k_spadd(int64_t nrows, const int32_t* __restrict__ ap,
                 ++j; cb = (j < je) ? bi[j] : INT32_MAX;
             }
             if (!prune || v != 0.0) {
-                if (FILL) { oidx[o] = col; out[o] = v; ++o; }
+                if (FILL) { oidx[o] = col; out[o] = v; ++o; nz += (v == 0.0); }
                 ++c;
             }
         }
         if (!FILL) cnt[r] = c;
+    }
+    if (FILL && zero_count) {       // replay of a recorded structure: exact zeros invalidate it
+        for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
+        if (nz && (threadIdx.x & 31) == 0)
+            atomicAdd((unsigned long long*)zero_count, (unsigned long long)nz);
     }
     if (!FILL) {
         for (int d = 16; d; d >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, d));
@@ -488,7 +495,7 @@ int npb_spadd_symbolic(int64_t nrows, const int32_t* a_indptr,
     NPB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), ST(stream)));
     k_spadd<false><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(
         nrows, a_indptr, a_indices, a_data, *a_sc, b_indptr, b_indices, b_data,
-        *b_sc, prune, counts, stats, nullptr, nullptr, nullptr);
+        *b_sc, prune, counts, stats, nullptr, nullptr, nullptr, nullptr);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("spadd_count");
     return npb_scan_launch(counts, indptr_out, nrows, scan_ws, stats, ST(stream));
@@ -504,9 +511,29 @@ int npb_spadd_numeric(int64_t nrows, const int32_t* a_indptr,
     if (nrows <= 0) return NPB_OK;
     k_spadd<true><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(
         nrows, a_indptr, a_indices, a_data, *a_sc, b_indptr, b_indices, b_data,
-        *b_sc, prune, nullptr, nullptr, indptr_out, indices_out, out);
+        *b_sc, prune, nullptr, nullptr, indptr_out, indices_out, out, nullptr);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("spadd_fill");
+    return NPB_OK;
+}
+
+// fill of a KNOWN union structure (indptr_out from an earlier symbolic phase with the same
+// operand patterns, see _dev.AssemblyPlan): every union entry is written, *zero_count (device,
+// reset here) receives the number of exact zeros among them
+int npb_spadd_numeric_zc(int64_t nrows, const int32_t* a_indptr,
+                         const int32_t* a_indices, const double* a_data,
+                         const npb_scales* a_sc, const int32_t* b_indptr,
+                         const int32_t* b_indices, const double* b_data,
+                         const npb_scales* b_sc, const int32_t* indptr_out,
+                         int32_t* indices_out, double* out, int64_t* zero_count,
+                         void* stream) {
+    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
+    if (nrows <= 0) return NPB_OK;
+    k_spadd<true><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(
+        nrows, a_indptr, a_indices, a_data, *a_sc, b_indptr, b_indices, b_data,
+        *b_sc, 0, nullptr, nullptr, indptr_out, indices_out, out, zero_count);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("spadd_fill_zc");
     return NPB_OK;
 }
 

@@ -506,9 +506,10 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
         // operator stored with fp32 values (multigrid preconditioner, single GPU): always the
         // TMA pipeline kernel; 8 instead of 12 bytes per entry
         spmv_epi e32{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
-        if ((((uintptr_t)idx | (uintptr_t)dat32) & 15) != 0 || nnz >= (int64_t)0x7fffffff - 2 * TM_CAP_MAX ||
-            (halo && halo->dist)) {
-            npb_set_error("spmv: fp32 operator not usable here (alignment / size / sharded)");
+        if (halo && halo->dist) { e32.xh = halo->recv; e32.n_own = (int32_t)halo->n_own; }
+        if (wait && e32.xh) e32.wait = *wait;
+        if ((((uintptr_t)idx | (uintptr_t)dat32) & 15) != 0 || nnz >= (int64_t)0x7fffffff - 2 * TM_CAP_MAX) {
+            npb_set_error("spmv: fp32 operator not usable here (alignment / size)");
             return NPB_ERR_ARG;
         }
         int rc = spmv_tma_dispatch(nrows, nnz, ptr, idx, dat32, x, e32, y, st);

@@ -326,12 +326,13 @@ static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const
     return e.xh ? launch_spmv_tma_h<ROWS, RPT, G, true, double>(nrows, nnz, ptr, idx, dat, x, e, y, st)
                 : launch_spmv_tma_h<ROWS, RPT, G, false, double>(nrows, nnz, ptr, idx, dat, x, e, y, st);
 }
-// fp32-stored operators: single-GPU only (the sharded hierarchy keeps fp64 values)
+// fp32-stored operators (multigrid preconditioner)
 template <int ROWS, int RPT, class G>
 static int launch_spmv_tma(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* idx,
                            const float* dat, const double* x, const spmv_epi& e, double* y,
                            cudaStream_t st) {
-    return launch_spmv_tma_h<ROWS, RPT, G, false, float>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+    return e.xh ? launch_spmv_tma_h<ROWS, RPT, G, true, float>(nrows, nnz, ptr, idx, dat, x, e, y, st)
+                : launch_spmv_tma_h<ROWS, RPT, G, false, float>(nrows, nnz, ptr, idx, dat, x, e, y, st);
 }
 
 template <class G, class T>

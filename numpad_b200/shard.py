@@ -108,7 +108,7 @@ class LocalOp:
     """rows [rcuts[rank], rcuts[rank+1]) of a global CSR matrix with the columns renumbered
     [owned | boundary values of rank 0 | rank 1 | ...] (npb_halo in the C header)."""
     __slots__ = ('shape', 'indptr', 'indices', 'data', 'nnz', 'n_own', 'send_idx', 'maxb',
-                 'recv', 'sharded_cols')
+                 'recv', 'sharded_cols', 'data32')
 
 
 def localize(indptr, indices, data, shape, rcuts, ccuts, rank, world, replicated_cols=False):
@@ -190,10 +190,16 @@ def strip_permutation(owner, world):
 # --------------------------------------------------------------------------- #
 # device side: sharded hierarchies, LSC preconditioner, FGMRES
 # --------------------------------------------------------------------------- #
-def _fill_mat(m, op, handle):
+def _fill_mat(m, op, handle, f32=False):
     """fill an amg.CsrMat from a LocalOp"""
     m.nrows, m.ncols, m.nnz = op.shape[0], op.shape[1], op.nnz
     m.indptr, m.indices, m.data = op.indptr.data_ptr(), op.indices.data_ptr(), op.data.data_ptr()
+    if f32:
+        # preconditioner operators: applied from fp32 values when large (amg.F32_MIN_ROWS)
+        from . import amg
+        if amg.F32_MIN_ROWS and op.shape[0] >= amg.F32_MIN_ROWS and 0 < op.nnz <= 96 * op.shape[0]:
+            op.data32 = op.data.to(torch.float32)
+            m.data32 = op.data32.data_ptr()
     if op.sharded_cols:
         m.halo.dist = handle
         m.halo.n_own = op.n_own
@@ -278,7 +284,7 @@ class ShardedHierarchy:
             p = _loc(lev['P'], c, cn, replicated_cols=last)
             r = _loc(lev['R'], cn, c)
             self.keep += [a, p, r]
-            _fill_mat(L.A, a, handle); _fill_mat(L.P, p, handle); _fill_mat(L.R, r, handle)
+            _fill_mat(L.A, a, handle, True); _fill_mat(L.P, p, handle, True); _fill_mat(L.R, r, handle, True)
             dinv = lev['dinv'][c[rank]:c[rank + 1]]
             n = c[rank + 1] - c[rank]
             w = [torch.zeros(max(n, 1), dtype=torch.float64, device=device()) for _ in range(4)]
@@ -344,7 +350,7 @@ class ShardedLsc:
         s.n, s.nv, s.np = cuts[rank + 1] - cuts[rank], nv, np_
         s.vset, s.pset = self.vset.data_ptr(), self.pset.data_ptr()
         for m, op in ((s.A, self.A), (s.G, self.G), (s.D, self.D), (s.Lm, self.Lm)):
-            _fill_mat(m, op, handle)
+            _fill_mat(m, op, handle, True)
         s.a_dinv = self.a_dinv.data_ptr()
         s.amg_a, s.amg_l = self.amg_a.addr, self.amg_l.addr
         s.a_gmres = 0
@@ -428,10 +434,12 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
     from . import _dev
     # the large Galerkin products of the setup are computed by row blocks, one per rank
     _dev.SPGEMM_SHARD = (rank, world, SHARD_PRODUCTS_ABOVE) if world > 1 and SHARD_PRODUCTS_ABOVE else None
+    f32_rows, amg.F32_MIN_ROWS = amg.F32_MIN_ROWS, 0     # (fp32 copies are made of the LOCAL slices)
     try:
         M = amg.LscPreconditioner(Jp, **(lsc_options or {}))
     finally:
         _dev.SPGEMM_SHARD = None
+        amg.F32_MIN_ROWS = f32_rows
     torch.cuda.synchronize(); t2 = time.perf_counter()
     _heap_reset()
     S = ShardedLsc(M, cuts)

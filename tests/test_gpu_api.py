@@ -119,3 +119,50 @@ def test_lsc_graph_replay_and_fp32_operators_do_not_change_the_solve(npd):
     assert out['graph32'][2] <= 1e-12 and abs(out['graph32'][1] - out['eager64'][1]) <= 4
     ref = out['eager64'][0]
     assert float((out['graph32'][0] - ref).norm() / ref.norm()) < 1e-9
+
+
+def test_assembly_plan_replay_is_bit_identical_and_self_checking(npd):
+    """trace once / replay: the second and later Jacobians of a tape reuse the
+    recorded sparsity patterns (no symbolic kernels, one host sync per assembly) and must equal
+    the plan-free assembly bit for bit; a state whose Jacobian has exact zeros (the script's
+    first step from rest) must fall back, and a different residual of the same size must not
+    be served from the stale plan"""
+    import torch
+    from numpad_b200 import _dev
+    from numpad_b200.workloads.cavity import CavityProblem
+    P = CavityProblem(npd, 48)
+
+    def jac(state, replay):
+        _dev.REPLAY = replay
+        u = npd.array(state.copy())
+        res = P.residual(u, npd.array(state.copy()), 1.0, 0)
+        return npd.diff_dev(res, u).materialized()
+    same = lambda a, b: (a.nnz == b.nnz and torch.equal(a.indptr, b.indptr) and
+                         torch.equal(a.indices, b.indices) and torch.equal(a.data, b.data))
+    try:
+        _dev.plans.clear()
+        for k in _dev.plan_stats:
+            _dev.plan_stats[k] = 0
+        s1, s2 = P.fixed_state(seed=1), P.fixed_state(seed=2)
+        ref1, ref2, ref0 = jac(s1, False), jac(s2, False), jac(np.zeros(P.n), False)
+        a = jac(s1, True)                       # records
+        assert _dev.plan_stats['recorded'] == 1 and same(a, ref1)
+        b = jac(s2, True)                       # replays
+        assert _dev.plan_stats['replayed'] == 1 and same(b, ref2)
+        z = jac(np.zeros(P.n), True)            # exact zeros -> mismatch -> plan-free assembly
+        assert _dev.plan_stats['mismatch'] == 1 and same(z, ref0)
+        assert z.nnz < ref1.nnz
+        c = jac(s1, True)                       # records again (the zero state's run is not kept)
+        d = jac(s2, True)
+        assert same(c, ref1) and same(d, ref2) and _dev.plan_stats['replayed'] >= 2
+        # another function of the same sizes: different index maps -> guarded
+        u = npd.array(s1.copy())
+        other = npd.hstack([u[1:] * u[:-1], u[:1]]) + npd.roll(u, 3)
+        J1 = npd.diff_dev(other, u).materialized()
+        _dev.REPLAY = False
+        u = npd.array(s1.copy())
+        other = npd.hstack([u[1:] * u[:-1], u[:1]]) + npd.roll(u, 3)
+        assert same(J1, npd.diff_dev(other, u).materialized())
+    finally:
+        _dev.REPLAY = True
+        _dev.plans.clear()

@@ -12,6 +12,8 @@ from numpad_b200.workloads.cavity import CavityProblem
 ap = argparse.ArgumentParser()
 ap.add_argument('--grid', type=int, default=256); ap.add_argument('--steps', type=int, default=3)
 ap.add_argument('--dt', type=float, default=1.0)
+ap.add_argument('--adjoint', action='store_true', help='config 3: d(kinetic energy)/d(force) through the last solve (test/cavity_adjoint.py:6-8)')
+ap.add_argument('--rtol', type=float, default=1e-12)
 a = ap.parse_args()
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 if world > 1:      # torchrun: the unmodified driver loop with row-sharded linear solves
@@ -19,7 +21,7 @@ if world > 1:      # torchrun: the unmodified driver loop with row-sharded linea
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
     dist.init_process_group('nccl', device_id=torch.device('cuda', torch.cuda.current_device()))
 linsolve.DEFAULTS['verbose'] = rank == 0
-linsolve.DEFAULTS['rtol'] = 1e-10
+linsolve.DEFAULTS['rtol'] = a.rtol
 P = CavityProblem(npd, a.grid)
 if world > 1:
     linsolve.DEFAULTS['shard_owner'] = P.partition(world)
@@ -35,7 +37,18 @@ for step in range(a.steps):
     if q._n_Newton == 1: break
     elif q._n_Newton < 4: dt *= 2
     t += dt
-    q.obliviate()
+    if step < a.steps - 1:
+        q.obliviate()
+if a.adjoint:
+    N = a.grid
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ke = 0.5 * npd.sum(q[N * N:] ** 2)
+    adj = np.asarray(ke.diff(force).todense()).ravel()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print('adjoint of the kinetic energy w.r.t. the force: |adj| = %.12e in %.2f s (%s, %d its)'
+              % (float(np.linalg.norm(adj)), time.perf_counter() - t0, linsolve.last_info.get('method'),
+                 linsolve.last_info.get('iters', -1)), flush=True)
 if world > 1:
     from numpad_b200 import shard
     shard.shutdown()
