@@ -128,16 +128,21 @@ int npb_spadd_numeric(int64_t nrows, const int32_t* a_indptr,
                       const npb_scales* b_sc, int prune,
                       const int32_t* indptr_out, int32_t* indices_out,
                       double* out, void* stream);
-/* fill of a KNOWN union structure (replay of a recorded assembly plan, trace-once / replay of
- * the tape): every union entry is written; *zero_count = exact zeros among them (the caller
- * discards the plan when it is not 0, because scipy's csr_plus_csr would have pruned them) */
-int npb_spadd_numeric_zc(int64_t nrows, const int32_t* a_indptr,
-                         const int32_t* a_indices, const double* a_data,
-                         const npb_scales* a_sc, const int32_t* b_indptr,
-                         const int32_t* b_indices, const double* b_data,
-                         const npb_scales* b_sc, const int32_t* indptr_out,
-                         int32_t* indices_out, double* out, int64_t* zero_count,
-                         void* stream);
+/* Replays of a recorded assembly plan (trace-once / replay of the tape, _dev.AssemblyPlan):
+ * fills into a RECORDED row structure.  Rows are written inside their recorded slots only;
+ * *mismatch (device, reset by the call) counts the rows whose entry count differs from the
+ * recording -- the caller discards the plan when the total of an assembly is not 0. */
+int npb_spadd_numeric_checked(int64_t nrows, const int32_t* a_indptr,
+                              const int32_t* a_indices, const double* a_data,
+                              const npb_scales* a_sc, const int32_t* b_indptr,
+                              const int32_t* b_indices, const double* b_data,
+                              const npb_scales* b_sc, int prune, const int32_t* indptr_out,
+                              int32_t* indices_out, double* out, int64_t* mismatch,
+                              void* stream);
+int npb_csr_prune_numeric_checked(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                                  const double* data, const npb_scales* sc,
+                                  const int32_t* indptr_out, int32_t* indices_out, double* out,
+                                  int64_t* mismatch, void* stream);
 
 /* ---- S1: general csr * csr (scipy csr_matmat), expansion to COO; finish
  * with npb_coo_to_csr_* (prune = 1: csr_matmat never stores a zero). */

@@ -76,10 +76,12 @@ def _read_stats(stats):
 #   * every entry carries the shapes / sizes of its operands: a different operation sequence
 #     raises PlanMismatch;
 #   * index maps that define a structure are compared ON THE DEVICE with the recorded ones;
-#   * numeric kernels count the exact zeros they produce (scipy prunes them: a value-dependent
-#     structure); a recording that saw any is not kept, a replay that sees any is discarded.
-# The comparison and zero counters are summed once at the end of the assembly (ONE sync); a
-# non-zero total raises PlanMismatch and the caller assembles again without a plan.
+#   * exact zeros are pruned like scipy does (a value-dependent structure: e.g. the 0/1 mask of
+#     an assignment): the recording keeps the PRUNED structure, and a replay fills it with
+#     kernels that stay inside every row's recorded slots and count the rows whose number of
+#     entries differs; products recorded without zeros count the zeros they produce now.
+# The counters are summed once at the end of the assembly (ONE sync); a non-zero total raises
+# PlanMismatch and the caller assembles again without a plan.
 class PlanMismatch(Exception):
     pass
 
@@ -89,19 +91,8 @@ class AssemblyPlan:
         self.entries = []          # (kind, signature, result, guard tensors)
         self.pos = 0
         self.recording = True
-        self.ok = True             # the recorded structure did not depend on values
-        self.cells = None
-        self.ncell = 0
-        self.ncells_recorded = 0
-        self.checks = []
-
-    def cell(self):
-        """a fresh zero counter of this replay"""
-        if self.ncell >= self.cells.numel():
-            raise PlanMismatch('more counters than recorded')
-        c = self.cells[self.ncell:self.ncell + 1]
-        self.ncell += 1
-        return c
+        self.ok = True
+        self.checks = []           # device counters of this replay that must all be 0
 
 
 _active_plan = None
@@ -120,11 +111,7 @@ class _PlanScope:
         if self.nested:
             return None                     # (a lazy Jacobian assembled inside a sweep)
         p = self.plan
-        p.recording, p.pos, p.ncell, p.checks = self.recording, 0, 0, []
-        if not self.recording:
-            p.cells = torch.zeros(max(p.ncells_recorded, 1), dtype=torch.int64, device=device())
-        else:
-            p.ncells_recorded = 0
+        p.recording, p.pos, p.checks = self.recording, 0, []
         _active_plan = p
         return p
 
@@ -136,9 +123,9 @@ class _PlanScope:
         if et is None and not self.recording:
             if p.pos != len(p.entries):
                 raise PlanMismatch('fewer operations than recorded')
-            bad = p.cells.sum()
+            bad = torch.zeros(1, dtype=torch.int64, device=device())
             for c in p.checks:
-                bad = bad + c
+                bad = bad + c.reshape(-1)[:1].to(torch.int64)
             if int(bad.item()) != 0:        # the one sync of a replayed assembly
                 raise PlanMismatch('structure changed (zeros produced or index maps differ)')
         return False
@@ -257,12 +244,20 @@ class DevCsr:
         return DevCsr(self.shape, self.indptr, self.indices, out, (), self.nnz, self.max_row,
                       self.clean)
 
-    def pruned(self):
+    def pruned(self, _plan_aware=True):
         """without its exactly-zero entries (what scipy's product / sum emit)"""
         if self.clean or self.nnz == 0:
             return self
         if any(v == 0.0 for v in self.scales):
             return DevCsr.empty(self.shape)
+        p = _active_plan if _plan_aware else None
+        if p is not None and not p.recording:
+            rec = _symbolic('prune', (self.shape, self.nnz), None)
+            if rec is None:                  # nothing was pruned then: verify there is no zero now
+                p.checks.append((self.data == 0).sum())
+                self.clean = True
+                return self
+            return self._pruned_into(*rec)
         m = self.shape[0]
         sc = make_scales(self.scales)
         cnt, ptr = _empty(m, torch.int32), _empty(m + 1, torch.int32)
@@ -271,11 +266,23 @@ class DevCsr:
         nnz, max_row = _read_stats(stats)
         if nnz == self.nnz:
             self.clean = True
+            if p is not None:
+                _symbolic('prune', (self.shape, self.nnz), lambda: None)
             return self
-        if _active_plan is not None:
-            _active_plan.ok = False      # value-dependent structure
+        if p is not None:
+            _symbolic('prune', (self.shape, self.nnz), lambda: (ptr, nnz, max_row))
         idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
         _call('npb_csr_prune_numeric', m, self.indptr, self.indices, self.data, sc, ptr, idx, dat)
+        return DevCsr(self.shape, ptr, idx, dat, (), nnz, max_row, True)
+
+    def _pruned_into(self, ptr, nnz, max_row):
+        """prune into a RECORDED structure (assembly plan replay): rows whose non-zero count
+        differs from the recording are counted on the device and fail the replay"""
+        idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+        bad = _empty(1, torch.int64)
+        _call('npb_csr_prune_numeric_checked', self.shape[0], self.indptr, self.indices, self.data,
+              make_scales(self.scales), ptr, idx, dat, bad)
+        _active_plan.checks.append(bad)
         return DevCsr(self.shape, ptr, idx, dat, (), nnz, max_row, True)
 
     def todev(self):
@@ -461,12 +468,6 @@ def coo_to_csr(shape, rows, cols, vals, prune):
 
 
 def _zero_cell():
-    p = _active_plan
-    if p is not None:
-        if p.recording:
-            p.ncells_recorded += 1
-        else:
-            return p.cell()
     return _empty(1, torch.int64)
 
 
@@ -475,13 +476,21 @@ def _finish(C, zc):
     `zc`; compact them away if there are any (csr_matmat never stores a zero)"""
     p = _active_plan
     if zc is not None and p is not None and not p.recording:
-        C.clean = True           # verified at the end of the replay (the counters are summed there)
-        return C
+        # replay: what the recording saw decides, the counters verify it at the end
+        pruned = _symbolic('finish', (C.shape, C.nnz), None)
+        if pruned is None:
+            p.checks.append(zc)              # no zero then: there must be none now
+            C.clean = True
+            return C
+        return C._pruned_into(*pruned)
     if zc is not None and int(zc.item()) > 0:
-        if p is not None:
-            p.ok = False         # value-dependent structure: this recording cannot be replayed
         C.clean = False
-        return C.pruned()
+        out = C.pruned(_plan_aware=False)
+        if p is not None:
+            _symbolic('finish', (C.shape, C.nnz), lambda: (out.indptr, out.nnz, out.max_row))
+        return out
+    if zc is not None and p is not None:
+        _symbolic('finish', (C.shape, C.nnz), lambda: None)
     C.clean = True
     return C
 
@@ -525,7 +534,10 @@ def _csr_times_sel(A, S):
                       _scan_ws(m), stats)
                 return (ptr,) + _read_stats(stats)
             ptr, nnz, max_row = _symbolic('relabel', (A.shape, A.nnz, S.n_cols), symbolic, (S.map,))
-            idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+            # (slack: in a replay whose operand deviated from the recording -- detected at the
+            # end -- a row may hold more entries than its recorded slots)
+            slack = A.max_row + 8 if _active_plan is not None else 0
+            idx, dat = _empty(nnz + slack, torch.int32)[:nnz], _empty(nnz + slack, torch.float64)[:nnz]
             zc = _zero_cell() if S.w is not None else None
             _call('npb_csr_relabel_numeric', m, A.indptr, A.indices, A.data, sc, S.map, S.w,
                   ptr, idx, dat, zc)
@@ -572,7 +584,8 @@ def _sel_times_csr(S, B):
         _call('npb_csr_gather_rows_symbolic', m, S.map, B.indptr, cnt, ptr, _scan_ws(m), stats)
         return (ptr,) + _read_stats(stats)
     ptr, nnz, max_row = _symbolic('gather_rows', (m, B.shape, B.nnz), symbolic, (S.map,))
-    idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
+    slack = B.max_row + 8 if _active_plan is not None else 0
+    idx, dat = _empty(nnz + slack, torch.int32)[:nnz], _empty(nnz + slack, torch.float64)[:nnz]
     zc = _zero_cell() if S.w is not None else None
     _call('npb_csr_gather_rows_numeric', m, S.map, S.w, B.indptr, B.indices, B.data,
           make_scales(B.scales), ptr, idx, dat, zc)
@@ -724,18 +737,16 @@ def _csr_plus_csr(A, B):
         return (ptr,) + _read_stats(stats)
     p = _active_plan
     if p is not None and not p.recording:
-        # replay: the recorded UNION structure (no sum was zero when it was recorded); the fill
-        # kernel writes every union entry and counts the zeros it meets -- verified at the end
+        # replay: fill the recorded (pruned) structure; a row whose entry count differs -- a sum
+        # that cancels exactly now but did not then, or the reverse -- fails the replay
         ptr, nnz, max_row = _symbolic('spadd', (A.shape, A.nnz, B.nnz), None)
         idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
-        _call('npb_spadd_numeric_zc', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
-              B.data, sb, ptr, idx, dat, _zero_cell())
+        bad = _empty(1, torch.int64)
+        _call('npb_spadd_numeric_checked', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
+              B.data, sb, 1, ptr, idx, dat, bad)
+        p.checks.append(bad)
         return DevCsr(A.shape, ptr, idx, dat, (), nnz, max_row, True)
     ptr, nnz, max_row = _symbolic('spadd', (A.shape, A.nnz, B.nnz), symbolic)
-    if p is not None:
-        p.ncells_recorded += 1
-        if p.ok and symbolic(0)[1] != nnz:
-            p.ok = False                 # a sum cancelled exactly: value-dependent structure
     idx, dat = _empty(nnz, torch.int32), _empty(nnz, torch.float64)
     _call('npb_spadd_numeric', m, A.indptr, A.indices, A.data, sa, B.indptr, B.indices,
           B.data, sb, 1, ptr, idx, dat)

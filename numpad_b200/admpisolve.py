@@ -17,8 +17,9 @@ on torch.distributed / NCCL and the CUDA kernels of the C-ABI:
     convention (operators are callables on LOCAL vectors, returns `(x, info)`,
     stops when ||r|| < tol*||b|| or < tol) and runs the C++ FGMRES with one
     batched all-reduce per group of inner products instead of one `Allreduce`
-    per dot (admpisolve.py:177-188, 386-390).  The LGMRES augmentation vectors
-    (`outer_k`, `outer_v`) are accepted and ignored.
+    per dot (admpisolve.py:177-188, 386-390).  The LGMRES augmentation (`outer_k`
+    corrections of earlier restart cycles, `outer_v` carried in and out by the caller)
+    enters the flexible GMRES as extra search directions of every cycle.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -150,17 +151,62 @@ def _lgmres(A, b, x0=None, tol=1e-5, maxiter=1000, M=None, callback=None,
         parallel.allreduce_sum(linsolve._tensor_from_ptr(buf, count))
         return 0
 
-    bn = _norm2(b)
-    x, info = linsolve.fgmres(None, b, x0=x0, precond=pre, matvec=matvec, rtol=tol, atol=tol,
-                              restart=inner_m, maxiter=maxiter,
-                              allreduce=allreduce if _world() > 1 else None)
-    if linsolve._cb_error:
-        e = linsolve._cb_error.pop()
-        linsolve._cb_error.clear()
-        raise e
-    if _rank() == 0 and callback is not None:
-        callback(x)
-    return x, (0 if info['status'] == 0 else maxiter)
+    # LGMRES(inner_m, outer_k) in flexible form: every restart cycle runs inner_m
+    # preconditioned Arnoldi steps and then feeds the (normalised) corrections dx of the last
+    # outer_k cycles in as extra search directions -- flexible GMRES accepts any z_j, the
+    # relation A Z = V H holds all the same -- so the information a plain restart throws away
+    # is carried over (reference admpisolve.py:229-236, 336-341, 432-445).  `outer_v` is
+    # modified in place like the reference's, so a caller can hand the vectors of one solve
+    # to the next (Newton-Krylov with slowly changing Jacobians).
+    if outer_v is None:
+        outer_v = []
+    aug = []
+    for v in outer_v:                       # user-supplied guesses: (v, Av) tuples or vectors
+        v = v[0] if isinstance(v, (tuple, list)) else v
+        aug.append(_dev_vec(v))
+    step = {'j': 0}
+
+    def search_direction(r, z):
+        j = step['j']
+        step['j'] += 1
+        if j < inner_m or j - inner_m >= len(aug):
+            if pre is None:
+                z.copy_(r)
+            else:
+                pre(r, z)
+        else:
+            z.copy_(aug[j - inner_m])
+
+    x = torch.zeros_like(b) if x0 is None else x0.clone()
+    status = 1
+    for k_outer in range(max(int(maxiter), 1)):
+        step['j'] = 0
+        m_tot = inner_m + len(aug)
+        x_old = x.clone()
+        x, info = linsolve.fgmres(None, b, x0=x, precond=search_direction, matvec=matvec, rtol=tol,
+                                  atol=tol, restart=m_tot, maxiter=m_tot,
+                                  allreduce=allreduce if _world() > 1 else None)
+        if linsolve._cb_error:
+            e = linsolve._cb_error.pop()
+            linsolve._cb_error.clear()
+            raise e
+        if _rank() == 0 and callback is not None:
+            callback(x)
+        if info['status'] == 0:
+            status = 0
+            break
+        dx = x - x_old
+        nx = _norm2(dx)
+        if nx == 0.0:
+            raise RuntimeError('LGMRES stagnated: a restart cycle made no progress '
+                               '(|r| = %.3e)' % info['rnorm'])
+        aug.append(dx / nx)
+        outer_v.append((aug[-1], None))
+        while len(aug) > outer_k:
+            del aug[0]
+        while len(outer_v) > outer_k:
+            del outer_v[0]
+    return x, (0 if status == 0 else maxiter)
 
 
 # ----------- nonlinear solver ------------ #

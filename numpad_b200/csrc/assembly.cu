@@ -209,13 +209,25 @@ __global__ void __launch_bounds__(TPB)
 k_prune_fill(int64_t nrows, const int32_t* __restrict__ ptr,
              const int32_t* __restrict__ idx, const double* __restrict__ dat,
              npb_scales sc, const int32_t* __restrict__ optr,
-             int32_t* __restrict__ oidx, double* __restrict__ out) {
+             int32_t* __restrict__ oidx, double* __restrict__ out,
+             int64_t* __restrict__ mismatch) {
     int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r >= nrows) return;
     int32_t o = optr[r];
+    // mismatch != NULL: optr comes from a RECORDED structure (assembly plan replay): never
+    // write past the row's slots, report a row whose non-zero count differs
+    const int32_t oe = mismatch ? optr[r + 1] : INT32_MAX;
     for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
         const double v = npb_apply(sc, dat[k]);
-        if (v != 0.0) { oidx[o] = idx[k]; out[o] = v; ++o; }
+        if (v != 0.0) {
+            if (o < oe) { oidx[o] = idx[k]; out[o] = v; }
+            ++o;
+        }
+    }
+    if (mismatch && o != oe) {
+        atomicAdd((unsigned long long*)mismatch, 1ull);
+        // the replay is void; leave defined (valid) entries for the kernels that still run
+        for (; o < oe; ++o) { oidx[o] = 0; out[o] = 0.0; }
     }
 }
 
@@ -231,13 +243,14 @@ k_spadd(int64_t nrows, const int32_t* __restrict__ ap,
         npb_scales bs, int prune, int32_t* __restrict__ cnt,
         int64_t* __restrict__ stats, const int32_t* __restrict__ optr,
         int32_t* __restrict__ oidx, double* __restrict__ out,
-        int64_t* __restrict__ zero_count) {
+        int64_t* __restrict__ mismatch) {
     int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     int32_t c = 0;
-    int nz = 0;
     if (r < nrows) {
         int32_t i = ap[r], ie = ap[r + 1], j = bp[r], je = bp[r + 1];
         int32_t o = FILL ? optr[r] : 0;
+        // mismatch != NULL: optr is a RECORDED structure (assembly plan replay)
+        const int32_t oe = (FILL && mismatch) ? optr[r + 1] : INT32_MAX;
         int32_t ca = (i < ie) ? ai[i] : INT32_MAX;
         int32_t cb = (j < je) ? bi[j] : INT32_MAX;
         while (i < ie || j < je) {
@@ -256,16 +269,19 @@ k_spadd(int64_t nrows, const int32_t* __restrict__ ap,
                 ++j; cb = (j < je) ? bi[j] : INT32_MAX;
             }
             if (!prune || v != 0.0) {
-                if (FILL) { oidx[o] = col; out[o] = v; ++o; nz += (v == 0.0); }
+                if (FILL) {
+                    if (o < oe) { oidx[o] = col; out[o] = v; }
+                    ++o;
+                }
                 ++c;
             }
         }
         if (!FILL) cnt[r] = c;
-    }
-    if (FILL && zero_count) {       // replay of a recorded structure: exact zeros invalidate it
-        for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
-        if (nz && (threadIdx.x & 31) == 0)
-            atomicAdd((unsigned long long*)zero_count, (unsigned long long)nz);
+        if (FILL && mismatch && o != oe) {
+            atomicAdd((unsigned long long*)mismatch, 1ull);
+            // the replay is void; leave defined (valid) entries for the kernels that still run
+            for (; o < oe; ++o) { oidx[o] = 0; out[o] = 0.0; }
+        }
     }
     if (!FILL) {
         for (int d = 16; d; d >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, d));
@@ -479,9 +495,25 @@ int npb_csr_prune_numeric(int64_t nrows, const int32_t* indptr, const int32_t* i
                           const int32_t* indptr_out, int32_t* indices_out, double* out,
                           void* stream) {
     if (nrows <= 0) return NPB_OK;
-    k_prune_fill<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, *sc, indptr_out, indices_out, out);
+    k_prune_fill<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, *sc, indptr_out, indices_out, out, nullptr);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_prune_fill");
+    return NPB_OK;
+}
+
+// the same into a RECORDED structure (replay of an assembly plan): rows are written inside
+// their recorded slots only and *mismatch (device, reset here) counts the rows whose number
+// of non-zeros differs from the recording
+int npb_csr_prune_numeric_checked(int64_t nrows, const int32_t* indptr, const int32_t* indices,
+                                  const double* data, const npb_scales* sc,
+                                  const int32_t* indptr_out, int32_t* indices_out, double* out,
+                                  int64_t* mismatch, void* stream) {
+    if (!mismatch) return NPB_ERR_ARG;
+    NPB_CUDA(cudaMemsetAsync(mismatch, 0, sizeof(int64_t), ST(stream)));
+    if (nrows <= 0) return NPB_OK;
+    k_prune_fill<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, *sc, indptr_out, indices_out, out, mismatch);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_prune_fill_checked");
     return NPB_OK;
 }
 
@@ -517,23 +549,25 @@ int npb_spadd_numeric(int64_t nrows, const int32_t* a_indptr,
     return NPB_OK;
 }
 
-// fill of a KNOWN union structure (indptr_out from an earlier symbolic phase with the same
-// operand patterns, see _dev.AssemblyPlan): every union entry is written, *zero_count (device,
-// reset here) receives the number of exact zeros among them
-int npb_spadd_numeric_zc(int64_t nrows, const int32_t* a_indptr,
-                         const int32_t* a_indices, const double* a_data,
-                         const npb_scales* a_sc, const int32_t* b_indptr,
-                         const int32_t* b_indices, const double* b_data,
-                         const npb_scales* b_sc, const int32_t* indptr_out,
-                         int32_t* indices_out, double* out, int64_t* zero_count,
-                         void* stream) {
-    if (zero_count) NPB_CUDA(cudaMemsetAsync(zero_count, 0, sizeof(int64_t), ST(stream)));
+// fill of a RECORDED structure (indptr_out from the symbolic phase of an earlier sum with the
+// same operand patterns, see _dev.AssemblyPlan): rows are written inside their recorded slots
+// only and *mismatch (device, reset here) counts the rows whose number of entries differs --
+// a sum that cancels exactly now but did not then, or the reverse
+int npb_spadd_numeric_checked(int64_t nrows, const int32_t* a_indptr,
+                              const int32_t* a_indices, const double* a_data,
+                              const npb_scales* a_sc, const int32_t* b_indptr,
+                              const int32_t* b_indices, const double* b_data,
+                              const npb_scales* b_sc, int prune, const int32_t* indptr_out,
+                              int32_t* indices_out, double* out, int64_t* mismatch,
+                              void* stream) {
+    if (!mismatch) return NPB_ERR_ARG;
+    NPB_CUDA(cudaMemsetAsync(mismatch, 0, sizeof(int64_t), ST(stream)));
     if (nrows <= 0) return NPB_OK;
     k_spadd<true><<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(
         nrows, a_indptr, a_indices, a_data, *a_sc, b_indptr, b_indices, b_data,
-        *b_sc, 0, nullptr, nullptr, indptr_out, indices_out, out, zero_count);
+        *b_sc, prune, nullptr, nullptr, indptr_out, indices_out, out, mismatch);
     NPB_COUNT_LAUNCH();
-    NPB_CHECK_LAUNCH("spadd_fill_zc");
+    NPB_CHECK_LAUNCH("spadd_fill_checked");
     return NPB_OK;
 }
 
