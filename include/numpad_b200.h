@@ -277,7 +277,8 @@ int npb_bt_window_spmm(const int32_t* indptr, const int32_t* indices, const doub
                        int64_t ldc, void* stream);
 int npb_bt_window_spmv(const int32_t* indptr, const int32_t* indices, const double* data,
                        int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double* x,
-                       double alpha, double beta, double* y, void* stream);
+                       double alpha, double beta, const double* y0 /* NULL: y */, double* y,
+                       void* stream);
 /* both sweeps of a solve in one call (x = A^-1 b, or A^-T b when trans); off [host]: K + 1 level
  * offsets, sinv [host]: K device pointers to the row-major inverses; with graph_id > 0 the
  * launch sequence is captured after the first call and replayed (buffers must not move) */
@@ -407,8 +408,11 @@ int npb_dist_init(const char* nccl_path, const char* id128, int rank, int world,
                   void** handle);                                  /* collective */
 int npb_dist_free(void* handle);
 /* symmetric heap for exchanges by direct stores into NVLink peer memory (same layout on
- * every rank; all_handles = world x 64 bytes of CUDA IPC handles in rank order) */
-int npb_dist_heap_create(void* handle, int64_t bytes, char* ipc64);
+ * every rank).  The memory is the CALLER's (`mem`, `bytes` long, kept alive until
+ * npb_dist_free): the library allocates no device memory.  ipc72 = CUDA IPC handle of the
+ * allocation containing `mem` (64 bytes) + offset of `mem` in it (8); all_handles = world x
+ * 72 bytes in rank order */
+int npb_dist_heap_create(void* handle, void* mem, int64_t bytes, char* ipc72);
 int npb_dist_heap_open(void* handle, const char* all_handles);         /* collective */
 int64_t npb_dist_heap_alloc(void* handle, int64_t bytes);              /* offset or < 0 */
 int npb_dist_heap_reset(void* handle, void* stream);    /* between barriers: drop all allocs */

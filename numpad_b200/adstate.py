@@ -8,6 +8,12 @@ sweeps lives in HBM: blocks are numbers, `dia_jac`, `sel_jac`, `csr_jac`
 (all device resident) and accumulated derivatives are `DevEye` / `DevCsr`;
 `_multiply_ops` / `_add_ops` dispatch to CUDA kernels through the C-ABI.
 
+Provenance: `IntermediateState` (fields, method names, generator order of froms()/tos(),
+the asserts) and the order of the two sweeps deliberately restate the reference's adstate.py
+(qiqi/numpad, GPLv3 -- see the reference's LICENSE): they ARE the extension protocol that
+admpi / adsolve and user subclasses program against.  The block algebra, the
+device kernels and the early freeing of intermediates are new.
+
 reference: adstate.py:34-229 (tape + sweeps), :233-297 (blocks, add/mul).
 """
 import numbers

@@ -79,11 +79,12 @@ k_bt_window_spmm(const int32_t* __restrict__ ptr, const int32_t* __restrict__ id
     if (j0 + BT_T < ncols) crow[j0 + BT_T] = (beta == 0.0 ? 0.0 : beta * crow[j0 + BT_T]) + alpha * acc1;
 }
 
-// y[r - r0] = beta * y[r - r0] + alpha * sum_{c in [c0, c1)} A[r, c] * x[c - c0]
+// y[r - r0] = beta * y0[r - r0] + alpha * sum_{c in [c0, c1)} A[r, c] * x[c - c0]   (y0 may be y)
 __global__ void __launch_bounds__(BT_T)
 k_bt_window_spmv(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                  const double* __restrict__ dat, int64_t r0, int64_t r1, int32_t c0, int32_t c1,
-                 const double* __restrict__ x, double alpha, double beta, double* __restrict__ y) {
+                 const double* __restrict__ x, double alpha, double beta, const double* y0,
+                 double* y) {
     const int lane = threadIdx.x & 7;
     const int64_t r = r0 + (((int64_t)blockIdx.x * BT_T + threadIdx.x) >> 3);
     double s = 0.0;
@@ -95,7 +96,7 @@ k_bt_window_spmv(const int32_t* __restrict__ ptr, const int32_t* __restrict__ id
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (r < r1 && lane == 0) y[r - r0] = (beta == 0.0 ? 0.0 : beta * y[r - r0]) + alpha * s;
+    if (r < r1 && lane == 0) y[r - r0] = (beta == 0.0 ? 0.0 : beta * y0[r - r0]) + alpha * s;
 }
 
 // y = beta * y0 + alpha * M x, M dense m x m row-major: one warp per row, 128-bit loads
@@ -241,10 +242,10 @@ int npb_bt_window_spmm(const int32_t* indptr, const int32_t* indices, const doub
 
 int npb_bt_window_spmv(const int32_t* indptr, const int32_t* indices, const double* data,
                        int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double* x,
-                       double alpha, double beta, double* y, void* stream) {
+                       double alpha, double beta, const double* y0, double* y, void* stream) {
     if (r1 <= r0) return NPB_OK;
     k_bt_window_spmv<<<npb_blocks((r1 - r0) * 8, BT_T), BT_T, 0, ST(stream)>>>(
-        indptr, indices, data, r0, r1, (int32_t)c0, (int32_t)c1, x, alpha, beta, y);
+        indptr, indices, data, r0, r1, (int32_t)c0, (int32_t)c1, x, alpha, beta, y0 ? y0 : y, y);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("bt_window_spmv");
     return NPB_OK;
@@ -300,15 +301,14 @@ int bt_sweeps(int K, const int64_t* off, const double* const* sinv, const int32_
         const double* src = bp + r0;
         if (k > 0) {
             const int64_t q0 = off[k - 1];
-            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, q0, r0, z + q0, -1.0, 0.0, c, st);
-            if (!rc) rc = npb_axpby_launch(m, 1.0, bp + r0, 1.0, c, st);      // c += b_k
+            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, q0, r0, z + q0, -1.0, 1.0, bp + r0, c, st);
             src = c;
         }
         if (!rc) rc = npb_bt_gemv(m, sinv[k], m, src, 1.0, 0.0, nullptr, z + r0, trans, scratch, st);
     }
     for (int k = K - 2; k >= 0 && !rc; --k) {
         const int64_t r0 = off[k], r1 = off[k + 1], m = r1 - r0;
-        rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, r1, off[k + 2], z + r1, 1.0, 0.0, c, st);
+        rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, r1, off[k + 2], z + r1, 1.0, 0.0, nullptr, c, st);
         if (!rc) rc = npb_bt_gemv(m, sinv[k], m, c, -1.0, 1.0, z + r0, z + r0, trans, scratch, st);
     }
     return rc;

@@ -299,28 +299,45 @@ int npb_dist_free(void* handle) {
     if (!d) return NPB_OK;
     cudaDeviceSynchronize();
     for (int q = 0; q < d->world && q < NPB_MAX_PEERS; ++q) {
-        if (!d->heap[q]) continue;
-        if (q == d->rank) cudaFree(d->heap[q]); else cudaIpcCloseMemHandle(d->heap[q]);
-    }
+        if (q != d->rank && d->ipc_base[q]) cudaIpcCloseMemHandle(d->ipc_base[q]);
+    }     // (this rank's own heap belongs to the caller)
     if (d->comm && g_nccl.destroy) g_nccl.destroy(d->comm);
     delete d;
     return NPB_OK;
 }
 
-// ---- symmetric heap (direct-store exchanges).  create: cudaMalloc + zero + IPC handle (64
-// bytes) of this rank's heap; open: collective, all_handles = world x 64 bytes in rank
-// order; alloc: bump allocation, the same call sequence on every rank gives the same
-// offsets everywhere.  Without a heap every exchange goes through NCCL.
-int npb_dist_heap_create(void* handle, int64_t bytes, char* ipc64) {
+// ---- symmetric heap (direct-store exchanges).  The library allocates no device memory:
+// create: the CALLER hands in `bytes` of device memory (`mem`, e.g. a torch tensor it keeps
+// alive until npb_dist_free); it is zeroed and described by 72 bytes -- the CUDA IPC handle of
+// the allocation that contains it (64) + the offset of `mem` inside that allocation (8).
+// open: collective, all_handles = world x 72 bytes in rank order; alloc: bump allocation, the
+// same call sequence on every rank gives the same offsets everywhere.  Without a heap every
+// exchange goes through NCCL.
+typedef int (*cu_get_range_fn)(unsigned long long* base, size_t* size, unsigned long long ptr);
+int npb_dist_heap_create(void* handle, void* mem, int64_t bytes, char* ipc72) {
     npb_dist* d = (npb_dist*)handle;
-    if (!d || d->world > NPB_MAX_PEERS || bytes <= 0) return NPB_ERR_ARG;
-    void* p = nullptr;
-    NPB_CUDA(cudaMalloc(&p, (size_t)bytes));
-    NPB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    if (!d || d->world > NPB_MAX_PEERS || bytes <= 0 || !mem) return NPB_ERR_ARG;
+    // base of the cudaMalloc allocation that contains `mem` (an allocator may hand out interior
+    // pointers): driver entry point resolved at run time, no link-time dependency on libcuda
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    NPB_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    if (!fn) { npb_set_error("heap_create: cuMemGetAddressRange unavailable"); return NPB_ERR_CUDA; }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (((cu_get_range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)mem) != 0) {
+        npb_set_error("heap_create: cuMemGetAddressRange failed");
+        return NPB_ERR_CUDA;
+    }
+    const int64_t off = (int64_t)((unsigned long long)(uintptr_t)mem - base);
+    if (off < 0 || (size_t)(off + bytes) > size) return NPB_ERR_ARG;
+    NPB_CUDA(cudaMemset(mem, 0, (size_t)bytes));
     cudaIpcMemHandle_t hnd;
-    NPB_CUDA(cudaIpcGetMemHandle(&hnd, p));
-    memcpy(ipc64, &hnd, sizeof(hnd) < 64 ? sizeof(hnd) : 64);
-    d->heap[d->rank] = (char*)p;
+    NPB_CUDA(cudaIpcGetMemHandle(&hnd, (void*)(uintptr_t)base));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc72, &hnd, 64);
+    memcpy(ipc72 + 64, &off, 8);
+    d->heap[d->rank] = (char*)mem;
     d->heap_bytes = bytes;
     d->heap_used = 0;
     return NPB_OK;
@@ -332,10 +349,13 @@ int npb_dist_heap_open(void* handle, const char* all_handles) {
     for (int q = 0; q < d->world; ++q) {
         if (q == d->rank) continue;
         cudaIpcMemHandle_t hnd;
-        memcpy(&hnd, all_handles + (size_t)q * 64, sizeof(hnd) < 64 ? sizeof(hnd) : 64);
+        int64_t off = 0;
+        memcpy(&hnd, all_handles + (size_t)q * 72, 64);
+        memcpy(&off, all_handles + (size_t)q * 72 + 64, 8);
         void* p = nullptr;
         NPB_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-        d->heap[q] = (char*)p;
+        d->ipc_base[q] = p;
+        d->heap[q] = (char*)p + off;
     }
     // all-reduce slots: 2 parities x world x NPB_RED_SLOT doubles + world counters
     d->red_data = 0;

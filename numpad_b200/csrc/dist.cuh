@@ -9,9 +9,10 @@ constexpr int NPB_RED_SLOT = 128;      // doubles per rank in the all-reduce slo
 struct npb_dist {            // one per process: the library's NCCL communicator
     void* comm = nullptr;
     int rank = 0, world = 1;
-    // symmetric heap for direct-store exchanges over NVLink peer memory: the same
-    // cudaMalloc'ed layout on every rank, opened on the peers through CUDA IPC
+    // symmetric heap for direct-store exchanges over NVLink peer memory: CALLER-OWNED device
+    // memory with the same layout on every rank, opened on the peers through CUDA IPC
     char* heap[NPB_MAX_PEERS] = {};        // heap[q] = base of rank q's heap in this process
+    void* ipc_base[NPB_MAX_PEERS] = {};    // mappings opened here (closed by npb_dist_free)
     int64_t heap_bytes = 0, heap_used = 0;
     int64_t red_data = -1, red_flags = -1; // offsets of the all-reduce slots
     unsigned long long red_seq = 0;

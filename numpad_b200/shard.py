@@ -40,7 +40,7 @@ SHARD_PRODUCTS_ABOVE = 500000
 # bytes of the symmetric heap for direct-store exchanges (0 / NPB_DIST_P2P=0: NCCL only)
 HEAP_BYTES = 64 << 20
 
-_handle = {'ptr': None, 'rank': 0, 'world': 1, 'p2p': False}
+_handle = {'ptr': None, 'rank': 0, 'world': 1, 'p2p': False, 'heap': None}
 
 
 def _nccl_path():
@@ -78,8 +78,11 @@ def init(group=None):
         raise RuntimeError('npb_dist_init failed: %s' % _lib.lib().last_error())
     _handle.update(ptr=h.value, rank=rank, world=world, p2p=False)
     if HEAP_BYTES and world <= 8 and os.environ.get('NPB_DIST_P2P', '1') != '0':
-        ipc = ctypes.create_string_buffer(64)
-        rc = L.npb_dist_heap_create(h, HEAP_BYTES, ipc)
+        ipc = ctypes.create_string_buffer(72)
+        # the heap is a torch allocation owned here (the library allocates nothing); its own
+        # cudaMalloc segment, so that the IPC mapping exposes nothing else of this process
+        _handle['heap'] = torch.empty(HEAP_BYTES, dtype=torch.uint8, device=dev)
+        rc = L.npb_dist_heap_create(h, ctypes.c_void_p(_handle['heap'].data_ptr()), HEAP_BYTES, ipc)
         ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 1:
@@ -98,7 +101,7 @@ def shutdown():
     from . import _lib
     if _handle['ptr'] is not None:
         _lib.lib().cdll.npb_dist_free(ctypes.c_void_p(_handle['ptr']))
-        _handle.update(ptr=None, rank=0, world=1, p2p=False)
+        _handle.update(ptr=None, rank=0, world=1, p2p=False, heap=None)
 
 
 # --------------------------------------------------------------------------- #

@@ -7,6 +7,10 @@ instantiated at any N and against any array namespace.
 
 Unknown layout (field-major, reference test/cavity.py:31-37):
     [ p (N*N) | u_x interior ((N-1)*N) | u_y interior (N*(N-1)) ],  n = 3N^2 - 2N
+
+Provenance: a workload definition, not engine code -- the operation sequence of the
+reference's test/cavity.py:31-94 (qiqi/numpad, GPLv3) is reproduced on purpose, because parity
+is defined on the tape it records (same states, same local Jacobians, same Newton trajectory).
 """
 import numpy as np
 

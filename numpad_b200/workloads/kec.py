@@ -10,6 +10,10 @@ Unknown layout (variable-major, reference euler_kec.py:11-12):
     w = [rho | rho*u | rho*v | E], each Ni x Nj,   n = 4 * Ni * Nj
 Synthetic mesh of SURVEY.md section 8(d) config 4: a straight 10 x 1 duct with
 a smooth distortion, so that any Ni x Nj can be generated.
+
+Provenance: a workload definition, not engine code -- the operation sequence of the
+reference's test/euler_kec.py:7-139 and test/navierstokes.py:7-177 (qiqi/numpad, GPLv3) is reproduced on purpose, because parity
+is defined on the tape it records (same states, same local Jacobians, same Newton trajectory).
 """
 import numpy as np
 

@@ -48,8 +48,12 @@ def test_window_kernels_vs_numpy(npd):
     x = torch.from_numpy(rng.standard_normal(c1 - c0)).cuda()
     y = torch.from_numpy(rng.standard_normal(r1 - r0)).cuda()
     want = 2.0 * y.cpu().numpy() - dense[r0:r1, c0:c1] @ x.cpu().numpy()
-    _call('npb_bt_window_spmv', A.indptr, A.indices, A.data, r0, r1, c0, c1, x, -1.0, 2.0, y)
+    y0 = y.clone()
+    _call('npb_bt_window_spmv', A.indptr, A.indices, A.data, r0, r1, c0, c1, x, -1.0, 2.0, None, y)
     np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
+    y2 = torch.empty_like(y)
+    _call('npb_bt_window_spmv', A.indptr, A.indices, A.data, r0, r1, c0, c1, x, -1.0, 2.0, y0, y2)
+    np.testing.assert_allclose(y2.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
     from numpad_b200 import _lib
     for m in (1, 63, 64, 257, 1000):
         M = torch.from_numpy(rng.standard_normal((m, m))).cuda()
