@@ -50,6 +50,10 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--grid', type=int, default=int(os.environ.get('NPB_BENCH_GRID', '2048')))
     ap.add_argument('--impl', default='ours')
+    ap.add_argument('--workload', default='cavity', choices=['cavity', 'euler', 'ns'],
+                    help='cavity (the headline metric, default grid 2048) or one implicit step of '
+                         'test/euler_kec.py / test/navierstokes.py on the synthetic duct mesh at the '
+                         "scripts' time step (configs 4 / 5; pass a --grid the direct solver can hold, e.g. 256)")
     ap.add_argument('--sample-grid', type=int, default=0,
                     help='reference arm: grid of the per-step sample (0: from --ref-budget)')
     ap.add_argument('--ref-budget', type=float, default=200.0,
@@ -62,8 +66,20 @@ def parse():
     return ap.parse_args()
 
 
-def workload_config(grid, gpus, parallel='sharded'):
+def workload_config(grid, gpus, parallel='sharded', workload='cavity'):
     """identical in both arms (the driver compares them)"""
+    if workload != 'cavity':
+        n = 4 * grid * grid
+        return {'workload': '%s on the synthetic %d x %d duct mesh of SURVEY 8(d) config %d, n=%d unknowns, '
+                            'dt=%s (the script\'s), state = uniform subsonic flow * (1 + 1e-3 '
+                            'RandomState(0).standard_normal); one Newton iteration (residual + Jacobian '
+                            'assembly + linear solve) per step, made through solve_newton_with_dt'
+                            % ('test/euler_kec.py' if workload == 'euler' else 'test/navierstokes.py',
+                               grid, grid, 4 if workload == 'euler' else 5, n,
+                               '0.1' if workload == 'euler' else '1/%d' % grid),
+                'grid': grid, 'unknowns': n, 'linear_rtol': LINEAR_RTOL,
+                'l2_policy': 'inputs larger than L2 above 256^2; smaller grids fit (stated)',
+                'parallelism': 'single GPU' if gpus <= 1 else '%d independent replicas' % gpus}
     n = grid * (3 * grid - 2)
     return {'workload': 'lid-driven cavity %d^2 (test/cavity.py residual), n=%d unknowns, '
                         'Re=1e4, dt=1, fixed state 1e-2*RandomState(0).standard_normal(n); '
@@ -105,6 +121,19 @@ def import_reference():
     return numpad_oracle, 'port'
 
 
+def kec_reference_problem(numpad, kind, N, viscous):
+    """the Euler / NS residual at grid N for the CPU arm: the restated workload
+    (numpad_b200/workloads/kec.py, loaded by path: no engine import) on the reference's or the
+    oracle's array namespace -- the scripts themselves hard-wire a 90 x 20 / 80 x 20 mesh file-free
+    geometry and pylab, SURVEY 8c"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        '_kec_workload', os.path.join(ROOT, 'numpad_b200', 'workloads', 'kec.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.KecProblem(numpad, N, N, viscous=viscous)
+
+
 def reference_residual(numpad, kind, N):
     """the cavity residual function bound to grid N: the reference's own test/cavity.py source
     (everything above its time-integration driver) / the restated workload for the port"""
@@ -123,15 +152,22 @@ def reference_residual(numpad, kind, N):
     return mod.CavityProblem(numpad, N).residual
 
 
-def cpu_newton_iteration(numpad, kind, N):
+def cpu_newton_iteration(numpad, kind, N, workload='cavity'):
     """one Newton iteration of the reference at grid N, phases timed separately"""
     import scipy.sparse.linalg as spla
-    func = reference_residual(numpad, kind, N)
-    n = N * (3 * N - 2)
-    u0 = 1e-2 * np.random.RandomState(0).standard_normal(n)
+    if workload == 'cavity':
+        func = reference_residual(numpad, kind, N)
+        n = N * (3 * N - 2)
+        u0 = 1e-2 * np.random.RandomState(0).standard_normal(n)
+        call = lambda u: func(u, numpad.array(u0), 1.0, 0)
+    else:
+        P = kec_reference_problem(numpad, kind, N, workload == 'ns')
+        n, u0 = P.n, P.fixed_state()
+        dt = 1.0 / N if workload == 'ns' else 0.1
+        call = lambda u: P.residual(u, numpad.array(u0), dt)
     t0 = time.perf_counter()
     u = numpad.array(u0.copy())
-    res = func(u, numpad.array(u0), 1.0, 0)
+    res = call(u)
     t1 = time.perf_counter()
     J = res.diff(u).tocsr()
     t2 = time.perf_counter()
@@ -158,19 +194,23 @@ def pick_sample_grid(budget_s, iters):
     return g
 
 
-def cpu_baseline(full_grid, sample_grid, steps=1, warmup=0, trend_grid=0, budget=200.0):
+def cpu_baseline(full_grid, sample_grid, steps=1, warmup=0, trend_grid=0, budget=200.0,
+                 workload='cavity'):
     numpad, kind = import_reference()
     if not sample_grid:
         sample_grid = pick_sample_grid(budget, steps + warmup)
-    n_full = full_grid * (3 * full_grid - 2)
-    runs = [cpu_newton_iteration(numpad, kind, sample_grid) for _ in range(warmup + steps)][warmup:]
+        if workload != 'cavity':        # 4 unknowns per cell, ~24-36 entries per row: ~3x the work
+            sample_grid = max(24, int(sample_grid * 0.55) // 8 * 8)
+        sample_grid = min(sample_grid, full_grid)
+    n_full = full_grid * (3 * full_grid - 2) if workload == 'cavity' else 4 * full_grid * full_grid
+    runs = [cpu_newton_iteration(numpad, kind, sample_grid, workload) for _ in range(warmup + steps)][warmup:]
     t = float(np.mean([r['total_s'] for r in runs]))
     r = runs[-1]
     frac = r['n'] / n_full
     trend = [dict(grid=r['grid'], n=r['n'], total_s=t, spsolve_s=float(np.mean([q['spsolve_s'] for q in runs])))]
     n15 = None
     if trend_grid and trend_grid > sample_grid:
-        q = cpu_newton_iteration(numpad, kind, trend_grid)
+        q = cpu_newton_iteration(numpad, kind, trend_grid, workload)
         trend.append(dict(grid=q['grid'], n=q['n'], total_s=q['total_s'], spsolve_s=q['spsolve_s']))
         # measured exponent of the factorisation between the two sizes, and the iteration time
         # it predicts at the full grid (reported, never used for `value`)
@@ -182,7 +222,7 @@ def cpu_baseline(full_grid, sample_grid, steps=1, warmup=0, trend_grid=0, budget
     return dict(
         value=frac / t, unit=UNIT, cores=1, kind=kind,
         sample=('one Newton iteration (residual %.2fs + scipy chain-rule assembly %.2fs + SuperLU '
-                'spsolve %.2fs) of %s on the same cavity residual at a %d^2 sub-grid (%d of %d '
+                'spsolve %.2fs) of %s on the same %s residual at a %d^2 sub-grid (%d of %d '
                 'unknowns = %.3g of the workload); value = that fraction / time, i.e. time scaled '
                 'LINEARLY in unknowns -- an upper bound on the reference throughput at the full grid '
                 '(the measured factorisation trend is in `trend`; the full grid itself needs hours and '
@@ -190,7 +230,7 @@ def cpu_baseline(full_grid, sample_grid, steps=1, warmup=0, trend_grid=0, budget
                 '(1 core of %d)'
                 % (r['residual_s'], r['assembly_s'], r['spsolve_s'],
                    'the UNMODIFIED reference (baseline/_ref/numpad)' if kind == 'reference'
-                   else 'the oracle port (baseline/_ref absent)',
+                   else 'the oracle port (baseline/_ref absent)', workload,
                    sample_grid, r['n'], n_full, frac, os.cpu_count())),
         sample_iters_per_sec=1.0 / t, sample_grid=sample_grid, sample_seconds=t,
         sample_relres=r['relres'], trend=trend, trend_extrapolation=n15,
@@ -203,15 +243,16 @@ def run_reference(args):
         return
     t0 = time.perf_counter()
     cb = cpu_baseline(args.grid, args.sample_grid, steps=args.steps, warmup=args.warmup,
-                      trend_grid=args.trend_grid, budget=args.ref_budget)
+                      trend_grid=args.trend_grid if args.workload == 'cavity' else 0,
+                      budget=args.ref_budget, workload=args.workload)
     line = {
-        'impl': 'reference', 'metric': METRIC,
+        'impl': 'reference', 'metric': METRIC if args.workload == 'cavity' else METRIC.replace('cavity', args.workload + '_kec'),
         'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * cb['sample_seconds'], 'higher_is_better': True,
         'scaling': 'strong' if (args.gpus > 1 and args.parallel == 'sharded') else 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args.grid, args.gpus, args.parallel),
+        'config': workload_config(args.grid, args.gpus, args.parallel, args.workload),
         'cpu_baseline': cb,
         'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -225,7 +266,8 @@ def cpu_baseline_subprocess(args):
     """the GPU arm's `cpu_baseline` leg: the reference arm in a fresh process (so that the
     reference never shares an interpreter with the engine), short budget"""
     cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--grid', str(args.grid),
-           '--steps', '1', '--warmup', '0', '--ref-budget', '25', '--trend-grid', '0']
+           '--workload', args.workload, '--steps', '1', '--warmup', '0', '--ref-budget', '25',
+           '--trend-grid', '0']
     env = {k: v for k, v in os.environ.items()
            if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT')}
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
@@ -296,8 +338,16 @@ def run_ours(args):
     from numpad_b200.workloads.cavity import CavityProblem
     assert linsolve.DEFAULTS['rtol'] == LINEAR_RTOL, 'bench must run at the product default tolerance'
     dev = torch.device('cuda', local)
-    sharded = world > 1 and args.parallel == 'sharded'
-    P = CavityProblem(npd, args.grid)
+    cavity = args.workload == 'cavity'
+    sharded = world > 1 and args.parallel == 'sharded' and cavity
+    if cavity:
+        P = CavityProblem(npd, args.grid)
+        step_args = lambda uold: (npd.adarray(uold), 1.0, 0)
+    else:
+        from numpad_b200.workloads.kec import KecProblem
+        P = KecProblem(npd, args.grid, args.grid, viscous=args.workload == 'ns')
+        kec_dt = 1.0 / args.grid if args.workload == 'ns' else 0.1
+        step_args = lambda uold: (npd.adarray(uold), kec_dt)
     n = P.n
     if sharded:
         # the product's own switch: solve() routes its Newton linear solves through shard.py
@@ -316,7 +366,7 @@ def run_ours(args):
         rel_tol=1: iteration 0 assembles and solves, iteration 1 re-evaluates the residual,
         sees it smaller and returns the adsolution."""
         precond.forget()       # every step pays the full preconditioner setup
-        return npd.solve_newton_with_dt(P.residual, npd.adarray(ud), (npd.adarray(uoldd), 1.0, 0),
+        return npd.solve_newton_with_dt(P.residual, npd.adarray(ud), step_args(uoldd),
                                         {}, np.inf, 2, 0.0, 1.0, False)
 
     def instrumented():
@@ -325,7 +375,7 @@ def run_ours(args):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         u = npd.adarray(u_dev)
-        res = P.residual(u, npd.adarray(uold_dev), 1.0, 0)
+        res = P.residual(u, *step_args(uold_dev))
         ev[1].record()
         J = npd.diff_dev(res, u)
         ev[2].record()
@@ -421,7 +471,7 @@ def run_ours(args):
     value = per_step * args.steps / (ms * 1e-3)
     e2e = per_step * args.steps / (ms_e2e * 1e-3)
     if rank == 0:
-        cfg = workload_config(args.grid, world, args.parallel)
+        cfg = workload_config(args.grid, world, args.parallel, args.workload)
         kry = None
         if phases.get('krylov_ms') and phases.get('krylov_algorithmic_bytes'):
             kgbs = phases['krylov_algorithmic_bytes'] / (phases['krylov_ms'] * 1e-3) / 1e9
@@ -431,7 +481,7 @@ def run_ours(args):
                            'vector kernel launched by the Krylov phase (operator, preconditioner, '
                            'Gram-Schmidt) / the phase time, host gaps included'}
         line = {
-            'metric': METRIC,
+            'metric': METRIC if cavity else METRIC.replace('cavity', args.workload + '_kec'),
             'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong' if sharded else 'weak',

@@ -341,7 +341,9 @@ typedef struct npb_halo {
     /* direct-store path: offsets into the symmetric heap (npb_dist_heap_alloc) of 2 x world x
      * maxb doubles and of world 64-bit arrival counters; < 0: NCCL all-gather into recv */
     int64_t p2p_data, p2p_flags;
-    unsigned long long* seq;        /* [host] exchange counter of this operator */
+    unsigned long long* seq;        /* DEVICE exchange counter of this operator (zero-initialised by
+                                       the caller; read and bumped by the kernels, so that launch
+                                       sequences do not depend on it and can be graph-captured) */
 } npb_halo;
 
 typedef struct npb_csr_mat {
@@ -361,7 +363,7 @@ typedef struct npb_amg_level {      /* [host] */
     int32_t gather, pad;            /* != 0: last row-sharded level; the levels below are  */
     const int64_t* offsets;         /* replicated: [host] world + 1 slice bounds of their rhs */
     int64_t g_data, g_flags;        /* direct-store gather: heap offsets of 2 x offsets[world]  */
-    unsigned long long* g_seq;      /* doubles / world counters (< 0: NCCL); [host] counter     */
+    unsigned long long* g_seq;      /* doubles / world counters (< 0: NCCL); DEVICE exchange counter */
 } npb_amg_level;
 
 typedef struct npb_amg {            /* [host] */

@@ -604,11 +604,10 @@ int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
         if (L.gather) {
             const npb_dist* d = (const npb_dist*)h->dist;
             if (L.g_data >= 0 && npb_dist_heap_ptr(d, 0)) {
-                const unsigned long long seq = ++(*L.g_seq);
-                const int64_t elem_off = (int64_t)(seq & 1) * L.offsets[d->world];
-                CB[l + 1] = npb_dist_heap_ptr(d, L.g_data) + elem_off;
+                // own slice written in place, the peers' slices arrive through the heap (g_seq:
+                // DEVICE exchange counter) and are copied into the level's right-hand side
                 rc = spmv_mat(L.R, L.r, nullptr, CB[l + 1] + L.offsets[d->rank], 0, st);
-                if (!rc) rc = npb_dist_push_slice(d, L.g_data, L.g_flags, elem_off, L.offsets, seq, st);
+                if (!rc) rc = npb_dist_push_slice(d, L.g_data, L.g_flags, L.offsets, L.g_seq, CB[l + 1], st);
             } else {
                 double* mine = CB[l + 1] + L.offsets[d->rank];
                 rc = spmv_mat(L.R, L.r, nullptr, mine, 0, st);
@@ -836,8 +835,9 @@ int npb_lsc_apply_cb(void* ctx, const double* r, double* z, void* stream) {
         k_gather<<<npb_blocks(np, TPB), TPB, 0, st>>>(np, c->pset, r, c->wp[0]);
         NPB_COUNT_LAUNCH();
     }
-    const bool graphable = g_graphs_enabled && c->graph_id > 0 && c->a_gmres <= 0 && !c->A.halo.dist &&
-                           !c->Lm.halo.dist && !(c->amg_a && c->amg_a->dist) && !c->amg_l->dist;
+    // (a row-sharded preconditioner gets a graph id only when EVERY exchange of it goes by direct
+    // stores -- device-side exchange counters, no NCCL call inside the sequence; shard.py decides)
+    const bool graphable = g_graphs_enabled && c->graph_id > 0 && c->a_gmres <= 0;
     lsc_graph* g = graphable ? &g_lsc_graphs[c->graph_id] : nullptr;
     if (g && !g->failed && g->exec) {
         if (cudaGraphLaunch(g->exec, st) != cudaSuccess) {

@@ -114,11 +114,14 @@ __device__ __forceinline__ void wait_peers(const unsigned long long* flags, int 
     __syncthreads();
 }
 
-// one CTA: out slot of every peer <- x[idx[0..n)], then wait for the peers' slots
+// one CTA: out slot of every peer <- x[idx[0..n)], then wait for the peers' slots.  The
+// exchange number is read from (and bumped in) device memory: *dseq + 1
 __global__ void __launch_bounds__(1024)
 k_push_halo(int n, const int32_t* __restrict__ idx, const double* __restrict__ x, peer_ptrs pp,
-            int64_t data_off, int64_t flag_off, int64_t slot, int world, int rank,
-            unsigned long long seq, int wait) {
+            int64_t data_off, int64_t flag_off, int64_t slot, int64_t pstride, int world, int rank,
+            unsigned long long* dseq, int wait) {
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(dseq) + 1;
+    slot += (int64_t)(seq & 1ull) * pstride;
     for (int i = threadIdx.x; i < n; i += 1024) {
         const double v = x[idx[i]];
         for (int q = 0; q < world; ++q)
@@ -130,31 +133,41 @@ k_push_halo(int n, const int32_t* __restrict__ idx, const double* __restrict__ x
         st_release_sys(reinterpret_cast<unsigned long long*>(pp.base[threadIdx.x] + flag_off) + rank, seq);
     if (wait)
         wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
+    if (threadIdx.x == 0) *dseq = seq;          // (every thread read it before the barrier above)
 }
 
-// one CTA: the slice [off, off + n) of this rank's copy of a replicated vector -> the same
-// place in every peer's copy; then wait for the peers' slices
+// one CTA: all-gather of a replicated vector `full` (LOCAL memory, fixed address) whose slice
+// [off, off + n) this rank has just written: the slice goes into the exchange's parity half of
+// every peer's heap region, then the peers' slices are copied from this rank's region into
+// `full`.  Exchange number in device memory (*dseq + 1), total = length of the vector.
 __global__ void __launch_bounds__(1024)
-k_push_slice(int64_t n, peer_ptrs pp, int64_t data_off, int64_t flag_off, int64_t off, int world,
-             int rank, unsigned long long seq) {
-    const double* mine = reinterpret_cast<const double*>(pp.base[rank] + data_off) + off;
+k_push_slice(int64_t n, peer_ptrs pp, int64_t data_off, int64_t flag_off, int64_t off, int64_t total,
+             int world, int rank, unsigned long long* dseq, double* full) {
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(dseq) + 1;
+    const int64_t par = (int64_t)(seq & 1ull) * total;
     for (int64_t i = threadIdx.x; i < n; i += 1024) {
-        const double v = mine[i];
+        const double v = full[off + i];
         for (int q = 0; q < world; ++q)
-            if (q != rank) reinterpret_cast<double*>(pp.base[q] + data_off)[off + i] = v;
+            if (q != rank) reinterpret_cast<double*>(pp.base[q] + data_off)[par + off + i] = v;
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < world && threadIdx.x != rank)
         st_release_sys(reinterpret_cast<unsigned long long*>(pp.base[threadIdx.x] + flag_off) + rank, seq);
     wait_peers(reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off), world, rank, seq);
+    const double* got = reinterpret_cast<const double*>(pp.base[rank] + data_off) + par;
+    for (int64_t i = threadIdx.x; i < total; i += 1024)
+        if (i < off || i >= off + n) full[i] = __ldcg(got + i);
+    if (threadIdx.x == 0) *dseq = seq;
 }
 
 // buf[0..count) <- sum over ranks (fixed rank order: identical bits on every rank)
 __global__ void __launch_bounds__(NPB_RED_SLOT)
 k_allreduce_p2p(double* __restrict__ buf, int count, peer_ptrs pp, int64_t data_off,
-                int64_t flag_off, int64_t parity_off, int world, int rank, unsigned long long seq) {
+                int64_t flag_off, int64_t pstride, int world, int rank, unsigned long long* dseq) {
     const int t = threadIdx.x;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(dseq) + 1;
+    const int64_t parity_off = (int64_t)(seq & 1ull) * pstride;
     if (t < count) {
         const double v = buf[t];
         for (int q = 0; q < world; ++q)
@@ -171,6 +184,7 @@ k_allreduce_p2p(double* __restrict__ buf, int count, peer_ptrs pp, int64_t data_
         for (int q = 0; q < world; ++q) s += mine[(int64_t)q * NPB_RED_SLOT + t];
         buf[t] = s;
     }
+    if (t == 0) *dseq = seq;
 }
 
 static inline peer_ptrs make_peers(const npb_dist* d) {
@@ -188,21 +202,24 @@ int npb_dist_halo_exchange(const npb_halo& h, const double* x, cudaStream_t st, 
     // boundary values of x -> this rank's slot of the gather buffer -> every rank
     const npb_dist* d = (const npb_dist*)h.dist;
     if (h.p2p_data >= 0 && d->heap[d->rank]) {
-        const unsigned long long seq = ++(*h.seq);
-        const int64_t parity_off = (int64_t)(seq & 1) * d->world * h.maxb;
+        // h.seq: DEVICE counter of this operator's exchanges (the kernels read / bump it)
+        const int64_t pstride = (int64_t)d->world * h.maxb;
         if (h.maxb > 0) {
             k_push_halo<<<1, 1024, 0, st>>>(h.n_send, h.send_idx, x, make_peers(d), h.p2p_data,
-                                            h.p2p_flags, parity_off + (int64_t)d->rank * h.maxb,
-                                            d->world, d->rank, seq, wait ? 0 : 1);
+                                            h.p2p_flags, (int64_t)d->rank * h.maxb, pstride,
+                                            d->world, d->rank, h.seq, wait ? 0 : 1);
             NPB_COUNT_LAUNCH();
             if (wait) {
                 wait->flags = reinterpret_cast<const unsigned long long*>(d->heap[d->rank] + h.p2p_flags);
-                wait->seq = seq;
+                wait->seq = 0;
                 wait->world = d->world;
                 wait->rank = d->rank;
+                wait->dseq = h.seq;
+                wait->pstride = pstride;
             }
         }
-        *xh = reinterpret_cast<const double*>(d->heap[d->rank] + h.p2p_data) + parity_off;
+        // base of parity 0: the consuming kernel adds the parity of the exchange (npb_halo_begin)
+        *xh = reinterpret_cast<const double*>(d->heap[d->rank] + h.p2p_data);
         return NPB_OK;
     }
     *xh = h.recv;
@@ -220,10 +237,9 @@ int npb_dist_allreduce_sum(const npb_dist* dc, double* buf, int count, cudaStrea
     npb_dist* d = const_cast<npb_dist*>(dc);
     if (!d || d->world <= 1 || count <= 0) return NPB_OK;
     if (d->red_data >= 0 && count <= NPB_RED_SLOT) {
-        const unsigned long long seq = ++d->red_seq;
         k_allreduce_p2p<<<1, NPB_RED_SLOT, 0, st>>>(buf, count, make_peers(d), d->red_data, d->red_flags,
-                                                   (int64_t)(seq & 1) * d->world * NPB_RED_SLOT,
-                                                   d->world, d->rank, seq);
+                                                   (int64_t)d->world * NPB_RED_SLOT, d->world, d->rank,
+                                                   reinterpret_cast<unsigned long long*>(d->heap[d->rank] + d->red_dseq));
         NPB_COUNT_LAUNCH();
         return NPB_OK;
     }
@@ -235,13 +251,15 @@ double* npb_dist_heap_ptr(const npb_dist* d, int64_t off) {
     return (d && d->heap[d->rank]) ? reinterpret_cast<double*>(d->heap[d->rank] + off) : nullptr;
 }
 
-// direct-store all-gather of a replicated vector living in the symmetric heap at data_off
-// (+ elem_off doubles for the parity): this rank's slice [offsets[rank], offsets[rank+1]) is
-// already written in its own copy
-int npb_dist_push_slice(const npb_dist* d, int64_t data_off, int64_t flag_off, int64_t elem_off,
-                        const int64_t* offsets, unsigned long long seq, cudaStream_t st) {
+// direct-store all-gather of the replicated vector `full` (local memory): this rank's slice
+// [offsets[rank], offsets[rank+1]) is already written in it; the heap region at data_off
+// (2 parities x offsets[world] doubles) carries the peers' slices; dseq = device counter
+int npb_dist_push_slice(const npb_dist* d, int64_t data_off, int64_t flag_off,
+                        const int64_t* offsets, unsigned long long* dseq, double* full,
+                        cudaStream_t st) {
     k_push_slice<<<1, 1024, 0, st>>>(offsets[d->rank + 1] - offsets[d->rank], make_peers(d), data_off,
-                                     flag_off, elem_off + offsets[d->rank], d->world, d->rank, seq);
+                                     flag_off, offsets[d->rank], offsets[d->world], d->world, d->rank,
+                                     dseq, full);
     NPB_COUNT_LAUNCH();
     return NPB_OK;
 }
@@ -360,8 +378,8 @@ int npb_dist_heap_open(void* handle, const char* all_handles) {
     // all-reduce slots: 2 parities x world x NPB_RED_SLOT doubles + world counters
     d->red_data = 0;
     d->red_flags = (int64_t)2 * d->world * NPB_RED_SLOT * 8;
+    d->red_dseq = d->red_flags + 128;          // (the flags take world * 8 <= 64 bytes)
     d->heap_used = d->red_flags + 256;
-    d->red_seq = 0;
     return NPB_OK;
 }
 

@@ -15,7 +15,7 @@ struct npb_dist {            // one per process: the library's NCCL communicator
     void* ipc_base[NPB_MAX_PEERS] = {};    // mappings opened here (closed by npb_dist_free)
     int64_t heap_bytes = 0, heap_used = 0;
     int64_t red_data = -1, red_flags = -1; // offsets of the all-reduce slots
-    unsigned long long red_seq = 0;
+    int64_t red_dseq = -1;                 // offset of the all-reduce exchange counter (device)
 };
 
 // Halo of one row-sharded operator.  Local column numbering: [0, n_own) = the columns this
@@ -36,10 +36,16 @@ struct npb_halo {
 
 // what the consumer of a direct-store exchange still has to wait for: the arrival counters
 // flags[q] (q != rank) of this rank reaching seq.  flags == NULL: nothing (already waited).
+// The sequence number of an exchange lives ON THE DEVICE (dseq, bumped by the publishing
+// kernel): neither the number nor the parity of the slots it selects is a kernel argument, so
+// the launch sequence of a solve phase is identical from call to call and can be replayed as a
+// CUDA graph.
 struct npb_wait {
     const unsigned long long* flags;
-    unsigned long long seq;
+    unsigned long long seq;              // filled in by npb_halo_begin from *dseq
     int world, rank;
+    const unsigned long long* dseq;      // exchange counter of the operator (already bumped)
+    long long pstride;                   // doubles between the two parities of the halo slots
 };
 
 __device__ __forceinline__ unsigned long long npb_ld_acquire_sys(const unsigned long long* p) {
@@ -62,6 +68,20 @@ __device__ __forceinline__ void npb_wait_peers(const npb_wait& w) {
     }
 }
 
+__device__ __forceinline__ unsigned long long npb_ld_volatile(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+// prologue of a kernel that reads a halo published by direct stores: pick the parity of this
+// exchange (xh is handed in as the base of parity 0), then wait for the peers
+__device__ __forceinline__ void npb_halo_begin(npb_wait& w, const double*& xh) {
+    if (w.flags) {
+        w.seq = npb_ld_volatile(w.dseq);
+        xh += (long long)(w.seq & 1ull) * w.pstride;
+    }
+    npb_wait_peers(w);
+}
+
 // publishes / fetches the boundary values of x; *xh = where the SpMV reads them.  With
 // `wait` != NULL a direct-store exchange only PUBLISHES and leaves the wait for the peers'
 // values to the consumer kernel (overlaps the NVLink latency with that kernel's launch).
@@ -71,5 +91,6 @@ int npb_dist_allreduce_sum(const npb_dist* d, double* buf, int count, cudaStream
 int npb_dist_allgatherv(const npb_dist* d, const double* mine, double* full,
                         const int64_t* offsets, cudaStream_t st);
 double* npb_dist_heap_ptr(const npb_dist* d, int64_t off);
-int npb_dist_push_slice(const npb_dist* d, int64_t data_off, int64_t flag_off, int64_t elem_off,
-                        const int64_t* offsets, unsigned long long seq, cudaStream_t st);
+int npb_dist_push_slice(const npb_dist* d, int64_t data_off, int64_t flag_off,
+                        const int64_t* offsets, unsigned long long* dseq, double* full,
+                        cudaStream_t st);

@@ -77,7 +77,7 @@ k_spmv_stream(int64_t nrows, const int32_t* __restrict__ ptr,
     constexpr int TPR = SP_THREADS / ROWS;
     __shared__ int32_t sptr[ROWS + 1];
     __shared__ double sprod[SP_TILE];
-    if (HALO) npb_wait_peers(epi.wait);
+    if (HALO) npb_halo_begin(epi.wait, epi.xh);
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS;
     const int nr = (int)min((int64_t)ROWS, nrows - r0);
@@ -123,7 +123,7 @@ k_spmv_stream_async(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
     __shared__ int32_t sptr[ROWS + 1];
     __shared__ __align__(16) int32_t sidx[SP_TILE];
     __shared__ __align__(16) double sdat[SP_TILE];
-    if (HALO) npb_wait_peers(epi.wait);
+    if (HALO) npb_halo_begin(epi.wait, epi.xh);
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS;
     const int nr = (int)min((int64_t)ROWS, nrows - r0);
@@ -178,7 +178,7 @@ k_spmv_stream_v4(int64_t nrows, int64_t nnz, const int32_t* __restrict__ ptr,
     constexpr int ROUNDS = SP_TILE / (SP_THREADS * 4);
     __shared__ int32_t sptr[ROWS + 1];
     __shared__ __align__(16) double sprod[SP_TILE];
-    if (HALO) npb_wait_peers(epi.wait);
+    if (HALO) npb_halo_begin(epi.wait, epi.xh);
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS;
     const int nr = (int)min((int64_t)ROWS, nrows - r0);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TPB)
 k_spmv(int64_t nrows, const int32_t* __restrict__ ptr,
        const int32_t* __restrict__ idx, const double* __restrict__ dat,
        const double* x, spmv_epi epi, double* y) {
-    if (HALO) npb_wait_peers(epi.wait);
+    if (HALO) npb_halo_begin(epi.wait, epi.xh);
     const int lane = threadIdx.x & (G - 1);
     const int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) / G;
     double s = 0.0;

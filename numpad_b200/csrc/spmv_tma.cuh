@@ -86,7 +86,7 @@ k_spmv_tma(int64_t nrows, int64_t nnz, int64_t nunits, const int32_t* __restrict
     tm_smem<G, T>& S = *reinterpret_cast<tm_smem<G, T>*>(
         (reinterpret_cast<uintptr_t>(tm_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x;
-    if (HALO) npb_wait_peers(epi.wait);
+    if (HALO) npb_halo_begin(epi.wait, epi.xh);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < TM_STAGES; ++s) {

@@ -39,6 +39,8 @@ SHARD_PRODUCTS_ABOVE = 500000
 
 # bytes of the symmetric heap for direct-store exchanges (0 / NPB_DIST_P2P=0: NCCL only)
 HEAP_BYTES = 64 << 20
+# replay the sharded preconditioner as a CUDA graph (needs the direct-store exchanges)
+GRAPHS = os.environ.get('NPB_DIST_GRAPHS', '1') != '0'
 
 _handle = {'ptr': None, 'rank': 0, 'world': 1, 'p2p': False, 'heap': None}
 
@@ -218,14 +220,26 @@ def _fill_mat(m, op, handle, f32=False):
             d = L.npb_dist_heap_alloc(ctypes.c_void_p(handle), 2 * world * op.maxb * 8)
             f = L.npb_dist_heap_alloc(ctypes.c_void_p(handle), world * 8)
             if d >= 0 and f >= 0:
-                seq = ctypes.c_ulonglong(0)
-                _seq_keep.append(seq)
                 m.halo.p2p_data, m.halo.p2p_flags = d, f
-                m.halo.seq = ctypes.addressof(seq)
+                m.halo.seq = _new_counter()
+            else:
+                _all_p2p[0] = False        # an exchange of this solve goes through NCCL
+        elif op.maxb > 0:
+            _all_p2p[0] = False
     return m
 
 
-_seq_keep = []          # host exchange counters of the current solve's operators
+_seq_keep = []          # device exchange counters of the current solve's operators
+_all_p2p = [True]       # every exchange of the current solve goes by direct stores
+
+
+def _new_counter():
+    """exchange counter of one operator, in device memory (the kernels read and bump it: the
+    launch sequence of the solve phase does not depend on it and can be graph-captured)"""
+    from ._dev import device
+    t = torch.zeros(1, dtype=torch.int64, device=device())
+    _seq_keep.append(t)
+    return t.data_ptr()
 
 
 def _heap_reset():
@@ -239,6 +253,7 @@ def _heap_reset():
     dist.barrier()
     _lib.lib().call('npb_dist_heap_reset', ctypes.c_void_p(_handle['ptr']), stream_ptr())
     _seq_keep.clear()
+    _all_p2p[0] = True
     dist.barrier()
 
 
@@ -307,9 +322,11 @@ class ShardedHierarchy:
                     d = Lc.npb_dist_heap_alloc(ctypes.c_void_p(handle), 2 * cn[world] * 8)
                     f = Lc.npb_dist_heap_alloc(ctypes.c_void_p(handle), world * 8)
                     if d >= 0 and f >= 0:
-                        seq = ctypes.c_ulonglong(0)
-                        _seq_keep.append(seq)
-                        L.g_data, L.g_flags, L.g_seq = d, f, ctypes.addressof(seq)
+                        L.g_data, L.g_flags, L.g_seq = d, f, _new_counter()
+                    else:
+                        _all_p2p[0] = False
+                else:
+                    _all_p2p[0] = False
         s = self.struct = amg.AmgStruct()
         ctypes.memmove(ctypes.addressof(s), ctypes.addressof(h.struct), ctypes.sizeof(amg.AmgStruct))
         s.levels = ctypes.cast(self.arr, ctypes.POINTER(amg.AmgLevel))
@@ -357,6 +374,13 @@ class ShardedLsc:
         s.a_dinv = self.a_dinv.data_ptr()
         s.amg_a, s.amg_l = self.amg_a.addr, self.amg_l.addr
         s.a_gmres = 0
+        # CUDA-graph replay of the apply (csrc/amg.cu): only when every exchange inside it goes by
+        # direct stores with device-side counters (no NCCL call, nothing host-dependent)
+        self.graph_id = 0
+        if _handle['p2p'] and _all_p2p[0] and GRAPHS:
+            amg.LscPreconditioner._next_graph_id += 1
+            self.graph_id = amg.LscPreconditioner._next_graph_id
+        s.graph_id = self.graph_id
         s.cycles_a, s.cycles_l = M.struct.cycles_a, M.struct.cycles_l
         for k in range(5):
             s.wv[k] = self.wv[k].data_ptr()
@@ -365,6 +389,14 @@ class ShardedLsc:
         s.scal, s.red = self.scal.data_ptr(), self.red.data_ptr()
         self.c_apply = ctypes.cast(_lib.lib().cdll.npb_lsc_apply_cb, ctypes.c_void_p).value
         self.c_ctx = ctypes.addressof(s)
+
+    def __del__(self):
+        try:
+            if self.graph_id:
+                from . import _lib
+                _lib.lib().cdll.npb_lsc_graph_release(int(self.graph_id))
+        except Exception:
+            pass
 
 
 def permuted(J, perm, inv):
