@@ -18,8 +18,8 @@ from numpad_b200.workloads.cavity import CavityProblem  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--grid', type=int, default=1024)
-ap.add_argument('--warmup', type=int, default=1)
-ap.add_argument('--rtol', type=float, default=1e-10)
+ap.add_argument('--warmup', type=int, default=2)
+ap.add_argument('--rtol', type=float, default=1e-12)
 ap.add_argument('--only', default='all', help='all | assembly | solve')
 a = ap.parse_args()
 
