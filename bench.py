@@ -365,13 +365,15 @@ def run_ours(args):
         """the timed call: ONE Newton iteration through the drop-in API.  max_iter=2 with
         rel_tol=1: iteration 0 assembles and solves, iteration 1 re-evaluates the residual,
         sees it smaller and returns the adsolution."""
-        precond.forget()       # every step pays the full preconditioner setup
+        precond.forget()       # every step pays the full preconditioner setup ...
+        linsolve.forget_factors()      # ... or the full direct factorisation (Euler / NS)
         return npd.solve_newton_with_dt(P.residual, npd.adarray(ud), step_args(uoldd),
                                         {}, np.inf, 2, 0.0, 1.0, False)
 
     def instrumented():
         """the same arithmetic phase by phase (reported in `phases`, not timed for `value`)"""
         precond.forget()
+        linsolve.forget_factors()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         u = npd.adarray(u_dev)

@@ -45,6 +45,12 @@ def reset_hints(hard=True):
         _stale['btlu'], _stale['sig'] = None, None
 
 
+def forget_factors():
+    """drop the block-tridiagonal factorisation kept for reuse as a preconditioner (the
+    robust-solver hint itself stays): the next robust solve factorises again"""
+    _stale['btlu'], _stale['sig'] = None, None
+
+
 class LinearSolveError(RuntimeError):
     pass
 
