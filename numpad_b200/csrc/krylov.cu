@@ -328,16 +328,22 @@ k_dot_multi(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
 // same for few vectors (kc <= KS: the CG inner products and norms, the first Gram-Schmidt
 // steps): the general kernel keeps only kc + 1 eight-byte loads in flight per thread, which
 // leaves a one- or two-vector product latency-bound; here every thread moves two elements
-// with 128-bit loads and two such pairs per round.  n even, V / w / ld 16-byte aligned.
+// with 128-bit loads and two such pairs per round.  V / w / ld 16-byte aligned; any n.
 template <int KS>
 __global__ void __launch_bounds__(TPB)
-k_dot_few(int64_t n2, int kc, const double* __restrict__ V, int64_t ld,
+k_dot_few(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
           const double* __restrict__ w, double* __restrict__ partial,
           unsigned int* __restrict__ ticket, double* __restrict__ out) {
     __shared__ double smem[(TPB / 32) * KS];
     double acc[KS];
 #pragma unroll
     for (int j = 0; j < KS; ++j) acc[j] = 0.0;
+    const int64_t n2 = n >> 1;              // element pairs; an odd last element goes to one thread
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < KS; ++j)
+            if (j < kc) acc[j] = V[(int64_t)j * ld + n - 1] * w[n - 1];
+    }
     const int64_t stride = (int64_t)gridDim.x * TPB;
     const double2* w2 = reinterpret_cast<const double2*>(w);
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n2; i += 2 * stride) {
@@ -555,14 +561,15 @@ static inline unsigned int* red_ticket(void* scratch) {
 
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st) {
-    const bool vec = (n % 2 == 0) && ((((uintptr_t)V | (uintptr_t)w) & 15) == 0) && (ld % 2 == 0 || k <= 1);
+    // (the pressure space of the cavity has N^2 - 1 unknowns: odd lengths must take the fast path too)
+    const bool vec = ((((uintptr_t)V | (uintptr_t)w) & 15) == 0) && (ld % 2 == 0 || k <= 1);
     for (int j0 = 0; j0 < k; j0 += KC) {
         int kc = k - j0 < KC ? k - j0 : KC;
         if (vec && kc <= 2 && n >= 4096)
-            k_dot_few<2><<<grid_for(n / 4), TPB, 0, st>>>(n / 2, kc, V + (int64_t)j0 * ld, ld, w,
+            k_dot_few<2><<<grid_for(n / 4), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
                                                         red_partial(scratch), red_ticket(scratch), out + j0);
         else if (vec && kc <= 6 && n >= 4096)
-            k_dot_few<6><<<grid_for(n / 4), TPB, 0, st>>>(n / 2, kc, V + (int64_t)j0 * ld, ld, w,
+            k_dot_few<6><<<grid_for(n / 4), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
                                                         red_partial(scratch), red_ticket(scratch), out + j0);
         else
             k_dot_multi<<<grid_for(n), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,

@@ -321,7 +321,8 @@ def test_spmv_tma_pipeline(dev, nrows, ncols, per_row):
 
 
 @pytest.mark.parametrize('n,k', [(1, 1), (7, 3), (1000, 1), (4097, 5), (200001, 17), (300000, 40),
-                                 (200000, 1), (200000, 2), (300000, 5), (65536, 6), (4096, 3)])
+                                 (200000, 1), (200000, 2), (300000, 5), (65536, 6), (4096, 3),
+                                 (200001, 1), (300001, 2), (65537, 6)])
 def test_multi_dot_and_axpy(dev, n, k):
     """Gram-Schmidt building blocks of the FGMRES (csrc/krylov.cu): out = V^T w, and
     w += sign * V h with ||w||^2, against numpy (odd lengths, k above and below the

@@ -318,3 +318,42 @@ def test_admpi_single_rank(npd):
     assert info == 0
     np.testing.assert_allclose(sol.cpu().numpy(), x.cpu().numpy(), atol=1e-9)
     assert abs(_dot(x, x) - float(x @ x)) < 1e-9 and abs(_norm2(x) - float(x.norm())) < 1e-10
+
+
+def test_multi_rhs_tangent_through_solve_vs_oracle(npd, orc):
+    """d u / d p for 16 parameters through one cavity solve (reference
+    adsolve.py:113-147: one LU solve per column of the densified dR/dp).  Here the solver is set
+    up once for all 16 right-hand sides (linsolve.solve_multi), operands stay on the device;
+    the result must match the oracle's to 1e-8."""
+    import time
+    from numpad_b200 import linsolve
+    from numpad_b200.workloads.cavity import CavityProblem
+    N, k = 96, 16
+    rng = np.random.RandomState(7)
+    n = N * (3 * N - 2)
+    B = np.zeros((n, k))
+    for j in range(k):                       # 16 localised forcing patterns
+        idx = rng.randint(N * N, n, 200)
+        B[idx, j] = rng.standard_normal(200)
+    out = {}
+    for name, xp in (('gpu', npd), ('cpu', orc)):
+        P = CavityProblem(xp, N)
+        q0 = xp.array(P.fixed_state(amp=1e-3))
+        p = xp.array(0.1 * np.ones(k))
+        Bx = xp.array(B)
+
+        def residual(q, q_old, dt, p):
+            return P.residual(q, q_old, dt, xp.dot(Bx, p))
+        t0 = time.perf_counter()
+        q = xp.solve(residual, q0, args=(q0, 0.02, p), rel_tol=1e-9, abs_tol=1e-9, verbose=False)
+        t1 = time.perf_counter()
+        dq = q.diff(p, 'tangent')
+        t2 = time.perf_counter()
+        out[name] = (np.asarray(dq.todense()), t1 - t0, t2 - t1)
+        if name == 'gpu':
+            assert 'reused' in linsolve.last_info['method'], linsolve.last_info['method']
+    g, c = out['gpu'][0], out['cpu'][0]
+    assert g.shape == c.shape == (n, k)
+    np.testing.assert_allclose(g, c, rtol=0, atol=1e-8 * np.abs(c).max())
+    print('multi-RHS tangent: GPU solve %.2fs, 16-column tangent %.2fs; oracle %.2fs / %.2fs'
+          % (out['gpu'][1], out['gpu'][2], out['cpu'][1], out['cpu'][2]))
