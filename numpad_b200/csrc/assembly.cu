@@ -127,18 +127,23 @@ k_relabel_fill(int64_t nrows, const int32_t* __restrict__ ptr,
     int nz = 0;
     if (r < nrows) {
         int32_t o = optr[r];
+        // optr may come from a RECORDED structure (assembly plan replay) whose operand has
+        // deviated: stay inside the row's slots and leave no slot undefined (the deviation
+        // itself is detected by the checked fills upstream; this only keeps later kernels
+        // of the doomed replay on valid indices)
+        const int32_t oe = optr[r + 1];
         for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
             const int32_t c = idx[k];
             const int32_t m = __ldg(map + c);
             if (m >= 0) {
                 double v = npb_apply(sc, in[k]);
                 if (w) v = __dmul_rn(v, __ldg(w + c));
-                oidx[o] = m;
-                out[o] = v;
+                if (o < oe) { oidx[o] = m; out[o] = v; }
                 nz += (v == 0.0);
                 ++o;
             }
         }
+        for (; o < oe; ++o) { oidx[o] = 0; out[o] = 0.0; }
     }
     for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
     if (nz && (threadIdx.x & 31) == 0 && zero_count)
@@ -173,8 +178,12 @@ k_gather_fill(int64_t nrows, const int32_t* __restrict__ map,
     int64_t r = ((int64_t)blockIdx.x * TPB + threadIdx.x) >> 3;
     int nz = 0;
     const int32_t m = (r < nrows) ? map[r] : -1;
-    if (m >= 0) {
-        const int32_t b0 = bptr[m], len = bptr[m + 1] - b0, o = optr[r];
+    if (r < nrows) {
+        // (bounded to the row's slots and no slot left undefined: optr may be a recorded
+        // structure, see k_relabel_fill)
+        const int32_t o = optr[r], slots = optr[r + 1] - o;
+        const int32_t b0 = m >= 0 ? bptr[m] : 0;
+        const int32_t len = m >= 0 ? min(bptr[m + 1] - b0, slots) : 0;
         const double wr = w ? w[r] : 1.0;
         for (int32_t k = lane; k < len; k += 8) {
             oidx[o + k] = bidx[b0 + k];
@@ -183,6 +192,7 @@ k_gather_fill(int64_t nrows, const int32_t* __restrict__ map,
             out[o + k] = v;
             nz += (v == 0.0);
         }
+        for (int32_t k = len + lane; k < slots; k += 8) { oidx[o + k] = 0; out[o + k] = 0.0; }
     }
     for (int dd = 16; dd; dd >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, dd);
     if (nz && (threadIdx.x & 31) == 0 && zero_count)
@@ -304,10 +314,10 @@ k_sel_fill(int64_t nrows, const int32_t* __restrict__ map,
     int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r >= nrows) return;
     const int32_t m = map[r];
-    if (m >= 0) {
-        const int32_t o = optr[r];
-        oidx[o] = m;
-        out[o] = w ? w[r] : 1.0;
+    const int32_t o = optr[r], oe = optr[r + 1];     // (bounded: optr may be a recorded structure)
+    if (o < oe) {
+        oidx[o] = m >= 0 ? m : 0;
+        out[o] = m >= 0 ? (w ? w[r] : 1.0) : 0.0;
     }
 }
 
