@@ -367,8 +367,11 @@ def run_ours(args):
         sees it smaller and returns the adsolution."""
         precond.forget()       # every step pays the full preconditioner setup ...
         linsolve.forget_factors()      # ... or the full direct factorisation (Euler / NS)
+        # (Euler / NS: max_iter=1 -- the same work, one iteration + the closing residual
+        # evaluation + adsolution -- because a first Newton step from the perturbed uniform flow
+        # need not lower the max-norm residual, which the rel_tol=1 exit of the cavity step relies on)
         return npd.solve_newton_with_dt(P.residual, npd.adarray(ud), step_args(uoldd),
-                                        {}, np.inf, 2, 0.0, 1.0, False)
+                                        {}, np.inf, 2 if cavity else 1, 0.0, 1.0, False)
 
     def instrumented():
         """the same arithmetic phase by phase (reported in `phases`, not timed for `value`)"""
@@ -429,7 +432,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         sol = step_resident()
-    assert sol._n_Newton == 2, 'the benchmark step must be exactly one Newton iteration'
+    assert sol._n_Newton == (2 if cavity else np.inf), 'the benchmark step must be exactly one Newton iteration'
     J, du = instrumented()
     with Clocks(local) as clk:
         L.npb_launch_count_reset()
