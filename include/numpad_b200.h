@@ -372,6 +372,8 @@ typedef struct npb_amg {            /* [host] */
     const double* coarse_inv;       /* dense inverse of the coarsest operator */
     npb_amg_level* levels;
     const void* dist;               /* npb_dist_init handle when levels are row-sharded */
+    int32_t gamma, gamma_from;      /* gamma > 1: levels >= gamma_from are visited gamma times per
+                                       cycle (W-cycle on the coarse part of the hierarchy) */
 } npb_amg;
 
 typedef struct npb_amg_precond {    /* [host] ctx of npb_amg_apply_cb */

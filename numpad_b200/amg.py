@@ -43,7 +43,8 @@ class AmgStruct(ctypes.Structure):
     _fields_ = [('nlevels', ctypes.c_int32), ('nu_pre', ctypes.c_int32),
                 ('nu_post', ctypes.c_int32), ('coarse_n', ctypes.c_int32),
                 ('omega', ctypes.c_double), ('coarse_inv', ctypes.c_void_p),
-                ('levels', ctypes.POINTER(AmgLevel)), ('dist', ctypes.c_void_p)]
+                ('levels', ctypes.POINTER(AmgLevel)), ('dist', ctypes.c_void_p),
+                ('gamma', ctypes.c_int32), ('gamma_from', ctypes.c_int32)]
 
 
 class AmgPrecondStruct(ctypes.Structure):
@@ -222,7 +223,8 @@ class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=600, max_levels=24, agg_passes=1, p_trunc=0.0, agg='mis1'):
+                 coarse_max=600, max_levels=24, agg_passes=1, p_trunc=0.0, agg='mis1',
+                 gamma=1, gamma_from=2):
         A = A.materialized()
         self.mats, self.keep = [], []
         levels = []
@@ -299,6 +301,7 @@ class Hierarchy:
         self.struct.nlevels = nl
         self.struct.nu_pre = self.struct.nu_post = int(nu)
         self.struct.omega = float(omega)
+        self.struct.gamma, self.struct.gamma_from = int(gamma), int(gamma_from)
         self.struct.levels = ctypes.cast(self.arr, ctypes.POINTER(AmgLevel))
         last = levels[-1]['A']
         nc = last.shape[0]
@@ -366,7 +369,7 @@ class LscPreconditioner:
 
     def __init__(self, J, cycles_a=1, cycles_l=(3, 4), theta_a=0.25, nu_a=4, nu_l=1, smooth_a=True,
                  reuse=None, a_gmres=0, agg_passes=1, agg_passes_a=None, p_trunc=0.1,
-                 agg_l='mis1', agg_a='mis2'):
+                 agg_l='mis1', agg_a='mis2', gamma_l=1, gamma_a=1, gamma_from=2):
         J = J.materialized()
         n = J.shape[0]
         d = diagonal(J)
@@ -399,7 +402,7 @@ class LscPreconditioner:
         else:
             self.Lm = _csr_times_csr(self.D, self.G).scaled(-1.0).materialized()
             self.amg_l = Hierarchy(self.Lm, theta=0.0, nu=nu_l, agg_passes=agg_passes,
-                                   p_trunc=p_trunc, agg=agg_l)
+                                   p_trunc=p_trunc, agg=agg_l, gamma=gamma_l, gamma_from=gamma_from)
         # momentum block: distance-2 aggregation on the strength graph, prolongator
         # smoothed with the strength-filtered operator (keeps the two velocity
         # components apart); operator complexity 1.4 (2.97 with distance-1 aggregates:
@@ -415,7 +418,7 @@ class LscPreconditioner:
         else:
             self.amg_a = Hierarchy(self.A, theta=theta_a, nu=nu_a, smooth=smooth_a,
                                    agg_passes=agg_passes if agg_passes_a is None else agg_passes_a,
-                                   p_trunc=p_trunc, agg=agg_a)
+                                   p_trunc=p_trunc, agg=agg_a, gamma=gamma_a, gamma_from=gamma_from)
             self.a_dinv = self.amg_a.levels[0]['dinv']
         self.a_gmres = int(a_gmres)
         self.wv = [torch.zeros(nv, dtype=torch.float64, device=device()) for _ in range(5)]

@@ -550,6 +550,7 @@ struct npb_amg {
     const double* coarse_inv;   // dense row-major inverse of the coarsest operator
     npb_amg_level* levels;      // [host] array of nlevels descriptors
     const void* dist;           // npb_dist* when the fine levels are row-sharded, else NULL
+    int32_t gamma, gamma_from;  // gamma > 1: levels >= gamma_from are visited gamma times per cycle
 };
 
 static int jacobi_sweep(const npb_amg_level& L, double omega, const double* b, const double* xin,
@@ -558,88 +559,101 @@ static int jacobi_sweep(const npb_amg_level& L, double omega, const double* b, c
     return spmv_mat(L.A, xin, b, xout, 3, st, L.dinv, omega);
 }
 
-// x <- V-cycle(b) from a zero initial guess.  b and x have the fine size and
-// must not alias the hierarchy's work vectors.
-int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
-    cudaStream_t st = ST(stream);
-    const int nl = h->nlevels;
-    if (nl > 64) { npb_set_error("amg_vcycle: more than 64 levels"); return NPB_ERR_ARG; }
-    // which of the two ping-pong buffers of a level holds its iterate: kept in locals, the
-    // level descriptors are never modified, so the launch sequence of a cycle (buffers
-    // included) is the same on every call -- a captured CUDA graph of it can be replayed
+// One multigrid cycle on level l from a zero initial guess; the result is left in X[l] (level 0:
+// in xfine).  Which of the two ping-pong buffers of a level holds its iterate is kept in the
+// caller's arrays: the level descriptors are never modified, so the launch sequence of a cycle
+// (buffers included) is the same on every call and a captured CUDA graph of it can be replayed.
+// gamma > 1: levels from gamma_from down are visited gamma times (W-cycle on the coarse part of
+// the hierarchy, where a visit costs a few launches): repeated coarse corrections, each from a
+// zero coarse guess, between the pre- and the post-smoothing of the parent.
+struct cycle_bufs {
     double* X[64];
     double* X2[64];
     double* CB[64];          // right-hand side of level l (l >= 1)
-    for (int l = 0; l < nl; ++l) { X[l] = h->levels[l].x; X2[l] = h->levels[l].x2; CB[l] = h->levels[l].b; }
-    // downward
-    for (int l = 0; l < nl; ++l) {
-        npb_amg_level& L = h->levels[l];
-        const int64_t n = L.A.nrows;
-        const double* bl = (l == 0) ? b : CB[l];
-        if (l == nl - 1 && h->coarse_n > 0) {
-            double* xl = (l == 0) ? x : X[l];
-            k_dense_mv<<<npb_blocks((int64_t)h->coarse_n * 32, TPB), TPB, 0, st>>>(h->coarse_n, h->coarse_inv, bl, xl);
-            NPB_COUNT_LAUNCH();
-            break;
-        }
-        // pre-smoothing from zero: x = omega dinv b, then nu_pre-1 sweeps
-        double* cur = X[l];
-        double* oth = X2[l];
-        k_jacobi0<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, L.dinv, h->omega, bl, cur);
+    const double* bfine;
+    double* xfine;
+};
+
+static int amg_cycle(const npb_amg* h, int l, cycle_bufs& w, cudaStream_t st) {
+    const int nl = h->nlevels;
+    npb_amg_level& L = h->levels[l];
+    const int64_t n = L.A.nrows;
+    const double* bl = (l == 0) ? w.bfine : w.CB[l];
+    if (l == nl - 1 && h->coarse_n > 0) {
+        double* xl = (l == 0) ? w.xfine : w.X[l];
+        k_dense_mv<<<npb_blocks((int64_t)h->coarse_n * 32, TPB), TPB, 0, st>>>(h->coarse_n, h->coarse_inv, bl, xl);
         NPB_COUNT_LAUNCH();
-        NPB_COUNT_BYTES(24.0 * n);
-        const int extra = (l == nl - 1) ? (h->nu_pre + h->nu_post + 6) : (h->nu_pre - 1);
-        for (int s = 0; s < extra; ++s) {
-            jacobi_sweep(L, h->omega, bl, cur, oth, st);
-            double* t = cur; cur = oth; oth = t;
-        }
-        X[l] = cur; X2[l] = oth;                      // the iterate is in X[l]
-        if (l == nl - 1) {
-            if (l == 0) NPB_CUDA(cudaMemcpyAsync(x, X[l], n * 8, cudaMemcpyDeviceToDevice, st));
-            break;
-        }
+        return NPB_OK;
+    }
+    // pre-smoothing from zero: x = omega dinv b, then nu_pre-1 sweeps
+    double* cur = w.X[l];
+    double* oth = w.X2[l];
+    k_jacobi0<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, L.dinv, h->omega, bl, cur);
+    NPB_COUNT_LAUNCH();
+    NPB_COUNT_BYTES(24.0 * n);
+    const int extra = (l == nl - 1) ? (h->nu_pre + h->nu_post + 6) : (h->nu_pre - 1);
+    for (int s = 0; s < extra; ++s) {
+        jacobi_sweep(L, h->omega, bl, cur, oth, st);
+        double* t = cur; cur = oth; oth = t;
+    }
+    w.X[l] = cur; w.X2[l] = oth;                      // the iterate is in X[l]
+    if (l == nl - 1) {
+        if (l == 0) NPB_CUDA(cudaMemcpyAsync(w.xfine, w.X[l], n * 8, cudaMemcpyDeviceToDevice, st));
+        return NPB_OK;
+    }
+    const int reps = (h->gamma > 1 && l + 1 >= h->gamma_from && l + 2 < nl) ? h->gamma : 1;
+    for (int rep = 0; rep < reps; ++rep) {
         // r = b - A x ; b_{l+1} = R r
-        int rc = spmv_mat(L.A, X[l], bl, L.r, 1, st);
+        int rc = spmv_mat(L.A, w.X[l], bl, L.r, 1, st);
         if (rc) return rc;
         if (L.gather) {
             const npb_dist* d = (const npb_dist*)h->dist;
             if (L.g_data >= 0 && npb_dist_heap_ptr(d, 0)) {
                 // own slice written in place, the peers' slices arrive through the heap (g_seq:
                 // DEVICE exchange counter) and are copied into the level's right-hand side
-                rc = spmv_mat(L.R, L.r, nullptr, CB[l + 1] + L.offsets[d->rank], 0, st);
-                if (!rc) rc = npb_dist_push_slice(d, L.g_data, L.g_flags, L.offsets, L.g_seq, CB[l + 1], st);
+                rc = spmv_mat(L.R, L.r, nullptr, w.CB[l + 1] + L.offsets[d->rank], 0, st);
+                if (!rc) rc = npb_dist_push_slice(d, L.g_data, L.g_flags, L.offsets, L.g_seq, w.CB[l + 1], st);
             } else {
-                double* mine = CB[l + 1] + L.offsets[d->rank];
+                double* mine = w.CB[l + 1] + L.offsets[d->rank];
                 rc = spmv_mat(L.R, L.r, nullptr, mine, 0, st);
-                if (!rc) rc = npb_dist_allgatherv(d, mine, CB[l + 1], L.offsets, st);
+                if (!rc) rc = npb_dist_allgatherv(d, mine, w.CB[l + 1], L.offsets, st);
             }
         } else {
-            rc = spmv_mat(L.R, L.r, nullptr, CB[l + 1], 0, st);
+            rc = spmv_mat(L.R, L.r, nullptr, w.CB[l + 1], 0, st);
         }
         if (rc) return rc;
-    }
-    // upward
-    for (int l = nl - 2; l >= 0; --l) {
-        npb_amg_level& L = h->levels[l];
-        const int64_t n = L.A.nrows;
-        const double* bl = (l == 0) ? b : CB[l];
+        if ((rc = amg_cycle(h, l + 1, w, st))) return rc;
         // x += P x_{l+1}
-        int rc = spmv_mat(L.P, X[l + 1], X[l], X[l], 2, st);
-        if (rc) return rc;
-        double* cur = X[l];
-        double* oth = X2[l];
-        for (int s = 0; s < h->nu_post; ++s) {
-            double* out = (l == 0 && s == h->nu_post - 1) ? x : oth;
-            jacobi_sweep(L, h->omega, bl, cur, out, st);
-            if (out == x) { cur = x; break; }
-            double* t = cur; cur = oth; oth = t;
-        }
-        if (l == 0) {
-            if (cur != x) NPB_CUDA(cudaMemcpyAsync(x, cur, n * 8, cudaMemcpyDeviceToDevice, st));
-        } else {
-            X[l] = cur; X2[l] = oth;
-        }
+        if ((rc = spmv_mat(L.P, w.X[l + 1], w.X[l], w.X[l], 2, st))) return rc;
     }
+    cur = w.X[l];
+    oth = w.X2[l];
+    for (int s = 0; s < h->nu_post; ++s) {
+        double* out = (l == 0 && s == h->nu_post - 1) ? w.xfine : oth;
+        jacobi_sweep(L, h->omega, bl, cur, out, st);
+        if (out == w.xfine) { cur = w.xfine; break; }
+        double* t = cur; cur = oth; oth = t;
+    }
+    if (l == 0) {
+        if (cur != w.xfine) NPB_CUDA(cudaMemcpyAsync(w.xfine, cur, n * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        w.X[l] = cur; w.X2[l] = oth;
+    }
+    return NPB_OK;
+}
+
+// x <- one cycle (V, or W on the coarse levels) on b from a zero initial guess.  b and x have
+// the fine size and must not alias the hierarchy's work vectors.
+int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
+    cudaStream_t st = ST(stream);
+    const int nl = h->nlevels;
+    if (nl > 64) { npb_set_error("amg_vcycle: more than 64 levels"); return NPB_ERR_ARG; }
+    cycle_bufs w;
+    for (int l = 0; l < nl; ++l) { w.X[l] = h->levels[l].x; w.X2[l] = h->levels[l].x2; w.CB[l] = h->levels[l].b; }
+    w.bfine = b;
+    w.xfine = x;
+    int rc = amg_cycle(h, 0, w, st);
+    if (rc) return rc;
     NPB_CHECK_LAUNCH("amg_vcycle");
     return NPB_OK;
 }
@@ -735,7 +749,7 @@ struct npb_lsc {
 // the host structs above are declared a second time in include/numpad_b200.h (and mirrored
 // with ctypes, tests/test_abi.py): a one-sided edit must not compile
 static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 120, "npb_csr_mat layout");
-static_assert(sizeof(npb_amg_level) == 440 && sizeof(npb_amg) == 48, "npb_amg layout");
+static_assert(sizeof(npb_amg_level) == 440 && sizeof(npb_amg) == 56, "npb_amg layout");
 static_assert(sizeof(npb_amg_precond) == 152 && sizeof(npb_lsc) == 696, "npb_lsc layout");
 
 // y = d .* x as an npb_apply_fn (Jacobi preconditioner; ctx = npb_diag_ctx)
