@@ -280,11 +280,14 @@ int npb_bt_window_spmv(const int32_t* indptr, const int32_t* indices, const doub
                        double alpha, double beta, const double* y0 /* NULL: y */, double* y,
                        void* stream);
 /* both sweeps of a solve in one call (x = A^-1 b, or A^-T b when trans); off [host]: K + 1 level
- * offsets, sinv [host]: K device pointers to the row-major inverses; with graph_id > 0 the
- * launch sequence is captured after the first call and replayed (buffers must not move) */
-int npb_bt_solve(int K, const int64_t* off, const double* const* sinv, const int32_t* indptr,
+ * offsets, sinv [host]: K device pointers to the row-major inverses; M: the level at which the
+ * two elimination chains of a twisted factorisation meet (K - 1: one chain from the top);
+ * c / scratch: 2 * mmax and 2 * npb_bt_gemv_scratch_doubles(mmax) doubles; with graph_id > 0 the
+ * launch sequence is captured after the first call (the two chains as two branches) and
+ * replayed (buffers must not move) */
+int npb_bt_solve(int K, int M, const int64_t* off, const double* const* sinv, const int32_t* indptr,
                  const int32_t* indices, const double* data, const double* bp, double* z,
-                 double* c, double* scratch, int trans, int graph_id, void* stream);
+                 double* c, double* scratch, int64_t mmax, int trans, int graph_id, void* stream);
 int npb_bt_graph_release(int graph_id);
 int64_t npb_bt_gemv_scratch_doubles(int64_t m);
 int npb_bt_gemv(int64_t m, const double* M, int64_t ld, const double* x, double alpha,

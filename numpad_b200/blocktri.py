@@ -10,7 +10,9 @@ rest (test/cavity.py:97-114) and the Euler / Navier-Stokes Jacobians at the scri
   levels   : BFS from a pseudo-peripheral node over the graph of A + A^T (host, cached per
              pattern: it is the same for every Newton iteration of a run);
   ordering : unknowns sorted by level; in that order A is block tridiagonal (L_k | D_k | U_k);
-  factor   : S_0 = D_0, S_k = D_k - L_k S_{k-1}^-1 U_{k-1}; the dense inverses S_k^-1 are kept
+  factor   : twisted -- two elimination chains, from the first level down and from the last
+             level up (S_k = D_k - L_k S_{k-1}^-1 U_{k-1}, resp. D_k - U_k S_{k+1}^-1 L_{k+1}),
+             issued alternately on two streams, meet at a middle level; the dense inverses are kept
              (sum m_k^2 doubles).  L_k S^-1 and (L_k S^-1) U_{k-1} are window products of the
              CSR matrix with dense rows (a few rows each, csrc/blocktri.cu); the dense
              inversion is torch.linalg.inv_ex (cuSOLVER getrf + getrs: a plain library call);
@@ -108,61 +110,89 @@ class BlockTriLU:
         dev = device()
         mmax = max(off[k + 1] - off[k] for k in range(K))
         self.mmax = mmax
-        self.Sinv = []
-        infos = []
+        # ---- twisted factorisation: two elimination chains, from level 0 downwards and from
+        # level K-1 upwards, meet at level M (chosen so that both eliminate as many unknowns:
+        # the dense inversions are latency-bound, ~5 us per column, not flop-bound).  The chains
+        # are independent until M, so they are issued alternately on two streams and overlap.
         import os
-        prof = os.environ.get('NPB_BT_PROFILE')
-        marks = []
+        twisted = K >= 8 and os.environ.get('NPB_BT_TWISTED', '1') != '0'
+        M = K - 1
+        if twisted:
+            half, acc = n / 2.0, 0
+            for k in range(K):
+                acc += off[k + 1] - off[k]
+                if acc >= half:
+                    M = min(max(k, 1), K - 2)
+                    break
+        self.M = M
+        Sinv = [None] * K
+        infos = []
 
-        def mark(tag):
-            if prof:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((tag, e))
-        for k in range(K):
-            mark('start')
+        def contribution(k, nb):
+            """-(coupling of level k with the eliminated neighbour level nb)^T as an m_k x m_k
+            matrix: -(C S_nb^-1 B)^T with C = A[k, nb], B = A[nb, k]"""
+            r0, r1 = off[k], off[k + 1]
+            q0, q1 = off[nb], off[nb + 1]
+            m, mp = r1 - r0, q1 - q0
+            # Y = C S_nb^-1  (m x mp): each row combines the few rows of S^-1 that the row of C
+            # references
+            Y = torch.empty((m, mp), dtype=torch.float64, device=dev)
+            _call('npb_bt_window_spmm', Ap.indptr, Ap.indices, Ap.data, r0, r1, q0, q1,
+                  Sinv[nb], mp, mp, 1.0, 0.0, Y, mp)
+            # -(Y B)^T = -B^T Y^T: rows of A^T in level k, columns in level nb
+            Yt = Y.t().contiguous()
+            Wt = torch.empty((m, m), dtype=torch.float64, device=dev)
+            _call('npb_bt_window_spmm', At.indptr, At.indices, At.data, r0, r1, q0, q1,
+                  Yt, m, m, -1.0, 0.0, Wt, m)
+            return Wt
+
+        def eliminate(k, nbs):
+            """S_k^T = D_k^T - sum of the neighbours' contributions; keep S_k^-1 (row-major).
+            S^T is assembled, not S: the library inverse comes back column-major, and the
+            column-major image of (S^T)^-1 IS the row-major S^-1 the kernels read"""
             r0, r1 = off[k], off[k + 1]
             m = r1 - r0
-            # S^T is assembled (not S): the library inverse comes back column-major, and the
-            # column-major image of (S^T)^-1 IS the row-major S^-1 the kernels read
-            if k == 0:
+            St = None
+            for nb in nbs:
+                Wt = contribution(k, nb)
+                St = Wt if St is None else St.add_(Wt)
+            if St is None:
                 St = torch.zeros((m, m), dtype=torch.float64, device=dev)
-            else:
-                q0, mp = off[k - 1], r0 - off[k - 1]
-                # Y = L_k S_{k-1}^-1   (m x mp): each row combines the few rows of S^-1 that
-                # the row of L_k references
-                Y = torch.empty((m, mp), dtype=torch.float64, device=dev)
-                _call('npb_bt_window_spmm', Ap.indptr, Ap.indices, Ap.data, r0, r1, q0, r0,
-                      self.Sinv[k - 1], mp, mp, 1.0, 0.0, Y, mp)
-                # -W^T = -U_{k-1}^T Y^T  (m x m): rows of A^T in level k, columns in level k-1
-                mark('spmm1')
-                Yt = Y.t().contiguous()
-                mark('transpose')
-                St = torch.empty((m, m), dtype=torch.float64, device=dev)
-                _call('npb_bt_window_spmm', At.indptr, At.indices, At.data, r0, r1, q0, r0,
-                      Yt, m, m, -1.0, 0.0, St, m)
-                del Y, Yt
-                mark('spmm2')
             _call('npb_bt_window_to_dense', At.indptr, At.indices, At.data, r0, r1, r0, r1, 1.0, St, m)
-            mark('scatter')
             Ri, info = torch.linalg.inv_ex(St)
-            mark('inverse')
-            del St
             Si = Ri.t()
-            self.Sinv.append(Si if Si.is_contiguous() else Si.contiguous())
+            Sinv[k] = Si if Si.is_contiguous() else Si.contiguous()
             infos.append(info)
-        if prof:
-            torch.cuda.synchronize()
-            tot = {}
-            for (t0, e0), (t1, e1) in zip(marks[:-1], marks[1:]):
-                if t1 != 'start':
-                    tot[t1] = tot.get(t1, 0.0) + e0.elapsed_time(e1)
-            print('    btlu factor profile (ms):', {k_: round(v, 1) for k_, v in tot.items()}, flush=True)
+
+        if M == K - 1:
+            for k in range(K):
+                eliminate(k, [k - 1] if k > 0 else [])
+        else:
+            cur = torch.cuda.current_stream()
+            sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+            sa.wait_stream(cur)
+            sb.wait_stream(cur)
+            ia, ib = 0, K - 1
+            while ia < M or ib > M:
+                if ia < M:
+                    with torch.cuda.stream(sa):
+                        eliminate(ia, [ia - 1] if ia > 0 else [])
+                    ia += 1
+                if ib > M:
+                    with torch.cuda.stream(sb):
+                        eliminate(ib, [ib + 1] if ib < K - 1 else [])
+                    ib -= 1
+            cur.wait_stream(sa)
+            cur.wait_stream(sb)
+            eliminate(M, [M - 1, M + 1])
+            for t in Sinv:                       # allocated on the side streams, used on `cur`
+                t.record_stream(cur)
+        self.Sinv = Sinv
         bad = torch.stack(infos).ne(0).nonzero().reshape(-1)
         if bad.numel():
             raise np.linalg.LinAlgError('block-tridiagonal LU: singular diagonal block at level %d'
                                         % int(bad[0]))
-        self.scratch = torch.empty(int(_lib.lib().cdll.npb_bt_gemv_scratch_doubles(mmax)),
+        self.scratch = torch.empty(2 * int(_lib.lib().cdll.npb_bt_gemv_scratch_doubles(mmax)),
                                    dtype=torch.float64, device=dev)
         self.bytes = sum(s.numel() for s in self.Sinv) * 8
         # host descriptors + device work buffers of the solve phase
@@ -170,13 +200,13 @@ class BlockTriLU:
         self.sinv_h = np.asarray([s.data_ptr() for s in self.Sinv], dtype=np.uint64)
         self.bp = torch.empty(n, dtype=torch.float64, device=dev)
         self.z = torch.empty(n, dtype=torch.float64, device=dev)
-        self.c = torch.empty(mmax, dtype=torch.float64, device=dev)
+        self.c = torch.empty(2 * mmax, dtype=torch.float64, device=dev)     # one half per chain
         BlockTriLU._next_graph_id += 1
         self.graph_id = BlockTriLU._next_graph_id
 
     def describe(self):
-        return ('block-tridiagonal LU: %d levels, largest block %d, %.1f GB of dense inverses'
-                % (self.K, self.mmax, self.bytes / 1e9))
+        return ('block-tridiagonal LU: %d levels (chains meet at %d), largest block %d, %.1f GB of '
+                'dense inverses' % (self.K, self.M, self.mmax, self.bytes / 1e9))
 
     _next_graph_id = 0
 
@@ -192,10 +222,10 @@ class BlockTriLU:
         the factorisation and never move"""
         M = self.At if transpose else self.Ap
         self.bp.copy_(b.reshape(-1)[self.perm])
-        rc = _lib.lib().cdll.npb_bt_solve(self.K, self.off_h.ctypes.data, self.sinv_h.ctypes.data,
+        rc = _lib.lib().cdll.npb_bt_solve(self.K, self.M, self.off_h.ctypes.data, self.sinv_h.ctypes.data,
                                           M.indptr.data_ptr(), M.indices.data_ptr(), M.data.data_ptr(),
                                           self.bp.data_ptr(), self.z.data_ptr(), self.c.data_ptr(),
-                                          self.scratch.data_ptr(), 1 if transpose else 0,
+                                          self.scratch.data_ptr(), self.mmax, 1 if transpose else 0,
                                           int(self.graph_id), stream_ptr())
         if rc:
             raise RuntimeError('block-tridiagonal solve failed: %s' % _lib.lib().last_error())

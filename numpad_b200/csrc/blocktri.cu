@@ -292,25 +292,79 @@ struct bt_graph { int calls = 0; cudaGraphExec_t exec = nullptr; bool failed = f
 std::map<long long, bt_graph> g_bt_graphs;
 cudaStream_t g_bt_capture = nullptr;
 
-int bt_sweeps(int K, const int64_t* off, const double* const* sinv, const int32_t* ip,
-              const int32_t* ix, const double* dat, const double* bp, double* z, double* c,
-              double* scratch, int trans, cudaStream_t st) {
+
+// Twisted sweeps: the factorisation ran from BOTH ends towards level M (S_k for k < M from the
+// top, for k > M from the bottom, S_M joins them; M = K - 1 is the plain one-chain form).  The
+// two chains of each sweep are independent: with st2 != st they run on two streams (two
+// branches of the captured graph), each with its own work buffers.
+int bt_chain_fwd(int k0, int k1, int dir, const int64_t* off, const double* const* sinv,
+                 const int32_t* ip, const int32_t* ix, const double* dat, const double* bp, double* z,
+                 double* c, double* scratch, int trans, cudaStream_t st) {
+    // k = k0, k0 + dir, ... (k1 exclusive): c_k = b_k - (block towards the chain's start) z_prev
     int rc = NPB_OK;
-    for (int k = 0; k < K && !rc; ++k) {
+    for (int k = k0; k != k1 && !rc; k += dir) {
         const int64_t r0 = off[k], r1 = off[k + 1], m = r1 - r0;
         const double* src = bp + r0;
-        if (k > 0) {
-            const int64_t q0 = off[k - 1];
-            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, q0, r0, z + q0, -1.0, 1.0, bp + r0, c, st);
+        if (k != k0) {
+            const int p = k - dir;                    // previous level of this chain
+            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, off[p], off[p + 1], z + off[p], -1.0, 1.0, bp + r0, c, st);
             src = c;
         }
         if (!rc) rc = npb_bt_gemv(m, sinv[k], m, src, 1.0, 0.0, nullptr, z + r0, trans, scratch, st);
     }
-    for (int k = K - 2; k >= 0 && !rc; --k) {
+    return rc;
+}
+
+int bt_chain_bwd(int k0, int k1, int dir, const int64_t* off, const double* const* sinv,
+                 const int32_t* ip, const int32_t* ix, const double* dat, double* z, double* c,
+                 double* scratch, int trans, cudaStream_t st) {
+    // k = k0, k0 + dir, ... (k1 exclusive), away from the middle: z_k -= S_k^-1 (block towards
+    // the middle) z_{k - dir}
+    int rc = NPB_OK;
+    for (int k = k0; k != k1 && !rc; k += dir) {
         const int64_t r0 = off[k], r1 = off[k + 1], m = r1 - r0;
-        rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, r1, off[k + 2], z + r1, 1.0, 0.0, nullptr, c, st);
+        const int p = k - dir;
+        rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, off[p], off[p + 1], z + off[p], 1.0, 0.0, nullptr, c, st);
         if (!rc) rc = npb_bt_gemv(m, sinv[k], m, c, -1.0, 1.0, z + r0, z + r0, trans, scratch, st);
     }
+    return rc;
+}
+
+struct bt_fork { cudaStream_t st2; cudaEvent_t e_fork, e_join; };
+bt_fork g_bt_fork = {};
+
+int bt_sweeps(int K, int M, const int64_t* off, const double* const* sinv, const int32_t* ip,
+              const int32_t* ix, const double* dat, const double* bp, double* z, double* c,
+              double* c2, double* scratch, double* scratch2, int trans, cudaStream_t st,
+              const bt_fork* fk) {
+    int rc = NPB_OK;
+    const bool two = fk && M < K - 1;
+    cudaStream_t sb = two ? fk->st2 : st;
+    // forward: chain A = levels 0 .. M-1 downwards, chain B = levels K-1 .. M+1 upwards
+    if (two) { NPB_CUDA(cudaEventRecord(fk->e_fork, st)); NPB_CUDA(cudaStreamWaitEvent(sb, fk->e_fork, 0)); }
+    rc = bt_chain_fwd(0, M, +1, off, sinv, ip, ix, dat, bp, z, c, scratch, trans, st);
+    if (!rc) rc = bt_chain_fwd(K - 1, M, -1, off, sinv, ip, ix, dat, bp, z, two ? c2 : c, two ? scratch2 : scratch, trans, sb);
+    if (two) { NPB_CUDA(cudaEventRecord(fk->e_join, sb)); NPB_CUDA(cudaStreamWaitEvent(st, fk->e_join, 0)); }
+    if (rc) return rc;
+    {   // middle level: c = b_M - (lower) z_{M-1} - (upper) z_{M+1};  z_M = S_M^-1 c
+        const int64_t r0 = off[M], r1 = off[M + 1], m = r1 - r0;
+        const double* src = bp + r0;
+        if (M > 0) {
+            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, off[M - 1], r0, z + off[M - 1], -1.0, 1.0, src, c, st);
+            src = c;
+        }
+        if (!rc && M < K - 1) {
+            rc = npb_bt_window_spmv(ip, ix, dat, r0, r1, r1, off[M + 2], z + r1, -1.0, 1.0, src, c, st);
+            src = c;
+        }
+        if (!rc) rc = npb_bt_gemv(m, sinv[M], m, src, 1.0, 0.0, nullptr, z + r0, trans, scratch, st);
+        if (rc) return rc;
+    }
+    // backward, away from the middle
+    if (two) { NPB_CUDA(cudaEventRecord(fk->e_fork, st)); NPB_CUDA(cudaStreamWaitEvent(sb, fk->e_fork, 0)); }
+    rc = bt_chain_bwd(M - 1, -1, -1, off, sinv, ip, ix, dat, z, c, scratch, trans, st);
+    if (!rc) rc = bt_chain_bwd(M + 1, K, +1, off, sinv, ip, ix, dat, z, two ? c2 : c, two ? scratch2 : scratch, trans, sb);
+    if (two) { NPB_CUDA(cudaEventRecord(fk->e_join, sb)); NPB_CUDA(cudaStreamWaitEvent(st, fk->e_join, 0)); }
     return rc;
 }
 }  // namespace
@@ -328,22 +382,34 @@ int npb_bt_graph_release(int graph_id) {
 }
 
 // off: [host] K + 1 level offsets; sinv: [host] K device pointers (row-major m_k x m_k);
-// (indptr, indices, data): the level-ordered matrix (its transpose when trans)
-int npb_bt_solve(int K, const int64_t* off, const double* const* sinv, const int32_t* indptr,
+// (indptr, indices, data): the level-ordered matrix (its transpose when trans); M: the level
+// the two chains of the factorisation meet at (K - 1: one chain); c, scratch: 2 x the longest
+// level / 2 x npb_bt_gemv_scratch_doubles(longest level) doubles (one half per chain)
+int npb_bt_solve(int K, int M, const int64_t* off, const double* const* sinv, const int32_t* indptr,
                  const int32_t* indices, const double* data, const double* bp, double* z,
-                 double* c, double* scratch, int trans, int graph_id, void* stream) {
+                 double* c, double* scratch, int64_t mmax, int trans, int graph_id, void* stream) {
     cudaStream_t st = ST(stream);
     if (K <= 0) return NPB_OK;
+    if (M < 0 || M >= K) return NPB_ERR_ARG;
+    double* c2 = c + mmax;
+    double* scratch2 = scratch + npb_bt_gemv_scratch_doubles(mmax);
     bt_graph* g = graph_id > 0 ? &g_bt_graphs[(long long)graph_id * 2 + (trans ? 1 : 0)] : nullptr;
     if (g && !g->failed && !g->exec && g->calls >= 1) {
-        if (!g_bt_capture) NPB_CUDA(cudaStreamCreateWithFlags(&g_bt_capture, cudaStreamNonBlocking));
+        if (!g_bt_capture) {
+            NPB_CUDA(cudaStreamCreateWithFlags(&g_bt_capture, cudaStreamNonBlocking));
+            NPB_CUDA(cudaStreamCreateWithFlags(&g_bt_fork.st2, cudaStreamNonBlocking));
+            NPB_CUDA(cudaEventCreateWithFlags(&g_bt_fork.e_fork, cudaEventDisableTiming));
+            NPB_CUDA(cudaEventCreateWithFlags(&g_bt_fork.e_join, cudaEventDisableTiming));
+        }
         const unsigned long long l0 = npb_launch_counter;
         const double b0 = npb_bytes_counter;
         cudaGraph_t graph = nullptr;
         bool ok = cudaStreamBeginCapture(g_bt_capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         int rc = NPB_OK;
         if (ok) {
-            rc = bt_sweeps(K, off, sinv, indptr, indices, data, bp, z, c, scratch, trans, g_bt_capture);
+            // the second stream joins the capture through the fork event: two graph branches
+            rc = bt_sweeps(K, M, off, sinv, indptr, indices, data, bp, z, c, c2, scratch, scratch2, trans,
+                           g_bt_capture, &g_bt_fork);
             ok = (cudaStreamEndCapture(g_bt_capture, &graph) == cudaSuccess) && rc == NPB_OK && graph;
         }
         if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
@@ -364,7 +430,7 @@ int npb_bt_solve(int K, const int64_t* off, const double* const* sinv, const int
         npb_bytes_counter += g->bytes;
         return NPB_OK;
     }
-    return bt_sweeps(K, off, sinv, indptr, indices, data, bp, z, c, scratch, trans, st);
+    return bt_sweeps(K, M, off, sinv, indptr, indices, data, bp, z, c, c2, scratch, scratch2, trans, st, nullptr);
 }
 
 }  // extern "C"

@@ -93,9 +93,15 @@ def test_btlu_on_convection_dominated_march_systems(npd):
     from numpad_b200.blocktri import BlockTriLU
     systems = _march_systems(48, 2)
     assert len(systems) >= 6
-    for J, rhs, du in systems[1::2]:
+    import os
+    for k, (J, rhs, du) in enumerate(systems[1::2]):
         A = _dev_csr(J)
-        M = BlockTriLU(A)
+        os.environ['NPB_BT_TWISTED'] = '0' if k == 0 else '1'     # one-chain and twisted forms
+        try:
+            M = BlockTriLU(A)
+        finally:
+            os.environ.pop('NPB_BT_TWISTED', None)
+        assert (M.M == M.K - 1) == (k == 0)
         b = torch.from_numpy(rhs).cuda()
         x = M.solve(b)
         x = x + M.solve(b - A.matvec(x))          # one refinement step
