@@ -268,6 +268,15 @@ int npb_bfs_levels_host(int64_t n, const int32_t* indptr /*[host]*/, const int32
                         const int32_t* indptr_t /*[host] pattern of A^T, may be NULL*/,
                         const int32_t* indices_t /*[host]*/, int32_t* level /*[host] out*/,
                         int32_t* nlevels /*[host] out*/);
+/* two BFS balls (around a pseudo-peripheral node and around the node farthest from it) and one
+ * middle level between them: level order for the twisted factorisation (elimination from both
+ * ends); has_diag [host, may be NULL]: 1 where the diagonal entry is non-zero (seeds are moved
+ * onto such nodes); NPB_ERR_ARG for disconnected / tiny graphs */
+int npb_bfs_levels_two_sided_host(int64_t n, const int32_t* indptr /*[host]*/,
+                                  const int32_t* indices /*[host]*/, const int32_t* indptr_t /*[host]*/,
+                                  const int32_t* indices_t /*[host]*/,
+                                  const unsigned char* has_diag /*[host]*/, int32_t* level /*[host] out*/,
+                                  int32_t* nlevels /*[host] out*/, int32_t* middle /*[host] out*/);
 int npb_bt_window_to_dense(const int32_t* indptr, const int32_t* indices, const double* data,
                            int64_t r0, int64_t r1, int64_t c0, int64_t c1, double alpha,
                            double* out, int64_t ld, void* stream);

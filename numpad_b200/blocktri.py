@@ -23,6 +23,7 @@ Memory is the limit: 51 GB for the 1024^2 cavity (n = 3.1 M), O(N^3) on an N x N
 `feasible()` checks it against the free HBM before anything is allocated.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -33,6 +34,8 @@ from ._dev import device, stream_ptr, _call
 _level_cache = {}
 # fraction of the free HBM the stored inverses may take
 MEMORY_FRACTION = 0.8
+# twisted factorisation (two elimination chains on two streams); NPB_BT_TWISTED=0: one chain
+TWISTED = os.environ.get('NPB_BT_TWISTED', '1') != '0'
 
 
 def _pattern_key(A):
@@ -42,10 +45,15 @@ def _pattern_key(A):
             int(A.indptr.to(torch.int64).sum().item()))
 
 
-def level_structure(A):
-    """-> (perm, inv, offsets): perm[new] = old index (device int64), offsets (python list,
-    len = levels + 1).  Cached on the sparsity pattern."""
-    key = _pattern_key(A)
+def level_structure(A, two_sided=True):
+    """-> (perm, inv, offsets, middle): perm[new] = old index (device int64), offsets (python
+    list, len = levels + 1), middle = the level at which the two elimination chains of the
+    twisted factorisation meet (levels - 1: one chain).  two_sided: BFS balls around a
+    pseudo-peripheral node and around the node farthest from it with one middle level between
+    them (npb_bfs_levels_two_sided_host) -- both chains then eliminate growing BFS balls;
+    otherwise (or for disconnected graphs) plain BFS levels from one node.  Cached on the
+    sparsity pattern."""
+    key = _pattern_key(A) + (bool(two_sided),)
     hit = _level_cache.get(key)
     if hit is not None and torch.equal(hit[0], A.indptr) and torch.equal(hit[1], A.indices):
         return hit[2]
@@ -56,18 +64,28 @@ def level_structure(A):
     ptr_t = np.ascontiguousarray(At.indptr.cpu().numpy())
     idx_t = np.ascontiguousarray(At.indices.cpu().numpy())
     level = np.empty(n, np.int32)
-    nlev = ctypes.c_int32(0)
-    rc = _lib.lib().cdll.npb_bfs_levels_host(n, ptr.ctypes.data, idx.ctypes.data, ptr_t.ctypes.data,
-                                             idx_t.ctypes.data, level.ctypes.data, ctypes.byref(nlev))
+    nlev, mid = ctypes.c_int32(0), ctypes.c_int32(-1)
+    L = _lib.lib().cdll
+    rc = -1
+    if two_sided:
+        from . import amg
+        has_diag = np.ascontiguousarray((amg.diagonal(A) != 0).to(torch.uint8).cpu().numpy())
+        rc = L.npb_bfs_levels_two_sided_host(n, ptr.ctypes.data, idx.ctypes.data, ptr_t.ctypes.data,
+                                             idx_t.ctypes.data, has_diag.ctypes.data, level.ctypes.data,
+                                             ctypes.byref(nlev), ctypes.byref(mid))
     if rc != 0:
-        raise RuntimeError('npb_bfs_levels_host failed')
+        rc = L.npb_bfs_levels_host(n, ptr.ctypes.data, idx.ctypes.data, ptr_t.ctypes.data,
+                                   idx_t.ctypes.data, level.ctypes.data, ctypes.byref(nlev))
+        if rc != 0:
+            raise RuntimeError('npb_bfs_levels_host failed')
+        mid = ctypes.c_int32(nlev.value - 1)
     counts = np.bincount(level, minlength=nlev.value)
     offsets = [0] + [int(v) for v in np.cumsum(counts)]
     lev_d = torch.from_numpy(level).to(device())
     perm = torch.sort(lev_d.to(torch.int64), stable=True)[1]
     inv = torch.empty_like(perm)
     inv[perm] = torch.arange(n, dtype=torch.int64, device=device())
-    out = (perm, inv, offsets)
+    out = (perm, inv, offsets, int(mid.value))
     if len(_level_cache) > 4:
         _level_cache.clear()
     _level_cache[key] = (A.indptr.clone(), A.indices.clone(), out)
@@ -83,7 +101,7 @@ def feasible(A, budget_bytes=None):
     """can the dense inverses of the diagonal blocks be held in HBM?"""
     if A.shape[0] != A.shape[1] or A.nnz == 0:
         return False
-    _, _, offsets = level_structure(A)
+    _, _, offsets, _ = level_structure(A, TWISTED)
     if max(np.diff(offsets)) > 60000:
         return False
     if budget_bytes is None:
@@ -97,11 +115,21 @@ def feasible(A, budget_bytes=None):
 class BlockTriLU:
     """P A P^T = block tridiagonal; dense inverses of the Schur complements on the device."""
 
-    def __init__(self, A):
+    def __init__(self, A, twisted=None):
         from .shard import permuted
         A = A.materialized()
         self.n = n = A.shape[0]
-        self.perm, self.inv, self.off = level_structure(A)
+        twisted = TWISTED if twisted is None else bool(twisted)
+        try:
+            self._factor(A, twisted, permuted)
+        except np.linalg.LinAlgError:
+            if not twisted:
+                raise
+            self._factor(A, False, permuted)         # a singular block of the second chain
+
+    def _factor(self, A, twisted, permuted):
+        n = self.n
+        self.perm, self.inv, self.off, M = level_structure(A, twisted)
         off = self.off
         K = self.K = len(off) - 1
         self.Ap = permuted(A, self.perm.to(torch.int32), self.inv.to(torch.int32)).materialized()
@@ -111,19 +139,9 @@ class BlockTriLU:
         mmax = max(off[k + 1] - off[k] for k in range(K))
         self.mmax = mmax
         # ---- twisted factorisation: two elimination chains, from level 0 downwards and from
-        # level K-1 upwards, meet at level M (chosen so that both eliminate as many unknowns:
-        # the dense inversions are latency-bound, ~5 us per column, not flop-bound).  The chains
-        # are independent until M, so they are issued alternately on two streams and overlap.
-        import os
-        twisted = K >= 8 and os.environ.get('NPB_BT_TWISTED', '1') != '0'
-        M = K - 1
-        if twisted:
-            half, acc = n / 2.0, 0
-            for k in range(K):
-                acc += off[k + 1] - off[k]
-                if acc >= half:
-                    M = min(max(k, 1), K - 2)
-                    break
+        # level K-1 upwards, meet at level M (level_structure balances the unknowns they
+        # eliminate: the dense inversions are latency-bound, ~5 us per column, not flop-bound).
+        # The chains are independent until M, so they are issued alternately on two streams.
         self.M = M
         Sinv = [None] * K
         infos = []

@@ -215,6 +215,88 @@ int npb_bfs_levels_host(int64_t n, const int32_t* ptr, const int32_t* idx, const
     return NPB_OK;
 }
 
+// Two-sided level structure for the twisted factorisation: BFS balls around a pseudo-peripheral
+// node A (levels 0 .. TA-1) and around the node B farthest from it (levels K-1 down to TA+1),
+// and ONE middle level TA holding everything in neither ball.  With TA + TB <= dist(A, B) the two
+// balls are disjoint and not adjacent, so the matrix is block tridiagonal in this order too, and
+// both elimination chains run over growing BFS balls -- whose leading blocks are non-singular
+// for saddle points as long as the seed has a non-zero diagonal (has_diag, may be NULL): a seed
+// without one is replaced by a neighbour that has.  Connected graphs only (returns
+// NPB_ERR_ARG otherwise: the caller uses the one-sided levels).  All arrays on the HOST.
+int npb_bfs_levels_two_sided_host(int64_t n, const int32_t* ptr, const int32_t* idx,
+                                  const int32_t* ptr_t, const int32_t* idx_t,
+                                  const unsigned char* has_diag, int32_t* level,
+                                  int32_t* nlevels, int32_t* middle) {
+    if (n <= 0) return NPB_ERR_ARG;
+    std::vector<int32_t> dist((size_t)n), frontier, next;
+    auto bfs = [&](int32_t root, std::vector<int32_t>& d, int64_t& visited) -> int32_t {
+        std::fill(d.begin(), d.end(), -1);
+        frontier.assign(1, root);
+        d[root] = 0;
+        visited = 1;
+        int32_t last = root, lev = 0;
+        while (!frontier.empty()) {
+            next.clear();
+            for (int32_t v : frontier)
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int32_t* p = pass ? ptr_t : ptr;
+                    const int32_t* ix = pass ? idx_t : idx;
+                    if (!p) continue;
+                    for (int32_t k = p[v]; k < p[v + 1]; ++k) {
+                        const int32_t w = ix[k];
+                        if (d[w] < 0) { d[w] = lev + 1; next.push_back(w); ++visited; }
+                    }
+                }
+            if (!next.empty()) { ++lev; last = next.back(); }
+            frontier.swap(next);
+        }
+        return last;
+    };
+    auto with_diag = [&](int32_t v) -> int32_t {
+        if (!has_diag || has_diag[v]) return v;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int32_t* p = pass ? ptr_t : ptr;
+            const int32_t* ix = pass ? idx_t : idx;
+            if (!p) continue;
+            for (int32_t k = p[v]; k < p[v + 1]; ++k)
+                if (has_diag[ix[k]]) return ix[k];
+        }
+        return v;
+    };
+    int64_t vis = 0;
+    int32_t a = bfs(0, dist, vis);
+    if (vis != n) return NPB_ERR_ARG;                 // not connected
+    a = bfs(a, dist, vis);                            // two exploratory sweeps
+    a = with_diag(a);
+    std::vector<int32_t> da((size_t)n), db((size_t)n);
+    int32_t b = with_diag(bfs(a, da, vis));
+    bfs(b, db, vis);
+    const int32_t D = da[b];
+    if (D < 4) return NPB_ERR_ARG;
+    // ball sizes by radius
+    std::vector<int64_t> ca((size_t)D + 2, 0), cb((size_t)D + 2, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (da[i] <= D) ++ca[da[i] + 1];
+        if (db[i] <= D) ++cb[db[i] + 1];
+    }
+    for (int32_t r = 1; r <= D + 1; ++r) { ca[r] += ca[r - 1]; cb[r] += cb[r - 1]; }   // c[r] = #{d < r}
+    int32_t TA = 1;
+    int64_t best = -1;
+    for (int32_t t = 1; t <= D - 1; ++t) {            // TB = D - t >= 1
+        const int64_t diff = ca[t] > cb[D - t] ? ca[t] - cb[D - t] : cb[D - t] - ca[t];
+        if (best < 0 || diff < best) { best = diff; TA = t; }
+    }
+    const int32_t TB = D - TA;
+    for (int64_t i = 0; i < n; ++i) {
+        if (da[i] < TA) level[i] = da[i];
+        else if (db[i] < TB) level[i] = TA + 1 + (TB - 1 - db[i]);
+        else level[i] = TA;
+    }
+    *nlevels = TA + TB + 1;
+    *middle = TA;
+    return NPB_OK;
+}
+
 int npb_bt_window_to_dense(const int32_t* indptr, const int32_t* indices, const double* data,
                            int64_t r0, int64_t r1, int64_t c0, int64_t c1, double alpha,
                            double* out, int64_t ld, void* stream) {

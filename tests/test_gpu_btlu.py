@@ -93,14 +93,9 @@ def test_btlu_on_convection_dominated_march_systems(npd):
     from numpad_b200.blocktri import BlockTriLU
     systems = _march_systems(48, 2)
     assert len(systems) >= 6
-    import os
     for k, (J, rhs, du) in enumerate(systems[1::2]):
         A = _dev_csr(J)
-        os.environ['NPB_BT_TWISTED'] = '0' if k == 0 else '1'     # one-chain and twisted forms
-        try:
-            M = BlockTriLU(A)
-        finally:
-            os.environ.pop('NPB_BT_TWISTED', None)
+        M = BlockTriLU(A, twisted=(k != 0))                       # one-chain and twisted forms
         assert (M.M == M.K - 1) == (k == 0)
         b = torch.from_numpy(rhs).cuda()
         x = M.solve(b)
