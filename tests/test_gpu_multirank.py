@@ -35,6 +35,10 @@ def _torchrun(script, n, *args, timeout=900):
                           '--master-port', str(port), os.path.join(ROOT, 'tools', script), *args],
                          capture_output=True, text=True, timeout=timeout, cwd=ROOT)
     log = out.stdout + '\n' + out.stderr[-3000:]
+    logdir = os.environ.get('NPB_TEST_LOG_DIR')           # evidence for profiles/
+    if logdir:
+        with open(os.path.join(logdir, 'multirank_%s_%dgpu.txt' % (script.replace('.py', ''), n)), 'w') as f:
+            f.write(' '.join([script, *args]) + '\n' + out.stdout)
     assert out.returncode == 0, log
     return out.stdout
 
