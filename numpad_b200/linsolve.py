@@ -27,6 +27,10 @@ DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=100, maxiter=600, precond='auto',
                 # with the same replicated A and b and gets the same x back.
                 shard_owner=None)
 
+# solve_multi: from this many right-hand sides on, the block-tridiagonal direct solver is
+# preferred over per-column Krylov solves
+MULTI_RHS_DIRECT = 8
+
 last_info = {}      # filled by every solve: iterations, residuals, method
 # 'robust': the multigrid-preconditioned solve failed on a matrix of signature 'sig' = (n, nnz):
 # later systems of the same signature (the next Newton iterations and time steps of the same
@@ -371,6 +375,13 @@ def solve_multi(A, B, transpose=False, **opts):
     -- is built ONCE for the first right-hand side and reused for the others."""
     keep = {}
     X = torch.empty_like(B)
+    if B.shape[0] >= MULTI_RHS_DIRECT and opts.get('precond', DEFAULTS['precond']) == 'auto':
+        # many right-hand sides: one factorisation + one pair of sweeps per column beats one
+        # preconditioned Krylov solve per column (when the dense blocks fit)
+        from . import blocktri, precond as _pc
+        Am = A.materialized()
+        if not _pc.direct_feasible(Am) and blocktri.feasible(Am):
+            opts = dict(opts, precond='btlu')
     for k in range(B.shape[0]):
         X[k] = solve(A, B[k], transpose=transpose, **dict(opts, _keep=keep))
     return X
