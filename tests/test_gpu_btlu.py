@@ -143,7 +143,7 @@ def test_kec_newton_step_vs_spsolve(npd, viscous):
     from oracle import numpad_oracle as orc
     from numpad_b200 import linsolve, precond
     from numpad_b200.workloads.kec import KecProblem
-    Ni = Nj = 48
+    Ni = Nj = 64
     Pg, Po = KecProblem(npd, Ni, Nj, viscous=viscous), KecProblem(orc, Ni, Nj, viscous=viscous)
     dt = 1.0 / Nj if viscous else 0.1
     w0 = Pg.fixed_state()
