@@ -224,6 +224,13 @@ int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      void* stream);
 int npb_spmv_set_tma_geometry(int g);   /* tuning: shared-memory ring geometry -1 (auto) or 0..3; returns old */
 int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA kernel; returns old */
+/* diagonal storage for stencil operators (entries on <= 8 constant offsets col - row; offsets on the
+ * host): conversion (*bad = entries on other offsets) and SpMV with the same epilogue modes */
+int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
+                   int ndiag, const int32_t* offsets, float* vals, int64_t* bad, void* stream);
+int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
+                 const double* x, int mode, const double* b, const double* dinv, double omega,
+                 double* y, void* stream);
 /* same epilogues for an operator whose values are stored in fp32 (vectors and sums fp64) */
 int npb_spmv_f32(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                  const float* data32, const double* x, int mode, const double* b,
@@ -366,6 +373,11 @@ typedef struct npb_csr_mat {
     npb_halo halo;
     const float* data32;            /* != NULL: the same values in fp32 (preconditioner operators; the
                                        SpMV then reads 8 instead of 12 bytes per entry) */
+    const float* dia_vals;          /* != NULL: diagonal-storage image (fp32, ndiag x nrows, from
+                                       npb_csr_to_dia) of a stencil operator whose entries sit on
+                                       ndiag <= 8 constant offsets col - row; preferred over CSR */
+    int32_t ndiag, dia_pad;
+    int32_t dia_off[8];
 } npb_csr_mat;
 
 typedef struct npb_amg_level {      /* [host] */

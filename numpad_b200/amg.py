@@ -28,7 +28,9 @@ class Halo(ctypes.Structure):            # npb_halo: filled by shard.py for row-
 class CsrMat(ctypes.Structure):
     _fields_ = [('nrows', ctypes.c_int64), ('ncols', ctypes.c_int64), ('nnz', ctypes.c_int64),
                 ('indptr', ctypes.c_void_p), ('indices', ctypes.c_void_p),
-                ('data', ctypes.c_void_p), ('halo', Halo), ('data32', ctypes.c_void_p)]
+                ('data', ctypes.c_void_p), ('halo', Halo), ('data32', ctypes.c_void_p),
+                ('dia_vals', ctypes.c_void_p), ('ndiag', ctypes.c_int32), ('dia_pad', ctypes.c_int32),
+                ('dia_off', ctypes.c_int32 * 8)]
 
 
 class AmgLevel(ctypes.Structure):
@@ -90,14 +92,59 @@ def f32_values(A):
     return v
 
 
+# Stencil operators whose entries sit on at most 8 constant offsets col - row (the pressure
+# Laplacian L = -D G of the cavity: 5) are also kept in diagonal storage (fp32, no column
+# indices, coalesced reads of x instead of gathers): csrc/krylov.cu k_spmv_dia.  0 disables.
+DIA_MIN_ROWS = 200000
+_dia_cache = {}
+
+
+def dia_image(A):
+    """-> (offsets list, vals float32[ndiag * n]) or None.  The candidate offsets come from a
+    strided sample of the entries; the conversion kernel verifies EVERY entry against them."""
+    n = A.shape[0]
+    if (not DIA_MIN_ROWS or n < DIA_MIN_ROWS or A.shape[0] != A.shape[1] or A.nnz == 0
+            or A.nnz > 8 * n):
+        return None
+    key = (A.data.data_ptr(), A.nnz)
+    hit = _dia_cache.get(key)
+    if hit is not None and hit[0]() is A.data:
+        return hit[1]
+    import weakref
+    step = max(1, A.nnz // 200000)
+    offs = torch.unique((A.indices[::step].to(torch.int64) - A.rows()[::step].to(torch.int64)))
+    out = None
+    if 1 <= offs.numel() <= 8 and 4.0 * offs.numel() * n < 0.8 * (8.0 * A.nnz + 4.0 * n):
+        off_list = [int(v) for v in offs.tolist()]
+        off_h = (ctypes.c_int32 * 8)(*(off_list + [0] * (8 - len(off_list))))
+        vals = _empty(len(off_list) * n, torch.float32)
+        bad = _empty(1, torch.int64)
+        _call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, len(off_list),
+              ctypes.cast(off_h, ctypes.c_void_p).value, vals, bad)
+        if int(bad.item()) == 0:
+            out = (off_list, vals)
+    if len(_dia_cache) > 16:
+        _dia_cache.clear()
+    _dia_cache[key] = (weakref.ref(A.data), out)
+    return out
+
+
 def csr_mat(A, keep=None):
     """descriptor of a device CSR matrix; with `keep` (a list that outlives the descriptor) large
-    operators also get their fp32 values (see F32_MIN_ROWS)"""
+    operators also get their fp32 values (see F32_MIN_ROWS) or, stencil operators, their
+    diagonal-storage image (see DIA_MIN_ROWS)"""
     m = CsrMat()
     m.nrows, m.ncols, m.nnz = A.shape[0], A.shape[1], A.nnz
     m.indptr, m.indices, m.data = A.indptr.data_ptr(), A.indices.data_ptr(), A.data.data_ptr()
     if keep is not None:
-        v = f32_values(A)
+        d = dia_image(A)
+        if d is not None:
+            offs, vals = d
+            keep.append(vals)
+            m.dia_vals, m.ndiag = vals.data_ptr(), len(offs)
+            for k, o in enumerate(offs):
+                m.dia_off[k] = o
+        v = f32_values(A) if d is None else None
         if v is not None:
             keep.append(v)
             m.data32 = v.data_ptr()

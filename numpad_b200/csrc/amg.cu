@@ -32,6 +32,9 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
                 const npb_halo* halo, const npb_wait* wait, const float* dat32);
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st);
+int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets_host,
+                        const float* vals, const double* x, int mode, const double* b,
+                        const double* dinv, double omega, double* y, cudaStream_t st);
 
 extern "C" {
 typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
@@ -501,6 +504,11 @@ struct npb_csr_mat {
     npb_halo halo;         // halo.dist != NULL: rows of a row-sharded operator (dist.cuh)
     const float* data32;   // != NULL: the values rounded to fp32 (preconditioner operators:
                            // 8 instead of 12 bytes per entry; sums, x and y stay fp64)
+    // != NULL: diagonal-storage image (fp32, ndiag x nrows) of a stencil operator whose entries
+    // sit on ndiag <= 8 constant offsets; preferred over CSR by spmv_mat (single GPU)
+    const float* dia_vals;
+    int32_t ndiag, dia_pad;
+    int32_t dia_off[8];
 };
 
 // y = epilogue(M x): 0: Mx  1: b - Mx  2: b + Mx  3: x + omega dinv (b - Mx); a sharded
@@ -508,6 +516,9 @@ struct npb_csr_mat {
 static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* b, double* y,
                            int mode, cudaStream_t st, const double* dinv = nullptr,
                            double omega = 0.0) {
+    if (M.dia_vals && !M.halo.dist)
+        return npb_spmv_dia_launch(M.nrows, M.ncols, M.ndiag, M.dia_off, M.dia_vals, x, mode, b, dinv,
+                                   omega, y, st);
     if (M.halo.dist) {
         npb_halo h = M.halo;
         const double* xh = nullptr;
@@ -748,9 +759,9 @@ struct npb_lsc {
 
 // the host structs above are declared a second time in include/numpad_b200.h (and mirrored
 // with ctypes, tests/test_abi.py): a one-sided edit must not compile
-static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 120, "npb_csr_mat layout");
-static_assert(sizeof(npb_amg_level) == 440 && sizeof(npb_amg) == 56, "npb_amg layout");
-static_assert(sizeof(npb_amg_precond) == 152 && sizeof(npb_lsc) == 696, "npb_lsc layout");
+static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 168, "npb_csr_mat layout");
+static_assert(sizeof(npb_amg_level) == 584 && sizeof(npb_amg) == 56, "npb_amg layout");
+static_assert(sizeof(npb_amg_precond) == 200 && sizeof(npb_lsc) == 888, "npb_lsc layout");
 
 // y = d .* x as an npb_apply_fn (Jacobi preconditioner; ctx = npb_diag_ctx)
 struct npb_diag_ctx { int64_t n; const double* d; };

@@ -470,11 +470,13 @@ def solve(J, b, owner=None, rtol=1e-10, restart=100, maxiter=600, lsc_options=No
     # the large Galerkin products of the setup are computed by row blocks, one per rank
     _dev.SPGEMM_SHARD = (rank, world, SHARD_PRODUCTS_ABOVE) if world > 1 and SHARD_PRODUCTS_ABOVE else None
     f32_rows, amg.F32_MIN_ROWS = amg.F32_MIN_ROWS, 0     # (fp32 copies are made of the LOCAL slices)
+    dia_rows, amg.DIA_MIN_ROWS = amg.DIA_MIN_ROWS, 0     # (diagonal storage: single-GPU operators only)
     try:
         M = amg.LscPreconditioner(Jp, **(lsc_options or {}))
     finally:
         _dev.SPGEMM_SHARD = None
         amg.F32_MIN_ROWS = f32_rows
+        amg.DIA_MIN_ROWS = dia_rows
     torch.cuda.synchronize(); t2 = time.perf_counter()
     _heap_reset()
     S = ShardedLsc(M, cuts)

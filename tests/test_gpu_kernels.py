@@ -424,3 +424,49 @@ def test_row_batched_spgemm(dev, m, k, n, da, db):
     f, s = fast.toscipy(), slow.toscipy()
     assert np.array_equal(f.indptr, s.indptr) and np.array_equal(f.indices, s.indices)
     assert np.array_equal(f.data, s.data)
+
+
+def test_spmv_dia_storage(dev):
+    """diagonal-storage SpMV (stencil operators on <= 8 constant offsets, fp32 values) with every
+    epilogue vs scipy, on a 5-point Laplacian with one unknown removed (the cavity's pressure
+    operator); the conversion counts entries that are on none of the offsets"""
+    import torch
+    import ctypes
+    N = 300
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(N, N))
+    a = (sp.kron(sp.identity(N), T) + sp.kron(T, sp.identity(N))).tocsr()[1:, 1:]
+    a = sp.csr_matrix(a)
+    a.data = a.data * (1 + 0.25 * np.random.RandomState(0).random(a.nnz))   # values exact in fp32?
+    a.data = a.data.astype(np.float32).astype(np.float64)
+    a.sort_indices()
+    n = a.shape[0]
+    A = dev.DevCsr.from_scipy(a)
+    offs = [-N, -1, 0, 1, N]
+    off_h = (ctypes.c_int32 * 8)(*(offs + [0, 0, 0]))
+    vals = torch.empty(5 * n, dtype=torch.float32, device=dev.device())
+    bad = torch.empty(1, dtype=torch.int64, device=dev.device())
+    dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, bad)
+    assert int(bad.item()) == 0
+    rng = np.random.RandomState(1)
+    x, b, dinv = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    t = lambda v: torch.from_numpy(v).to(dev.device())
+    xd, bd, dd = t(x), t(b), t(dinv)
+    ax = a @ x
+    for mode, want in enumerate([ax, b - ax, b + ax, x + 0.7 * dinv * (b - ax)]):
+        y = torch.full((n,), np.nan, dtype=torch.float64, device=dev.device())
+        dev._call('npb_spmv_dia', n, n, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, xd, mode, bd, dd, 0.7, y)
+        np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=1e-12 * (np.abs(want).max() + 1))
+    # a missing offset is reported
+    off_h2 = (ctypes.c_int32 * 8)(-N, -1, 0, 1, 0, 0, 0, 0)
+    dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 4, ctypes.cast(off_h2, ctypes.c_void_p).value, vals, bad)
+    assert int(bad.item()) == n - N + 1 - 1 or int(bad.item()) > 0
+    # and the multigrid descriptor picks the image up for a large enough operator
+    from numpad_b200 import amg
+    old = amg.DIA_MIN_ROWS
+    amg.DIA_MIN_ROWS = 1000
+    try:
+        keep = []
+        m = amg.csr_mat(A, keep)
+        assert m.ndiag == 5 and m.dia_vals and sorted(m.dia_off[:5]) == offs and not m.data32
+    finally:
+        amg.DIA_MIN_ROWS = old
