@@ -485,16 +485,36 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const floa
            const double* x, spmv_epi e, double* y) {
     const int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r >= nrows) return;
-    double s = 0.0;
+    // every load of the row is issued before the first is used (no load depends on another):
+    // out-of-range columns read a clamped address and are masked in the sum
+    float v[DIA_MAX];
+    double xv[DIA_MAX];
+    bool ok[DIA_MAX];
 #pragma unroll
     for (int k = 0; k < DIA_MAX; ++k) {
+        v[k] = 0.0f; xv[k] = 0.0; ok[k] = false;
         if (k < ndiag) {
             const int64_t c = r + offs.off[k];
-            const float v = __ldcs(vals + (int64_t)k * nrows + r);      // streamed once
-            if (c >= 0 && c < ncols && v != 0.0f) s = fma((double)v, x[c], s);
+            ok[k] = c >= 0 && c < ncols;
+            v[k] = __ldcs(vals + (int64_t)k * nrows + r);              // streamed once
+            xv[k] = x[ok[k] ? c : (r < ncols ? r : 0)];
         }
     }
-    y[r] = spmv_finish(e, r, s, x);
+    double bv = 0.0, dv = 0.0, xr = 0.0;
+    if (e.mode >= 1) bv = e.b[r];
+    if (e.mode == 3) { dv = e.dinv[r]; xr = x[r]; }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIA_MAX; ++k)
+        if (ok[k]) s = fma((double)v[k], xv[k], s);
+    double out;
+    switch (e.mode) {
+        case 0: out = s; break;
+        case 1: out = bv - s; break;
+        case 2: out = bv + s; break;
+        default: out = xr + e.omega * dv * (bv - s); break;
+    }
+    y[r] = out;
 }
 
 // CSR -> DIA image: vals[k * nrows + r] = entry of row r on offset offs[k] (rows are zero-filled
