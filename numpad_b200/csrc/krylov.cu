@@ -480,41 +480,56 @@ int grid_for(int64_t n) {
 constexpr int DIA_MAX = 8;
 struct dia_offsets { int32_t off[DIA_MAX]; };
 
+constexpr int DIA_R = 4;       // rows per thread and round: 4 x (ndiag values + ndiag x) loads in flight
+template <int ND>              // compile-time bound on ndiag (register arrays)
 __global__ void __launch_bounds__(TPB)
 k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const float* __restrict__ vals,
            const double* x, spmv_epi e, double* y) {
-    const int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (r >= nrows) return;
-    // every load of the row is issued before the first is used (no load depends on another):
-    // out-of-range columns read a clamped address and are masked in the sum
-    float v[DIA_MAX];
-    double xv[DIA_MAX];
-    bool ok[DIA_MAX];
+    // persistent grid, DIA_R rows per thread and round (a row per thread leaves the kernel bound
+    // by CTA turnover: 16 K CTAs of one short-lived warp-load each).  Every load of a round is
+    // issued before the first is used; out-of-range columns read a clamped address and are
+    // masked in the sum.
+    for (int64_t base = (int64_t)blockIdx.x * (TPB * DIA_R); base < nrows;
+         base += (int64_t)gridDim.x * (TPB * DIA_R)) {
+        float v[DIA_R][ND];
+        double xv[DIA_R][ND];
+        double bv[DIA_R], dv[DIA_R], xr[DIA_R];
 #pragma unroll
-    for (int k = 0; k < DIA_MAX; ++k) {
-        v[k] = 0.0f; xv[k] = 0.0; ok[k] = false;
-        if (k < ndiag) {
-            const int64_t c = r + offs.off[k];
-            ok[k] = c >= 0 && c < ncols;
-            v[k] = __ldcs(vals + (int64_t)k * nrows + r);              // streamed once
-            xv[k] = x[ok[k] ? c : (r < ncols ? r : 0)];
+        for (int j = 0; j < DIA_R; ++j) {
+            const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
+            const bool live = r < nrows;
+            bv[j] = dv[j] = xr[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) {
+                v[j][k] = 0.0f; xv[j][k] = 0.0;
+                if (k < ndiag && live) {
+                    const int64_t c = r + offs.off[k];
+                    const bool ok = c >= 0 && c < ncols;
+                    const float t = __ldcs(vals + (int64_t)k * nrows + r);     // streamed once
+                    v[j][k] = ok ? t : 0.0f;
+                    xv[j][k] = x[ok ? c : (r < ncols ? r : 0)];
+                }
+            }
+            if (live && e.mode >= 1) bv[j] = e.b[r];
+            if (live && e.mode == 3) { dv[j] = e.dinv[r]; xr[j] = x[r]; }
+        }
+#pragma unroll
+        for (int j = 0; j < DIA_R; ++j) {
+            const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
+            if (r >= nrows) continue;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) s = fma((double)v[j][k], xv[j][k], s);
+            double out;
+            switch (e.mode) {
+                case 0: out = s; break;
+                case 1: out = bv[j] - s; break;
+                case 2: out = bv[j] + s; break;
+                default: out = xr[j] + e.omega * dv[j] * (bv[j] - s); break;
+            }
+            y[r] = out;
         }
     }
-    double bv = 0.0, dv = 0.0, xr = 0.0;
-    if (e.mode >= 1) bv = e.b[r];
-    if (e.mode == 3) { dv = e.dinv[r]; xr = x[r]; }
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < DIA_MAX; ++k)
-        if (ok[k]) s = fma((double)v[k], xv[k], s);
-    double out;
-    switch (e.mode) {
-        case 0: out = s; break;
-        case 1: out = bv - s; break;
-        case 2: out = bv + s; break;
-        default: out = xr + e.omega * dv * (bv - s); break;
-    }
-    y[r] = out;
 }
 
 // CSR -> DIA image: vals[k * nrows + r] = entry of row r on offset offs[k] (rows are zero-filled
@@ -545,7 +560,11 @@ int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, const int32_t* 
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets_host[k] : 0;
     spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
-    k_spmv_dia<<<npb_blocks(nrows, TPB), TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
+    int64_t grid = (nrows + TPB * DIA_R - 1) / (TPB * DIA_R);
+    if (grid > (int64_t)NPB_NUM_SMS * 8) grid = (int64_t)NPB_NUM_SMS * 8;
+    if (ndiag <= 3) k_spmv_dia<3><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
+    else if (ndiag <= 5) k_spmv_dia<5><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
+    else k_spmv_dia<8><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
     NPB_COUNT_LAUNCH();
     NPB_COUNT_BYTES(4.0 * ndiag * nrows + 8.0 * nrows * (2 + (mode >= 1) + 2 * (mode == 3)));
     NPB_CHECK_LAUNCH("spmv_dia");
