@@ -228,6 +228,7 @@ int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA 
  * host): conversion (*bad = entries on other offsets) and SpMV with the same epilogue modes */
 int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
                    int ndiag, const int32_t* offsets, float* vals, int64_t* bad, void* stream);
+int npb_spmv_dia_set_rows(int rows_per_thread);      /* tuning switch (1 or 2), returns the old value */
 int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
                  const double* x, int mode, const double* b, const double* dinv, double omega,
                  double* y, void* stream);

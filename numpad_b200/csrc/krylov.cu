@@ -480,22 +480,20 @@ int grid_for(int64_t n) {
 constexpr int DIA_MAX = 8;
 struct dia_offsets { int32_t off[DIA_MAX]; };
 
-constexpr int DIA_R = 4;       // rows per thread and round: 4 x (ndiag values + ndiag x) loads in flight
-template <int ND>              // compile-time bound on ndiag (register arrays)
+// ND: compile-time bound on ndiag (register arrays); R rows per thread, grid-stride over rounds.
+// Every load of a round is issued before the first is used; out-of-range columns read a clamped
+// address and are masked in the sum.
+template <int ND, int R>
 __global__ void __launch_bounds__(TPB)
 k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const float* __restrict__ vals,
-           const double* x, spmv_epi e, double* y) {
-    // persistent grid, DIA_R rows per thread and round (a row per thread leaves the kernel bound
-    // by CTA turnover: 16 K CTAs of one short-lived warp-load each).  Every load of a round is
-    // issued before the first is used; out-of-range columns read a clamped address and are
-    // masked in the sum.
-    for (int64_t base = (int64_t)blockIdx.x * (TPB * DIA_R); base < nrows;
-         base += (int64_t)gridDim.x * (TPB * DIA_R)) {
-        float v[DIA_R][ND];
-        double xv[DIA_R][ND];
-        double bv[DIA_R], dv[DIA_R], xr[DIA_R];
+           const double* __restrict__ x, spmv_epi e, double* __restrict__ y) {
+    for (int64_t base = (int64_t)blockIdx.x * (TPB * R); base < nrows;
+         base += (int64_t)gridDim.x * (TPB * R)) {
+        float v[R][ND];
+        double xv[R][ND];
+        double bv[R], dv[R], xr[R];
 #pragma unroll
-        for (int j = 0; j < DIA_R; ++j) {
+        for (int j = 0; j < R; ++j) {
             const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
             const bool live = r < nrows;
             bv[j] = dv[j] = xr[j] = 0.0;
@@ -505,16 +503,15 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const floa
                 if (k < ndiag && live) {
                     const int64_t c = r + offs.off[k];
                     const bool ok = c >= 0 && c < ncols;
-                    const float t = __ldcs(vals + (int64_t)k * nrows + r);     // streamed once
-                    v[j][k] = ok ? t : 0.0f;
-                    xv[j][k] = x[ok ? c : (r < ncols ? r : 0)];
+                    v[j][k] = ok ? __ldcs(vals + (int64_t)k * nrows + r) : 0.0f;    // streamed once
+                    xv[j][k] = ok ? __ldg(x + c) : 0.0;
                 }
             }
-            if (live && e.mode >= 1) bv[j] = e.b[r];
-            if (live && e.mode == 3) { dv[j] = e.dinv[r]; xr[j] = x[r]; }
+            if (live && e.mode >= 1) bv[j] = __ldg(e.b + r);
+            if (live && e.mode == 3) { dv[j] = __ldg(e.dinv + r); xr[j] = __ldg(x + r); }
         }
 #pragma unroll
-        for (int j = 0; j < DIA_R; ++j) {
+        for (int j = 0; j < R; ++j) {
             const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
             if (r >= nrows) continue;
             double s = 0.0;
@@ -531,6 +528,8 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const floa
         }
     }
 }
+
+static int npb_dia_rows = 1;       // rows per thread (tuning switch npb_spmv_dia_set_rows)
 
 // CSR -> DIA image: vals[k * nrows + r] = entry of row r on offset offs[k] (rows are zero-filled
 // by the caller); *bad counts entries on an offset that is not in the table
@@ -560,11 +559,19 @@ int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, const int32_t* 
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets_host[k] : 0;
     spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
-    int64_t grid = (nrows + TPB * DIA_R - 1) / (TPB * DIA_R);
-    if (grid > (int64_t)NPB_NUM_SMS * 8) grid = (int64_t)NPB_NUM_SMS * 8;
-    if (ndiag <= 3) k_spmv_dia<3><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
-    else if (ndiag <= 5) k_spmv_dia<5><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
-    else k_spmv_dia<8><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y);
+    // x is only read and never aliases y here (the Jacobi epilogue requires y != x): the kernel
+    // reads it through the non-coherent path
+    const int R = npb_dia_rows;
+    int64_t grid = (nrows + (int64_t)TPB * R - 1) / ((int64_t)TPB * R);
+    const int64_t cap = (int64_t)NPB_NUM_SMS * 64;
+    if (grid > cap) grid = cap;
+#define NPB_DIA_LAUNCH(ND_, R_) k_spmv_dia<ND_, R_><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y)
+    if (R == 2) {
+        if (ndiag <= 3) NPB_DIA_LAUNCH(3, 2); else if (ndiag <= 5) NPB_DIA_LAUNCH(5, 2); else NPB_DIA_LAUNCH(8, 2);
+    } else {
+        if (ndiag <= 3) NPB_DIA_LAUNCH(3, 1); else if (ndiag <= 5) NPB_DIA_LAUNCH(5, 1); else NPB_DIA_LAUNCH(8, 1);
+    }
+#undef NPB_DIA_LAUNCH
     NPB_COUNT_LAUNCH();
     NPB_COUNT_BYTES(4.0 * ndiag * nrows + 8.0 * nrows * (2 + (mode >= 1) + 2 * (mode == 3)));
     NPB_CHECK_LAUNCH("spmv_dia");
@@ -781,6 +788,13 @@ int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices,
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_to_dia");
     return NPB_OK;
+}
+
+// tuning switch: rows per thread of the DIA kernel (1 or 2); returns the old value
+int npb_spmv_dia_set_rows(int r) {
+    const int old = npb_dia_rows;
+    if (r == 1 || r == 2) npb_dia_rows = r;
+    return old;
 }
 
 // y = epilogue(A x) from the diagonal-storage image (same modes as npb_spmv_epilogue)

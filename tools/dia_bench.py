@@ -26,11 +26,15 @@ def timeit(fn, reps=200):
     e1.record(); torch.cuda.synchronize()
     return 1e3 * e0.elapsed_time(e1) / reps
 print('L: n = %d, nnz = %d, offsets %s' % (n, L.nnz, offs))
-for mode in (0, 1, 3):
-    t64 = timeit(lambda: _call('npb_spmv_epilogue', n, L.nnz, L.indptr, L.indices, L.data, x, mode, b, dinv, 0.67, y, 0))
-    t32 = timeit(lambda: _call('npb_spmv_f32', n, L.nnz, L.indptr, L.indices, v32, x, mode, b, dinv, 0.67, y))
-    td = timeit(lambda: _call('npb_spmv_dia', n, n, len(offs), ctypes.cast(off_h, ctypes.c_void_p).value, vals, x, mode, b, dinv, 0.67, y))
-    vec = 8.0 * n * (2 + (mode >= 1) + 2 * (mode == 3))
-    print('mode %d: csr64 %.1f us (%.0f GB/s)  csr32 %.1f us (%.0f GB/s)  dia32 %.1f us (%.0f GB/s)' % (
-        mode, t64, (12.0 * L.nnz + 4 * n + vec) / t64 / 1e3, t32, (8.0 * L.nnz + 4 * n + vec) / t32 / 1e3,
-        td, (4.0 * len(offs) * n + vec) / td / 1e3))
+from numpad_b200 import _lib
+for rows in (1, 2):
+  _lib.lib().cdll.npb_spmv_dia_set_rows(rows)
+  print('rows per thread', rows)
+  for mode in (0, 1, 3):
+      t64 = timeit(lambda: _call('npb_spmv_epilogue', n, L.nnz, L.indptr, L.indices, L.data, x, mode, b, dinv, 0.67, y, 0))
+      t32 = timeit(lambda: _call('npb_spmv_f32', n, L.nnz, L.indptr, L.indices, v32, x, mode, b, dinv, 0.67, y))
+      td = timeit(lambda: _call('npb_spmv_dia', n, n, len(offs), ctypes.cast(off_h, ctypes.c_void_p).value, vals, x, mode, b, dinv, 0.67, y))
+      vec = 8.0 * n * (2 + (mode >= 1) + 2 * (mode == 3))
+      print('mode %d: csr64 %.1f us (%.0f GB/s)  csr32 %.1f us (%.0f GB/s)  dia32 %.1f us (%.0f GB/s)' % (
+          mode, t64, (12.0 * L.nnz + 4 * n + vec) / t64 / 1e3, t32, (8.0 * L.nnz + 4 * n + vec) / t32 / 1e3,
+          td, (4.0 * len(offs) * n + vec) / td / 1e3))
