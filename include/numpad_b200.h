@@ -227,11 +227,12 @@ int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA 
 /* diagonal storage for stencil operators (entries on <= 8 constant offsets col - row; offsets on the
  * host): conversion (*bad = entries on other offsets) and SpMV with the same epilogue modes */
 int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
-                   int ndiag, const int32_t* offsets, float* vals, int64_t* bad, void* stream);
+                   int ndiag, const int32_t* offsets, float* vals, int64_t ld, int64_t* bad,
+                   void* stream);
 int npb_spmv_dia_set_rows(int rows_per_thread);      /* tuning switch (1 or 2), returns the old value */
 int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
-                 const double* x, int mode, const double* b, const double* dinv, double omega,
-                 double* y, void* stream);
+                 int64_t ld, const double* x, int mode, const double* b, const double* dinv,
+                 double omega, double* y, void* stream);
 /* same epilogues for an operator whose values are stored in fp32 (vectors and sums fp64) */
 int npb_spmv_f32(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                  const float* data32, const double* x, int mode, const double* b,
@@ -377,7 +378,7 @@ typedef struct npb_csr_mat {
     const float* dia_vals;          /* != NULL: diagonal-storage image (fp32, ndiag x nrows, from
                                        npb_csr_to_dia) of a stencil operator whose entries sit on
                                        ndiag <= 8 constant offsets col - row; preferred over CSR */
-    int32_t ndiag, dia_pad;
+    int32_t ndiag, dia_ld;          /* dia_ld: floats between consecutive diagonals (>= nrows) */
     int32_t dia_off[8];
 } npb_csr_mat;
 

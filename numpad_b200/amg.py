@@ -29,7 +29,7 @@ class CsrMat(ctypes.Structure):
     _fields_ = [('nrows', ctypes.c_int64), ('ncols', ctypes.c_int64), ('nnz', ctypes.c_int64),
                 ('indptr', ctypes.c_void_p), ('indices', ctypes.c_void_p),
                 ('data', ctypes.c_void_p), ('halo', Halo), ('data32', ctypes.c_void_p),
-                ('dia_vals', ctypes.c_void_p), ('ndiag', ctypes.c_int32), ('dia_pad', ctypes.c_int32),
+                ('dia_vals', ctypes.c_void_p), ('ndiag', ctypes.c_int32), ('dia_ld', ctypes.c_int32),
                 ('dia_off', ctypes.c_int32 * 8)]
 
 
@@ -100,7 +100,7 @@ _dia_cache = {}
 
 
 def dia_image(A):
-    """-> (offsets list, vals float32[ndiag * n]) or None.  The candidate offsets come from a
+    """-> (offsets list, vals float32[ndiag * ld], ld) or None.  The candidate offsets come from a
     strided sample of the entries; the conversion kernel verifies EVERY entry against them."""
     n = A.shape[0]
     if (not DIA_MIN_ROWS or n < DIA_MIN_ROWS or A.shape[0] != A.shape[1] or A.nnz == 0
@@ -117,12 +117,13 @@ def dia_image(A):
     if 1 <= offs.numel() <= 8 and 4.0 * offs.numel() * n < 0.8 * (8.0 * A.nnz + 4.0 * n):
         off_list = [int(v) for v in offs.tolist()]
         off_h = (ctypes.c_int32 * 8)(*(off_list + [0] * (8 - len(off_list))))
-        vals = _empty(len(off_list) * n, torch.float32)
+        ld = (n + 31) // 32 * 32                     # every diagonal 128-byte aligned
+        vals = _empty(len(off_list) * ld, torch.float32)
         bad = _empty(1, torch.int64)
         _call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, len(off_list),
-              ctypes.cast(off_h, ctypes.c_void_p).value, vals, bad)
+              ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, bad)
         if int(bad.item()) == 0:
-            out = (off_list, vals)
+            out = (off_list, vals, ld)
     if len(_dia_cache) > 16:
         _dia_cache.clear()
     _dia_cache[key] = (weakref.ref(A.data), out)
@@ -139,9 +140,9 @@ def csr_mat(A, keep=None):
     if keep is not None:
         d = dia_image(A)
         if d is not None:
-            offs, vals = d
+            offs, vals, ld = d
             keep.append(vals)
-            m.dia_vals, m.ndiag = vals.data_ptr(), len(offs)
+            m.dia_vals, m.ndiag, m.dia_ld = vals.data_ptr(), len(offs), ld
             for k, o in enumerate(offs):
                 m.dia_off[k] = o
         v = f32_values(A) if d is None else None

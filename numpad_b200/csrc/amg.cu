@@ -32,9 +32,10 @@ int npb_spmv_ex(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_t* i
                 const npb_halo* halo, const npb_wait* wait, const float* dat32);
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st);
-int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets_host,
-                        const float* vals, const double* x, int mode, const double* b,
-                        const double* dinv, double omega, double* y, cudaStream_t st);
+int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
+                        const int32_t* offsets_host, const float* vals, const double* x, int mode,
+                        const double* b, const double* dinv, double omega, double* y,
+                        cudaStream_t st);
 
 extern "C" {
 typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
@@ -507,7 +508,7 @@ struct npb_csr_mat {
     // != NULL: diagonal-storage image (fp32, ndiag x nrows) of a stencil operator whose entries
     // sit on ndiag <= 8 constant offsets; preferred over CSR by spmv_mat (single GPU)
     const float* dia_vals;
-    int32_t ndiag, dia_pad;
+    int32_t ndiag, dia_ld;     // dia_ld: floats between consecutive diagonals (>= nrows)
     int32_t dia_off[8];
 };
 
@@ -517,8 +518,8 @@ static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* 
                            int mode, cudaStream_t st, const double* dinv = nullptr,
                            double omega = 0.0) {
     if (M.dia_vals && !M.halo.dist)
-        return npb_spmv_dia_launch(M.nrows, M.ncols, M.ndiag, M.dia_off, M.dia_vals, x, mode, b, dinv,
-                                   omega, y, st);
+        return npb_spmv_dia_launch(M.nrows, M.ncols, M.ndiag, M.dia_ld, M.dia_off, M.dia_vals, x, mode, b,
+                                   dinv, omega, y, st);
     if (M.halo.dist) {
         npb_halo h = M.halo;
         const double* xh = nullptr;

@@ -485,8 +485,9 @@ struct dia_offsets { int32_t off[DIA_MAX]; };
 // address and are masked in the sum.
 template <int ND, int R>
 __global__ void __launch_bounds__(TPB)
-k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const float* __restrict__ vals,
-           const double* __restrict__ x, spmv_epi e, double* __restrict__ y) {
+k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs,
+           const float* __restrict__ vals, const double* __restrict__ x, spmv_epi e,
+           double* __restrict__ y) {
     for (int64_t base = (int64_t)blockIdx.x * (TPB * R); base < nrows;
          base += (int64_t)gridDim.x * (TPB * R)) {
         float v[R][ND];
@@ -503,7 +504,7 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, dia_offsets offs, const floa
                 if (k < ndiag && live) {
                     const int64_t c = r + offs.off[k];
                     const bool ok = c >= 0 && c < ncols;
-                    v[j][k] = ok ? __ldcs(vals + (int64_t)k * nrows + r) : 0.0f;    // streamed once
+                    v[j][k] = ok ? __ldcs(vals + (int64_t)k * ld + r) : 0.0f;       // streamed once
                     xv[j][k] = ok ? __ldg(x + c) : 0.0;
                 }
             }
@@ -535,8 +536,8 @@ static int npb_dia_rows = 1;       // rows per thread (tuning switch npb_spmv_di
 // by the caller); *bad counts entries on an offset that is not in the table
 __global__ void __launch_bounds__(TPB)
 k_csr_to_dia(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-             const double* __restrict__ dat, int ndiag, dia_offsets offs, float* __restrict__ vals,
-             int64_t* __restrict__ bad) {
+             const double* __restrict__ dat, int ndiag, int64_t ld, dia_offsets offs,
+             float* __restrict__ vals, int64_t* __restrict__ bad) {
     const int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r >= nrows) return;
     for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
@@ -544,18 +545,19 @@ k_csr_to_dia(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __re
         int hit = -1;
         for (int d = 0; d < ndiag; ++d)
             if (offs.off[d] == o) hit = d;
-        if (hit >= 0) vals[(int64_t)hit * nrows + r] = (float)dat[k];
+        if (hit >= 0) vals[(int64_t)hit * ld + r] = (float)dat[k];
         else atomicAdd((unsigned long long*)bad, 1ull);
     }
 }
 
 #define ST(s) ((cudaStream_t)(s))
 
-int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets_host,
-                        const float* vals, const double* x, int mode, const double* b,
-                        const double* dinv, double omega, double* y, cudaStream_t st) {
+int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
+                        const int32_t* offsets_host, const float* vals, const double* x, int mode,
+                        const double* b, const double* dinv, double omega, double* y,
+                        cudaStream_t st) {
     if (nrows <= 0) return NPB_OK;
-    if (ndiag < 1 || ndiag > DIA_MAX) return NPB_ERR_ARG;
+    if (ndiag < 1 || ndiag > DIA_MAX || ld < nrows) return NPB_ERR_ARG;
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets_host[k] : 0;
     spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
@@ -565,7 +567,7 @@ int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, const int32_t* 
     int64_t grid = (nrows + (int64_t)TPB * R - 1) / ((int64_t)TPB * R);
     const int64_t cap = (int64_t)NPB_NUM_SMS * 64;
     if (grid > cap) grid = cap;
-#define NPB_DIA_LAUNCH(ND_, R_) k_spmv_dia<ND_, R_><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, o, vals, x, e, y)
+#define NPB_DIA_LAUNCH(ND_, R_) k_spmv_dia<ND_, R_><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, ld, o, vals, x, e, y)
     if (R == 2) {
         if (ndiag <= 3) NPB_DIA_LAUNCH(3, 2); else if (ndiag <= 5) NPB_DIA_LAUNCH(5, 2); else NPB_DIA_LAUNCH(8, 2);
     } else {
@@ -774,17 +776,19 @@ int npb_spmv_f32(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_
 }
 
 // diagonal-storage image of a CSR operator whose entries sit on `ndiag` (<= 8) constant offsets
-// col - row (offsets: [host]); vals: ndiag * nrows floats (zeroed here); *bad (device, reset
+// col - row (offsets: [host]); vals: ndiag * ld floats (zeroed here), diagonal k at vals + k * ld
+// (ld >= nrows; a multiple of 32 keeps every diagonal 128-byte aligned); *bad (device, reset
 // here) = entries found on other offsets (the image is then unusable)
 int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
-                   int ndiag, const int32_t* offsets, float* vals, int64_t* bad, void* stream) {
-    if (ndiag < 1 || ndiag > DIA_MAX || !bad) return NPB_ERR_ARG;
+                   int ndiag, const int32_t* offsets, float* vals, int64_t ld, int64_t* bad,
+                   void* stream) {
+    if (ndiag < 1 || ndiag > DIA_MAX || !bad || ld < nrows) return NPB_ERR_ARG;
     NPB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int64_t), ST(stream)));
     if (nrows <= 0) return NPB_OK;
-    NPB_CUDA(cudaMemsetAsync(vals, 0, sizeof(float) * (size_t)ndiag * (size_t)nrows, ST(stream)));
+    NPB_CUDA(cudaMemsetAsync(vals, 0, sizeof(float) * (size_t)ndiag * (size_t)ld, ST(stream)));
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets[k] : 0;
-    k_csr_to_dia<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, ndiag, o, vals, bad);
+    k_csr_to_dia<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, ndiag, ld, o, vals, bad);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_to_dia");
     return NPB_OK;
@@ -799,13 +803,13 @@ int npb_spmv_dia_set_rows(int r) {
 
 // y = epilogue(A x) from the diagonal-storage image (same modes as npb_spmv_epilogue)
 int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
-                 const double* x, int mode, const double* b, const double* dinv, double omega,
-                 double* y, void* stream) {
+                 int64_t ld, const double* x, int mode, const double* b, const double* dinv,
+                 double omega, double* y, void* stream) {
     if (mode < 0 || mode > 3 || (mode >= 1 && !b) || (mode == 3 && (!dinv || x == y))) {
         npb_set_error("spmv_dia: bad mode / operands");
         return NPB_ERR_ARG;
     }
-    return npb_spmv_dia_launch(nrows, ncols, ndiag, offsets, vals, x, mode, b, dinv, omega, y, ST(stream));
+    return npb_spmv_dia_launch(nrows, ncols, ndiag, ld, offsets, vals, x, mode, b, dinv, omega, y, ST(stream));
 }
 
 // y = b - A x

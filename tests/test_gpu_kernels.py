@@ -443,9 +443,10 @@ def test_spmv_dia_storage(dev):
     A = dev.DevCsr.from_scipy(a)
     offs = [-N, -1, 0, 1, N]
     off_h = (ctypes.c_int32 * 8)(*(offs + [0, 0, 0]))
-    vals = torch.empty(5 * n, dtype=torch.float32, device=dev.device())
+    ld = (n + 31) // 32 * 32
+    vals = torch.empty(5 * ld, dtype=torch.float32, device=dev.device())
     bad = torch.empty(1, dtype=torch.int64, device=dev.device())
-    dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, bad)
+    dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, bad)
     assert int(bad.item()) == 0
     rng = np.random.RandomState(1)
     x, b, dinv = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
@@ -454,11 +455,11 @@ def test_spmv_dia_storage(dev):
     ax = a @ x
     for mode, want in enumerate([ax, b - ax, b + ax, x + 0.7 * dinv * (b - ax)]):
         y = torch.full((n,), np.nan, dtype=torch.float64, device=dev.device())
-        dev._call('npb_spmv_dia', n, n, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, xd, mode, bd, dd, 0.7, y)
+        dev._call('npb_spmv_dia', n, n, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, xd, mode, bd, dd, 0.7, y)
         np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=1e-12 * (np.abs(want).max() + 1))
     # a missing offset is reported
     off_h2 = (ctypes.c_int32 * 8)(-N, -1, 0, 1, 0, 0, 0, 0)
-    dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 4, ctypes.cast(off_h2, ctypes.c_void_p).value, vals, bad)
+    dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 4, ctypes.cast(off_h2, ctypes.c_void_p).value, vals, ld, bad)
     assert int(bad.item()) == n - N + 1 - 1 or int(bad.item()) > 0
     # and the multigrid descriptor picks the image up for a large enough operator
     from numpad_b200 import amg

@@ -15,7 +15,7 @@ M = amg.LscPreconditioner(J)
 L = M.Lm
 n = L.shape[0]
 x = torch.randn(n, dtype=torch.float64, device='cuda'); b = torch.randn_like(x); dinv = torch.rand_like(x); y = torch.empty_like(x)
-offs, vals = amg.dia_image(L)
+offs, vals, ld = amg.dia_image(L)
 off_h = (ctypes.c_int32 * 8)(*(offs + [0] * (8 - len(offs))))
 v32 = L.data.float()
 def timeit(fn, reps=200):
@@ -33,7 +33,7 @@ for rows in (1, 2):
   for mode in (0, 1, 3):
       t64 = timeit(lambda: _call('npb_spmv_epilogue', n, L.nnz, L.indptr, L.indices, L.data, x, mode, b, dinv, 0.67, y, 0))
       t32 = timeit(lambda: _call('npb_spmv_f32', n, L.nnz, L.indptr, L.indices, v32, x, mode, b, dinv, 0.67, y))
-      td = timeit(lambda: _call('npb_spmv_dia', n, n, len(offs), ctypes.cast(off_h, ctypes.c_void_p).value, vals, x, mode, b, dinv, 0.67, y))
+      td = timeit(lambda: _call('npb_spmv_dia', n, n, len(offs), ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, x, mode, b, dinv, 0.67, y))
       vec = 8.0 * n * (2 + (mode >= 1) + 2 * (mode == 3))
       print('mode %d: csr64 %.1f us (%.0f GB/s)  csr32 %.1f us (%.0f GB/s)  dia32 %.1f us (%.0f GB/s)' % (
           mode, t64, (12.0 * L.nnz + 4 * n + vec) / t64 / 1e3, t32, (8.0 * L.nnz + 4 * n + vec) / t32 / 1e3,
