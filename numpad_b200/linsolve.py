@@ -269,6 +269,8 @@ def solve(A, b, transpose=False, **opts):
     sig = (n, A.nnz)
     if _hints['robust'] and _hints['sig'] != sig:
         reset_hints()
+    if _stale['btlu'] is not None and _stale['sig'] != sig:
+        forget_factors()          # a different system: do not sit on tens of GB of old inverses
     if o['precond'] in ('auto', 'lsc', 'amg') and _hints['robust'] and not _pc.direct_feasible(A):
         o['precond'] = _pc.robust_kind(A)
     if o['precond'] == 'btlu':
