@@ -223,6 +223,7 @@ int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      4 stream+128-bit loads, 5 persistent TMA pipeline */,
                      void* stream);
 int npb_spmv_set_tma_geometry(int g);   /* tuning: shared-memory ring geometry -1 (auto) or 0..3; returns old */
+int npb_spmv_set_tma_f32_three(int mode); /* tuning: ring geometry of the fp32 operators, 0..4 (1 = 3 CTAs / SM, default); returns old */
 int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA kernel; returns old */
 /* diagonal storage for stencil operators (entries on <= 8 constant offsets col - row; offsets on the
  * host): conversion (*bad = entries on other offsets) and SpMV with the same epilogue modes */
@@ -253,6 +254,16 @@ int npb_dot_multi(int64_t n, int k, const double* V, int64_t ld,
 int npb_axpy_multi(int64_t n, int k, const double* V, int64_t ld,
                    const double* h, double sign, double* w, double* out_norm2,
                    void* scratch, void* stream);
+/* Gram-Schmidt with delayed re-orthogonalisation (npb_fgmres): both products of a step in one
+ * sweep over the basis, out0[j] = V_j . w0 and out1[j] = V_j . w1 (j < k); and both updates in
+ * one sweep, u <- (u - sum_j c_j V_j) * inv_rho, w <- w - sum_j a_j V_j - b * u_old with
+ * *out_norm2 = ||w||^2 afterwards; coef = [c (k), a (k), inv_rho, b] on the device. */
+int npb_dot_multi2(int64_t n, int k, const double* V, int64_t ld,
+                   const double* w0, const double* w1, double* out0, double* out1,
+                   void* scratch, void* stream);
+int npb_axpy_multi2(int64_t n, int k, const double* V, int64_t ld,
+                    const double* coef, double* u, double* w, double* out_norm2,
+                    void* scratch, void* stream);
 int npb_axpby(int64_t n, double a, const double* x, double b, double* y,
               void* stream);
 

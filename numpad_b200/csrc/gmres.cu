@@ -9,10 +9,16 @@
 // row-sharded multi-GPU case (matvec = halo exchange + local SpMV, allreduce =
 // NCCL) and any preconditioner written on top of the C-ABI.
 //
-// Per inner iteration: 1 preconditioner apply, 1 matvec, classical Gram-Schmidt
-// = 1 multi-dot (which also yields ||w||^2) + 1 multi-axpy (which also yields
-// ||w'||^2), a second pass only when the DGKS test asks for it, 1 scale; ONE
-// device->host copy of the Hessenberg column, Givens on the host.
+// Per inner iteration: 1 preconditioner apply, 1 matvec, classical Gram-Schmidt applied
+// TWICE with the second pass DELAYED (DCGS2, Bielich et al. 2022): the re-orthogonalisation
+// of basis vector j rides on the first orthogonalisation of vector j + 1, so the basis is read
+// twice per iteration (one two-right-hand-side multi-dot, one double multi-axpy) instead of
+// four times, with the orthogonality of CGS2 (single-pass CGS loses it as (||r0||/||r_j||)^2
+// and the old on-demand DGKS test asked for the second pass in every iteration of the cavity
+// solve).  The preconditioner sees the once-orthogonalised vector u_j, which a FLEXIBLE
+// method may: only A Z = V H has to hold, and the column of step j - 1 is corrected when v_j
+// becomes final.  Two small device->host copies per iteration (products, then the norm),
+// least squares on the host.  tools/proto_dcgs2.py is the numpy model of this loop.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,6 +35,12 @@ int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const do
 int npb_axpy_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* h,
                           double sign, double* w, double* out_norm2, void* scratch,
                           cudaStream_t st);
+int npb_dot_multi2_launch(int64_t n, int k, const double* V, int64_t ld, const double* w0,
+                          const double* w1, double* out0, double* out1, void* scratch,
+                          cudaStream_t st);
+int npb_axpy_multi2_launch(int64_t n, int k, const double* V, int64_t ld, const double* coef,
+                           double* u, double* w, double* out_norm2, void* scratch,
+                           cudaStream_t st);
 int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st);
 extern "C" int64_t npb_reduce_scratch_bytes(void);
 
@@ -131,21 +143,28 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
     double* r = (double*)p;                p += (size_t)ld * 8;
     double* dsmall = (double*)p;           p += 4 * ((size_t)m + 8) * 8;
     void* scratch = (void*)p;
-    double* d_h1 = dsmall;                 // m+2
-    double* d_h2 = dsmall + (m + 8);       // m+2 ; [m+1] = norm^2 slot
-    double* d_y = dsmall + 2 * (m + 8);    // m
+    // dsmall: [0, 2(m+8)) products of a step, packed (j + 2 for u, j + 2 for w);
+    // [2(m+8), 4(m+8) - 4) coefficients of the update pass / y of the cycle end; then ||w'||^2
+    double* d_h1 = dsmall;
+    double* d_coef = dsmall + 2 * (m + 8);
+    double* d_y = d_coef;
+    double* d_nrm = dsmall + 4 * (m + 8) - 4;
     NPB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)npb_reduce_scratch_bytes(), st));
 
-    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(2 * (m + 8));
-    // pinned staging buffer, cached across calls (one Python thread per process)
+    // raw Hessenberg (column-major, stride m+1) and its QR, recomputed per step: a column is
+    // corrected one step after it was written
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), R((size_t)(m + 1) * m, 0.0), g(m + 1), y(m);
+    std::vector<double> hcol(2 * (m + 8)), cs(m), sn(m);
+    // pinned staging buffers (fetch / upload), cached across calls (one Python thread per process)
     static double* h_pin = nullptr;
     static size_t h_pin_elems = 0;
-    if (h_pin_elems < (size_t)2 * (m + 8)) {
+    if (h_pin_elems < (size_t)4 * (m + 8)) {
         if (h_pin) cudaFreeHost(h_pin);
         h_pin = nullptr; h_pin_elems = 0;
-        NPB_CUDA(cudaMallocHost(&h_pin, sizeof(double) * 2 * (m + 8)));
-        h_pin_elems = (size_t)2 * (m + 8);
+        NPB_CUDA(cudaMallocHost(&h_pin, sizeof(double) * 4 * (m + 8)));
+        h_pin_elems = (size_t)4 * (m + 8);
     }
+    double* h_up = h_pin + 2 * (m + 8);
 
     auto allreduce = [&](double* buf, int count) -> int {
         if (ops->allreduce) return ops->allreduce(ops->allreduce_ctx, buf, count, stream);
@@ -185,78 +204,101 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
             if (!(rnorm == rnorm)) { status = NPB_ERR_BREAKDOWN; break; }   // NaN
             if (rnorm <= tol) { status = 0; break; }
             if (iters >= maxiter) { status = NPB_ERR_NOCONV; break; }
-            // V0 = r / beta
+            // u_0 = v_0 = r / beta
             GM_TRY(npb_axpby_launch(n, 1.0 / rnorm, r, 0.0, V, st));
-            std::fill(g.begin(), g.end(), 0.0);
-            g[0] = rnorm;
             int j = 0;
-            bool inner_conv = false;
+            double eta = 0.0;                      // ||w'|| of the previous step
+            double gnext = rnorm;                  // least-squares residual estimate
             for (; j < m && iters < maxiter; ++j, ++iters) {
-                double* vj = V + (size_t)j * ld;
+                double* uj = V + (size_t)j * ld;   // u_j now, v_j after the update pass
                 double* zj = flexible ? Z + (size_t)j * ld : Z;
-                if (ops->precond) GM_TRY(ops->precond(ops->precond_ctx, vj, zj, stream));
-                else zj = vj;
+                if (ops->precond) GM_TRY(ops->precond(ops->precond_ctx, uj, zj, stream));
+                else zj = uj;
                 // w lives in the slot of the next basis vector
                 double* wj = V + (size_t)(j + 1) * ld;
                 GM_TRY(ops->matvec(ops->matvec_ctx, zj, wj, stream));
-                // classical Gram-Schmidt with DGKS re-orthogonalisation on demand:
-                // h1 = V^T w and ||w||^2 in ONE multi-dot (w is vector j+1 of the
-                // same array), w -= V h1 (+ ||w'||^2), host round trip; a second
-                // pass only if ||w'|| < ||w|| / sqrt(2)
-                GM_TRY(npb_dot_multi_launch(n, j + 2, V, ld, wj, d_h1, scratch, st));
-                GM_TRY(allreduce(d_h1, j + 2));
-                GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h1, -1.0, wj, d_h2 + m + 1, scratch, st));
-                GM_TRY(allreduce(d_h2 + m + 1, 1));
-                GM_TRY(fetch(hcol.data(), dsmall, 2 * (m + 8)));
-                double* Hj = &H[(size_t)j * (m + 1)];
-                for (int i = 0; i <= j; ++i) Hj[i] = hcol[i];
-                const double w2_before = hcol[j + 1];
-                double w2_after = hcol[(m + 8) + m + 1];
-                if (w2_after < 0.5 * w2_before) {
-                    GM_TRY(npb_dot_multi_launch(n, j + 1, V, ld, wj, d_h2, scratch, st));
-                    GM_TRY(allreduce(d_h2, j + 1));
-                    GM_TRY(npb_axpy_multi_launch(n, j + 1, V, ld, d_h2, -1.0, wj, d_h2 + m + 1, scratch, st));
-                    GM_TRY(allreduce(d_h2 + m + 1, 1));
-                    GM_TRY(fetch(hcol.data(), dsmall, 2 * (m + 8)));
-                    for (int i = 0; i <= j; ++i) Hj[i] += hcol[(m + 8) + i];
-                    w2_after = hcol[(m + 8) + m + 1];
-                    ++reorth;
-                }
-                double hn = sqrt(w2_after > 0.0 ? w2_after : 0.0);
-                Hj[j + 1] = hn;
-                // Givens
+                // products: rows v_0 .. v_{j-1}, u_j, w against (u_j, w) in ONE sweep:
+                //   p0 = [s (j), u.u, u.w],  p1 = [t (j), u.w, w.w]
+                const int kp = j + 2;
+                GM_TRY(npb_dot_multi2_launch(n, kp, V, ld, uj, wj, d_h1, d_h1 + kp, scratch, st));
+                if (2 * kp <= 128) GM_TRY(allreduce(d_h1, 2 * kp));
+                else { GM_TRY(allreduce(d_h1, kp)); GM_TRY(allreduce(d_h1 + kp, kp)); }
+                GM_TRY(fetch(hcol.data(), d_h1, 2 * kp));
+                const double* sv = hcol.data();
+                const double* tv = hcol.data() + kp;
+                double ss = 0.0, st_ = 0.0;
+                for (int i = 0; i < j; ++i) { ss += sv[i] * sv[i]; st_ += sv[i] * tv[i]; }
+                const double rho2 = sv[j] - ss;
+                if (!(rho2 > 0.0)) { status = NPB_ERR_BREAKDOWN; goto cycle_end; }
+                const double rho = sqrt(rho2);
+                const double gp = (tv[j] - st_) / rho;          // v_j . w
+                // update pass: v_j = (u_j - V s) / rho ; w' = w - V a - b u_j ; ||w'||^2
                 for (int i = 0; i < j; ++i) {
-                    double t = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
-                    Hj[i + 1] = -sn[i] * Hj[i] + cs[i] * Hj[i + 1];
-                    Hj[i] = t;
+                    h_up[i] = sv[i];
+                    h_up[j + i] = tv[i] - (gp / rho) * sv[i];
                 }
-                double den = hypot(Hj[j], Hj[j + 1]);
-                if (den == 0.0 || !(den == den)) { status = NPB_ERR_BREAKDOWN; goto cycle_end; }
-                cs[j] = Hj[j] / den; sn[j] = Hj[j + 1] / den;
-                Hj[j] = den; Hj[j + 1] = 0.0;
-                g[j + 1] = -sn[j] * g[j];
-                g[j] = cs[j] * g[j];
-                if (fabs(g[j + 1]) <= tol) { inner_conv = true; ++j; ++iters; break; }
-                if (hn <= 1e-300) { inner_conv = true; ++j; ++iters; break; }   // lucky breakdown
-                GM_TRY(npb_axpby_launch(n, 1.0 / hn, wj, 0.0, wj, st));   // in-place scale
+                h_up[2 * j] = 1.0 / rho;
+                h_up[2 * j + 1] = gp / rho;
+                NPB_CUDA(cudaMemcpyAsync(d_coef, h_up, sizeof(double) * (2 * j + 2), cudaMemcpyHostToDevice, st));
+                GM_TRY(npb_axpy_multi2_launch(n, j, V, ld, d_coef, uj, wj, d_nrm, scratch, st));
+                GM_TRY(allreduce(d_nrm, 1));
+                // the column of step j - 1 now refers to the final v_j
+                if (j > 0) {
+                    double* Hp = &H[(size_t)(j - 1) * (m + 1)];
+                    for (int i = 0; i < j; ++i) Hp[i] += eta * sv[i];
+                    Hp[j] = eta * rho;
+                }
+                double w2;
+                GM_TRY(fetch(&w2, d_nrm, 1));
+                eta = sqrt(w2 > 0.0 ? w2 : 0.0);
+                double* Hj = &H[(size_t)j * (m + 1)];
+                for (int i = 0; i < j; ++i) Hj[i] = tv[i];
+                Hj[j] = gp;
+                Hj[j + 1] = eta;
+                if (!(eta == eta)) { status = NPB_ERR_BREAKDOWN; goto cycle_end; }
+                // QR of the raw Hessenberg by Givens rotations, columns 0 .. j (O(j^2) on the host)
+                std::fill(g.begin(), g.end(), 0.0);
+                g[0] = rnorm;
+                bool singular = false;
+                for (int c = 0; c <= j; ++c) {
+                    double* Rc = &R[(size_t)c * (m + 1)];
+                    const double* Hc = &H[(size_t)c * (m + 1)];
+                    for (int i = 0; i <= c + 1; ++i) Rc[i] = Hc[i];
+                    for (int i = 0; i < c; ++i) {
+                        const double t = cs[i] * Rc[i] + sn[i] * Rc[i + 1];
+                        Rc[i + 1] = -sn[i] * Rc[i] + cs[i] * Rc[i + 1];
+                        Rc[i] = t;
+                    }
+                    const double den = hypot(Rc[c], Rc[c + 1]);
+                    if (den == 0.0 || !(den == den)) { singular = true; break; }
+                    cs[c] = Rc[c] / den; sn[c] = Rc[c + 1] / den;
+                    Rc[c] = den; Rc[c + 1] = 0.0;
+                    g[c + 1] = -sn[c] * g[c];
+                    g[c] = cs[c] * g[c];
+                }
+                if (singular) { status = NPB_ERR_BREAKDOWN; goto cycle_end; }
+                gnext = fabs(g[j + 1]);
+                if (gnext <= tol) { ++j; ++iters; break; }
+                if (eta <= 1e-300) { ++j; ++iters; break; }   // lucky breakdown
+                GM_TRY(npb_axpby_launch(n, 1.0 / eta, wj, 0.0, wj, st));   // u_{j+1}, in place
             }
         cycle_end:
-            (void)inner_conv;
-            // y = H^{-1} g (upper triangular, column-major with stride m+1)
+            (void)gnext;
+            // y = R^{-1} g (upper triangular, column-major with stride m+1)
             for (int i = j - 1; i >= 0; --i) {
                 double s = g[i];
-                for (int k = i + 1; k < j; ++k) s -= H[(size_t)k * (m + 1) + i] * y[k];
-                y[i] = s / H[(size_t)i * (m + 1) + i];
+                for (int k = i + 1; k < j; ++k) s -= R[(size_t)k * (m + 1) + i] * y[k];
+                y[i] = s / R[(size_t)i * (m + 1) + i];
             }
             if (j > 0) {
                 NPB_CUDA(cudaMemcpyAsync(d_y, y.data(), sizeof(double) * j, cudaMemcpyHostToDevice, st));
                 if (flexible || !ops->precond) {
                     const double* basis = ops->precond ? Z : V;
-                    GM_TRY(npb_axpy_multi_launch(n, j, basis, ld, d_y, 1.0, x, d_h2 + m + 1, scratch, st));
+                    GM_TRY(npb_axpy_multi_launch(n, j, basis, ld, d_y, 1.0, x, d_nrm, scratch, st));
                 } else {
                     // x += M^{-1} (V y)
                     NPB_CUDA(cudaMemsetAsync(w, 0, (size_t)n * 8, st));
-                    GM_TRY(npb_axpy_multi_launch(n, j, V, ld, d_y, 1.0, w, d_h2 + m + 1, scratch, st));
+                    GM_TRY(npb_axpy_multi_launch(n, j, V, ld, d_y, 1.0, w, d_nrm, scratch, st));
                     GM_TRY(ops->precond(ops->precond_ctx, w, Z, stream));
                     GM_TRY(npb_axpby_launch(n, 1.0, Z, 1.0, x, st));
                 }
@@ -274,7 +316,7 @@ done:
     if (info) {
         info->iters = iters; info->restarts = restarts;
         info->status = rc ? rc : status;
-        info->pad = reorth;      // number of re-orthogonalisation passes
+        info->pad = reorth;      // (re-orthogonalisation is part of every step)
         info->bnorm = bnorm; info->rnorm0 = rnorm0; info->rnorm = rnorm;
     }
     return rc ? rc : status;

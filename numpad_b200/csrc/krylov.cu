@@ -385,6 +385,70 @@ k_dot_few(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
     }
 }
 
+// out_r[j] = V_j . w_r for j < kc (kc <= KS) and r < NR right-hand vectors, all read ONCE:
+// the Gram-Schmidt products of the Krylov loop (NR = 2: the delayed second pass over the
+// previous basis vector rides on the first pass over the new one, gmres.cu).  Every thread
+// moves one element pair per vector and round with 128-bit loads (KS + NR of them in flight;
+// the scalar kernel above, 8 bytes per load, stays at ~4.3 of ~6.7 TB/s).  V / w_r / ld
+// 16-byte aligned; any n.
+template <int KS, int NR>
+__global__ void __launch_bounds__(TPB, 2)
+k_dot_block(int64_t n, int kc, const double* __restrict__ V, int64_t ld,
+            const double* __restrict__ w0, const double* __restrict__ w1,
+            double* __restrict__ partial, unsigned int* __restrict__ ticket,
+            double* __restrict__ out0, double* __restrict__ out1) {
+    constexpr int NV = KS * NR;
+    __shared__ double smem[(TPB / 32) * NV];
+    double acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = 0.0;
+    const int64_t n2 = n >> 1;
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double a0 = w0[n - 1], a1 = (NR > 1) ? w1[n - 1] : 0.0;
+#pragma unroll
+        for (int j = 0; j < KS; ++j)
+            if (j < kc) {
+                const double v = V[(int64_t)j * ld + n - 1];
+                acc[j] = v * a0;
+                if (NR > 1) acc[KS + j] = v * a1;
+            }
+    }
+    const double2* p0 = reinterpret_cast<const double2*>(w0);
+    const double2* p1 = reinterpret_cast<const double2*>(NR > 1 ? w1 : w0);
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n2;
+         i += (int64_t)gridDim.x * TPB) {
+        const double2 a0 = p0[i];
+        double2 a1 = make_double2(0.0, 0.0);
+        if (NR > 1) a1 = p1[i];
+        double2 v[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            v[j] = make_double2(0.0, 0.0);
+            if (j < kc) v[j] = reinterpret_cast<const double2*>(V + (int64_t)j * ld)[i];
+        }
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            acc[j] = fma(v[j].x, a0.x, fma(v[j].y, a0.y, acc[j]));
+            if (NR > 1) acc[KS + j] = fma(v[j].x, a1.x, fma(v[j].y, a1.y, acc[KS + j]));
+        }
+    }
+    block_sum<NV>(acc, smem);
+    if (threadIdx.x < NV) partial[(int64_t)blockIdx.x * NV + threadIdx.x] = smem[threadIdx.x];
+    if (last_block(ticket)) {
+        __threadfence();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int q = warp; q < NR * kc; q += TPB / 32) {
+            const int r = q / kc, j = q - r * kc;
+            double t = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += partial[(int64_t)b * NV + r * KS + j];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (lane == 0) (r == 0 ? out0 : out1)[j] = t;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
 // w += sum_j hs[j] V_j (j < k, hs = sign * h), and out_norm2 = ||w_new||^2.
 // Two elements per thread (128-bit loads) and four basis vectors per round: 8 x 16 B
 // in flight per thread -- the kernel streams (k + 2) vectors and has nothing to hide
@@ -438,6 +502,88 @@ k_axpy_multi(int64_t n, int k, const double* __restrict__ V, int64_t ld,
         }
         if (j < k) s0 = fma(hs[j], V[j * ld + i], s0);
         const double wi = w[i] + (s0 + s1);
+        w[i] = wi;
+        nrm[0] = fma(wi, wi, nrm[0]);
+    }
+    block_sum<1>(nrm, smem);
+    if (threadIdx.x == 0) partial[blockIdx.x] = smem[0];
+    if (last_block(ticket)) {
+        __threadfence();
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += partial[b];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (threadIdx.x == 0) { *out_norm2 = t; *ticket = 0; }
+        }
+    }
+}
+
+// The update pass of the Gram-Schmidt step with delayed re-orthogonalisation (gmres.cu): ONE
+// sweep over the k final basis vectors does both
+//     u <- (u - sum_j c_j V_j) * inv_rho            (second pass over the previous vector)
+//     w <- w - sum_j a_j V_j - b * u_old            (first pass over the new one)
+// and returns ||w_new||^2.  coef = [c_0..c_{k-1}, a_0..a_{k-1}, inv_rho, b] (device).
+template <bool VEC>
+__global__ void __launch_bounds__(TPB)
+k_axpy_multi2(int64_t n, int k, const double* __restrict__ V, int64_t ld,
+              const double* __restrict__ coef, double* __restrict__ u, double* __restrict__ w,
+              double* __restrict__ partial, unsigned int* __restrict__ ticket,
+              double* __restrict__ out_norm2) {
+    extern __shared__ double hs[];          // 2k + 2 coefficients + reduce scratch
+    double* smem = hs + 2 * k + 2;
+    for (int j = threadIdx.x; j < 2 * k + 2; j += TPB) hs[j] = coef[j];
+    __syncthreads();
+    const double* hc = hs;
+    const double* ha = hs + k;
+    const double inv_rho = hs[2 * k], bu = hs[2 * k + 1];
+    double nrm[1] = {0.0};
+    if (VEC) {
+        const int64_t n2 = n >> 1;
+        for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n2;
+             i += (int64_t)gridDim.x * TPB) {
+            double2 su = make_double2(0.0, 0.0), sw = su;
+            int j = 0;
+            for (; j + 3 < k; j += 4) {
+                const double2 a0 = reinterpret_cast<const double2*>(V + (int64_t)j * ld)[i];
+                const double2 a1 = reinterpret_cast<const double2*>(V + (int64_t)(j + 1) * ld)[i];
+                const double2 a2 = reinterpret_cast<const double2*>(V + (int64_t)(j + 2) * ld)[i];
+                const double2 a3 = reinterpret_cast<const double2*>(V + (int64_t)(j + 3) * ld)[i];
+                su.x = fma(hc[j], a0.x, su.x);         su.y = fma(hc[j], a0.y, su.y);
+                sw.x = fma(ha[j], a0.x, sw.x);         sw.y = fma(ha[j], a0.y, sw.y);
+                su.x = fma(hc[j + 1], a1.x, su.x);     su.y = fma(hc[j + 1], a1.y, su.y);
+                sw.x = fma(ha[j + 1], a1.x, sw.x);     sw.y = fma(ha[j + 1], a1.y, sw.y);
+                su.x = fma(hc[j + 2], a2.x, su.x);     su.y = fma(hc[j + 2], a2.y, su.y);
+                sw.x = fma(ha[j + 2], a2.x, sw.x);     sw.y = fma(ha[j + 2], a2.y, sw.y);
+                su.x = fma(hc[j + 3], a3.x, su.x);     su.y = fma(hc[j + 3], a3.y, su.y);
+                sw.x = fma(ha[j + 3], a3.x, sw.x);     sw.y = fma(ha[j + 3], a3.y, sw.y);
+            }
+            for (; j < k; ++j) {
+                const double2 a0 = reinterpret_cast<const double2*>(V + (int64_t)j * ld)[i];
+                su.x = fma(hc[j], a0.x, su.x);         su.y = fma(hc[j], a0.y, su.y);
+                sw.x = fma(ha[j], a0.x, sw.x);         sw.y = fma(ha[j], a0.y, sw.y);
+            }
+            const double2 uo = reinterpret_cast<double2*>(u)[i];
+            double2 wi = reinterpret_cast<double2*>(w)[i];
+            wi.x = wi.x - sw.x - bu * uo.x;
+            wi.y = wi.y - sw.y - bu * uo.y;
+            reinterpret_cast<double2*>(u)[i] = make_double2((uo.x - su.x) * inv_rho, (uo.y - su.y) * inv_rho);
+            reinterpret_cast<double2*>(w)[i] = wi;
+            nrm[0] = fma(wi.x, wi.x, fma(wi.y, wi.y, nrm[0]));
+        }
+    }
+    // scalar path: everything (VEC = false) or the odd last element
+    for (int64_t i = (VEC ? (n & ~(int64_t)1) : 0) + (int64_t)blockIdx.x * TPB + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * TPB) {
+        double su = 0.0, sw = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const double v = V[(int64_t)j * ld + i];
+            su = fma(hc[j], v, su);
+            sw = fma(ha[j], v, sw);
+        }
+        const double uo = u[i];
+        const double wi = w[i] - sw - bu * uo;
+        u[i] = (uo - su) * inv_rho;
         w[i] = wi;
         nrm[0] = fma(wi, wi, nrm[0]);
     }
@@ -660,10 +806,10 @@ int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_
     return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st, nullptr, nullptr, nullptr);
 }
 
-// scratch: RED_BLOCKS*KC doubles of partials followed by one uint ticket
+// scratch: RED_BLOCKS*KC*2 doubles of partials (two right-hand sides) followed by one uint ticket
 static inline double* red_partial(void* scratch) { return (double*)scratch; }
 static inline unsigned int* red_ticket(void* scratch) {
-    return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC);
+    return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC * 2);
 }
 
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
@@ -678,6 +824,10 @@ int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const do
         else if (vec && kc <= 6 && n >= 4096)
             k_dot_few<6><<<grid_for(n / 4), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
                                                         red_partial(scratch), red_ticket(scratch), out + j0);
+        else if (vec && n >= 4096)
+            k_dot_block<KC, 1><<<grid_for(n / 2), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w, w,
+                                                               red_partial(scratch), red_ticket(scratch),
+                                                               out + j0, out + j0);
         else
             k_dot_multi<<<grid_for(n), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w,
                                                      red_partial(scratch), red_ticket(scratch),
@@ -686,6 +836,32 @@ int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const do
     }
     NPB_COUNT_BYTES(8.0 * n * (k + 1));
     NPB_CHECK_LAUNCH("dot_multi");
+    return NPB_OK;
+}
+
+// out0[j] = V_j . w0, out1[j] = V_j . w1 (j < k): V is read once for both
+int npb_dot_multi2_launch(int64_t n, int k, const double* V, int64_t ld, const double* w0,
+                          const double* w1, double* out0, double* out1, void* scratch,
+                          cudaStream_t st) {
+    const bool vec = ((((uintptr_t)V | (uintptr_t)w0 | (uintptr_t)w1) & 15) == 0) && (ld % 2 == 0 || k <= 1);
+    if (!vec) {
+        int rc = npb_dot_multi_launch(n, k, V, ld, w0, out0, scratch, st);
+        return rc ? rc : npb_dot_multi_launch(n, k, V, ld, w1, out1, scratch, st);
+    }
+    for (int j0 = 0; j0 < k; j0 += KC) {
+        int kc = k - j0 < KC ? k - j0 : KC;
+        if (kc <= 8)
+            k_dot_block<8, 2><<<grid_for(n / 2), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w0, w1,
+                                                              red_partial(scratch), red_ticket(scratch),
+                                                              out0 + j0, out1 + j0);
+        else
+            k_dot_block<KC, 2><<<grid_for(n / 2), TPB, 0, st>>>(n, kc, V + (int64_t)j0 * ld, ld, w0, w1,
+                                                               red_partial(scratch), red_ticket(scratch),
+                                                               out0 + j0, out1 + j0);
+        NPB_COUNT_LAUNCH();
+    }
+    NPB_COUNT_BYTES(8.0 * n * (k + 2));
+    NPB_CHECK_LAUNCH("dot_multi2");
     return NPB_OK;
 }
 
@@ -706,6 +882,23 @@ int npb_axpy_multi_launch(int64_t n, int k, const double* V, int64_t ld, const d
     return NPB_OK;
 }
 
+int npb_axpy_multi2_launch(int64_t n, int k, const double* V, int64_t ld, const double* coef,
+                           double* u, double* w, double* out_norm2, void* scratch,
+                           cudaStream_t st) {
+    size_t sh = sizeof(double) * ((size_t)2 * k + 2 + TPB / 32);
+    const bool vec = ((((uintptr_t)V | (uintptr_t)u | (uintptr_t)w) & 15) == 0) && (ld % 2 == 0 || k <= 1);
+    if (vec)
+        k_axpy_multi2<true><<<grid_for((n + 1) / 2), TPB, sh, st>>>(n, k, V, ld, coef, u, w, red_partial(scratch),
+                                                                   red_ticket(scratch), out_norm2);
+    else
+        k_axpy_multi2<false><<<grid_for(n), TPB, sh, st>>>(n, k, V, ld, coef, u, w, red_partial(scratch),
+                                                          red_ticket(scratch), out_norm2);
+    NPB_COUNT_LAUNCH();
+    NPB_COUNT_BYTES(8.0 * n * (k + 4));
+    NPB_CHECK_LAUNCH("axpy_multi2");
+    return NPB_OK;
+}
+
 int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, cudaStream_t st) {
     if (n <= 0) return NPB_OK;
     k_axpby<<<grid_for(n), TPB, 0, st>>>(n, a, x, b, y);
@@ -718,7 +911,7 @@ int npb_axpby_launch(int64_t n, double a, const double* x, double b, double* y, 
 extern "C" {
 
 int64_t npb_reduce_scratch_bytes(void) {
-    return (int64_t)(sizeof(double) * (size_t)RED_BLOCKS * KC + 64);
+    return (int64_t)(sizeof(double) * (size_t)RED_BLOCKS * KC * 2 + 64);
 }
 
 int npb_spmv(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
@@ -738,6 +931,13 @@ int npb_spmv_set_default_tma(int on) {
 int npb_spmv_set_tma_geometry(int g) {
     const int old = npb_tma_geometry;
     if (g >= -1 && g <= 3) npb_tma_geometry = g;
+    return old;
+}
+
+// tuning switch: ring geometry of the fp32-stored operators (0..4, see spmv_tma.cuh)
+int npb_spmv_set_tma_f32_three(int mode) {
+    const int old = npb_tma_f32_three;
+    if (mode >= 0 && mode <= 4) npb_tma_f32_three = mode;
     return old;
 }
 
@@ -830,6 +1030,19 @@ int npb_dot_multi(int64_t n, int k, const double* V, int64_t ld, const double* w
 int npb_axpy_multi(int64_t n, int k, const double* V, int64_t ld, const double* h,
                    double sign, double* w, double* out_norm2, void* scratch, void* stream) {
     return npb_axpy_multi_launch(n, k, V, ld, h, sign, w, out_norm2, scratch, ST(stream));
+}
+
+// out0[j] = V_j . w0 and out1[j] = V_j . w1 for j < k in one sweep over V
+int npb_dot_multi2(int64_t n, int k, const double* V, int64_t ld, const double* w0,
+                   const double* w1, double* out0, double* out1, void* scratch, void* stream) {
+    return npb_dot_multi2_launch(n, k, V, ld, w0, w1, out0, out1, scratch, ST(stream));
+}
+
+// u <- (u - sum_j c_j V_j) * inv_rho ; w <- w - sum_j a_j V_j - b * u_old ; *out_norm2 = ||w||^2
+// coef = [c (k), a (k), inv_rho, b] on the device
+int npb_axpy_multi2(int64_t n, int k, const double* V, int64_t ld, const double* coef,
+                    double* u, double* w, double* out_norm2, void* scratch, void* stream) {
+    return npb_axpy_multi2_launch(n, k, V, ld, coef, u, w, out_norm2, scratch, ST(stream));
 }
 
 int npb_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream) {

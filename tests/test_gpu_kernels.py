@@ -361,6 +361,49 @@ def test_multi_dot_and_axpy(dev, n, k):
                                    atol=1e-13 * (np.abs(w) .max() + (np.abs(h) @ np.abs(V[:, :n])).max()))
 
 
+@pytest.mark.parametrize('n,k', [(1, 0), (9, 1), (4097, 3), (65536, 8), (65537, 9), (200001, 17),
+                                 (300000, 40), (4096, 0), (300001, 33)])
+def test_dcgs2_passes(dev, n, k):
+    """the two sweeps of a Gram-Schmidt step with delayed re-orthogonalisation (csrc/krylov.cu,
+    used by npb_fgmres): V^T [w0 w1] in one pass, and u <- (u - V c) / rho, w <- w - V a - b u_old
+    with ||w||^2 in one pass; against numpy, odd lengths, k around the 8 / 16-vector passes, and
+    an unaligned view (scalar path)"""
+    import torch
+    from numpad_b200 import _lib
+    rng = np.random.RandomState(n % 89 + k)
+    ld = (n + 31) // 32 * 32
+    V = np.zeros((max(k, 1), ld))
+    V[:k, :n] = rng.standard_normal((k, n))
+    w0, w1 = rng.standard_normal(n), rng.standard_normal(n)
+    coef = rng.standard_normal(2 * k + 2)
+    D = dev.device()
+    Vd = torch.from_numpy(V).to(D)
+    scratch = torch.zeros(_lib.lib().cdll.npb_reduce_scratch_bytes(), dtype=torch.uint8, device=D)
+    for off in ((0, 1) if n > 8 else (0,)):
+        m = n - off
+        Vv = Vd.reshape(-1)[off:]
+        ud = torch.from_numpy(w0.copy()).to(D)[off:]
+        wd = torch.from_numpy(w1.copy()).to(D)[off:]
+        Vh = V[:k, off:n]
+        if k > 0:
+            o0 = torch.zeros(k, dtype=torch.float64, device=D)
+            o1 = torch.zeros(k, dtype=torch.float64, device=D)
+            dev._call('npb_dot_multi2', m, k, Vv, ld, ud, wd, o0, o1, scratch)
+            for got, rhs in ((o0, w0[off:]), (o1, w1[off:])):
+                np.testing.assert_allclose(got.cpu().numpy(), Vh @ rhs, rtol=0,
+                                           atol=1e-13 * np.abs(Vh).dot(np.abs(rhs)).max())
+        cd = torch.from_numpy(coef).to(D)
+        nrm = torch.zeros(1, dtype=torch.float64, device=D)
+        dev._call('npb_axpy_multi2', m, k, Vv, ld, cd, ud, wd, nrm, scratch)
+        c, a, inv_rho, b = coef[:k], coef[k:2 * k], coef[2 * k], coef[2 * k + 1]
+        u_new = (w0[off:] - c @ Vh) * inv_rho
+        w_new = w1[off:] - a @ Vh - b * w0[off:]
+        scale = (np.abs(w0).max() + np.abs(w1).max() + (np.abs(coef[:2 * k]).sum() + 1) * 5.0)
+        np.testing.assert_allclose(ud.cpu().numpy(), u_new, rtol=0, atol=1e-13 * scale * abs(inv_rho))
+        np.testing.assert_allclose(wd.cpu().numpy(), w_new, rtol=0, atol=1e-13 * scale)
+        np.testing.assert_allclose(float(nrm.item()), w_new @ w_new, rtol=1e-12)
+
+
 @pytest.mark.parametrize('kind', ['mis1', 'mis2'])
 def test_aggregation_properties(dev, kind):
     """MIS aggregation on a 2-D 5-point operator: every node gets an aggregate id in
