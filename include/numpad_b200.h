@@ -223,17 +223,29 @@ int npb_spmv_variant(int64_t nrows, int64_t nnz, const int32_t* indptr,
                      4 stream+128-bit loads, 5 persistent TMA pipeline */,
                      void* stream);
 int npb_spmv_set_tma_geometry(int g);   /* tuning: shared-memory ring geometry -1 (auto) or 0..3; returns old */
-int npb_spmv_set_tma_f32_three(int mode); /* tuning: ring geometry of the fp32 operators, 0..4 (1 = 3 CTAs / SM, default); returns old */
+int npb_spmv_set_tma_f32_three(int on); /* tuning: fp32 operators on 3 resident CTAs per SM (default 1); returns old */
 int npb_spmv_set_default_tma(int on);   /* tuning: 0 keeps npb_spmv off the TMA kernel; returns old */
 /* diagonal storage for stencil operators (entries on <= 8 constant offsets col - row; offsets on the
  * host): conversion (*bad = entries on other offsets) and SpMV with the same epilogue modes */
 int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
                    int ndiag, const int32_t* offsets, float* vals, int64_t ld, int64_t* bad,
                    void* stream);
+int npb_spmv_dia_set_dot_ctas(int ctas_per_sm);      /* tuning switch: grid of the fused-dot DIA kernels, returns old */
 int npb_spmv_dia_set_rows(int rows_per_thread);      /* tuning switch (1 or 2), returns the old value */
 int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
                  int64_t ld, const double* x, int mode, const double* b, const double* dinv,
                  double omega, double* y, void* stream);
+/* fused kernels of the preconditioned CG on a diagonal-storage operator (pressure solves of the
+ * LSC preconditioner): the Jacobi sweep that ends a multigrid cycle also returns b . y; the
+ * direction update p <- z + beta p, q <- L z + beta q (= L p) and p . q are one kernel
+ * (beta = *rz_new / *rz_old on the device, first != 0: beta = 0).  red: reduction scratch. */
+int npb_spmv_dia_jacobi_dot(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets,
+                            const float* vals, int64_t ld, const double* x, const double* b,
+                            const double* dinv, double omega, double* y, double* dot_out,
+                            void* red, void* stream);
+int npb_dia_cg_dir(int64_t nrows, int ndiag, const int32_t* offsets, const float* vals, int64_t ld,
+                   const double* z, const double* rz_new, const double* rz_old, int first,
+                   double* p, double* q, double* pq, void* red, void* stream);
 /* same epilogues for an operator whose values are stored in fp32 (vectors and sums fp64) */
 int npb_spmv_f32(int64_t nrows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                  const float* data32, const double* x, int mode, const double* b,

@@ -267,13 +267,19 @@ def truncated(P, theta):
     return DevCsr(P.shape, ptr, idx, dat, (), nnz, P.max_row, True)
 
 
+# a level of at most this many unknowns ends the hierarchy (dense inverse)
+COARSE_MAX = 600
+
+
 class Hierarchy:
     """Smoothed-aggregation AMG for one operator."""
 
     def __init__(self, A, theta=0.0, smooth=True, nu=1, omega=0.67, omega_p=0.67,
-                 coarse_max=600, max_levels=24, agg_passes=1, p_trunc=0.0, agg='mis1',
+                 coarse_max=None, max_levels=24, agg_passes=1, p_trunc=0.0, agg='mis1',
                  gamma=1, gamma_from=2):
         A = A.materialized()
+        if coarse_max is None:
+            coarse_max = COARSE_MAX
         self.mats, self.keep = [], []
         levels = []
         cur = A

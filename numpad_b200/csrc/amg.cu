@@ -35,7 +35,11 @@ int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const do
 int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
                         const int32_t* offsets_host, const float* vals, const double* x, int mode,
                         const double* b, const double* dinv, double omega, double* y,
-                        cudaStream_t st);
+                        cudaStream_t st, double* dot_out, void* red);
+int npb_dia_cg_dir_launch(int64_t nrows, int ndiag, int64_t ld, const int32_t* offsets_host,
+                          const float* vals, const double* z, const double* rz_new,
+                          const double* rz_old, int first, double* p, double* q, double* pq_out,
+                          void* red, cudaStream_t st);
 
 extern "C" {
 typedef int (*npb_apply_fn)(void* ctx, const double* x, double* y, void* stream);
@@ -105,17 +109,18 @@ k_cg_dir(int64_t n, const double* __restrict__ rz_new, const double* __restrict_
     p[i] = fma(beta, p[i], z[i]);
 }
 
-// alpha = rz / pq ;  x += alpha p ;  r -= alpha q
+// alpha = rz / pq ;  x += alpha p ;  r = r_in - alpha q   (r_in may be r; r == NULL: the last
+// step of a fixed number, whose residual nobody reads)
 __global__ void __launch_bounds__(TPB)
 k_cg_update(int64_t n, const double* __restrict__ rz, const double* __restrict__ pq,
             const double* __restrict__ p, const double* __restrict__ q,
-            double* __restrict__ x, double* __restrict__ r, int first) {
+            double* __restrict__ x, const double* r_in, double* r, int first) {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     const double den = *pq;
     const double alpha = den != 0.0 ? *rz / den : 0.0;
     x[i] = first ? alpha * p[i] : fma(alpha, p[i], x[i]);
-    r[i] = fma(-alpha, q[i], r[i]);
+    if (r) r[i] = fma(-alpha, q[i], r_in[i]);
 }
 
 // y = d .* x
@@ -514,12 +519,13 @@ struct npb_csr_mat {
 
 // y = epilogue(M x): 0: Mx  1: b - Mx  2: b + Mx  3: x + omega dinv (b - Mx); a sharded
 // operator first publishes / fetches the boundary values of x
+// (dot_out: only with a diagonal-storage operator and mode 3, see npb_spmv_dia_launch)
 static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* b, double* y,
                            int mode, cudaStream_t st, const double* dinv = nullptr,
-                           double omega = 0.0) {
+                           double omega = 0.0, double* dot_out = nullptr, void* red = nullptr) {
     if (M.dia_vals && !M.halo.dist)
         return npb_spmv_dia_launch(M.nrows, M.ncols, M.ndiag, M.dia_ld, M.dia_off, M.dia_vals, x, mode, b,
-                                   dinv, omega, y, st);
+                                   dinv, omega, y, st, dot_out, red);
     if (M.halo.dist) {
         npb_halo h = M.halo;
         const double* xh = nullptr;
@@ -584,6 +590,8 @@ struct cycle_bufs {
     double* CB[64];          // right-hand side of level l (l >= 1)
     const double* bfine;
     double* xfine;
+    double* dot_out;         // != NULL: the last fine sweep also returns bfine . xfine (DIA level 0)
+    void* red;
 };
 
 static int amg_cycle(const npb_amg* h, int l, cycle_bufs& w, cudaStream_t st) {
@@ -642,7 +650,12 @@ static int amg_cycle(const npb_amg* h, int l, cycle_bufs& w, cudaStream_t st) {
     oth = w.X2[l];
     for (int s = 0; s < h->nu_post; ++s) {
         double* out = (l == 0 && s == h->nu_post - 1) ? w.xfine : oth;
-        jacobi_sweep(L, h->omega, bl, cur, out, st);
+        if (out == w.xfine && w.dot_out) {
+            int rc = spmv_mat(L.A, cur, bl, out, 3, st, L.dinv, h->omega, w.dot_out, w.red);
+            if (rc) return rc;
+        } else {
+            jacobi_sweep(L, h->omega, bl, cur, out, st);
+        }
         if (out == w.xfine) { cur = w.xfine; break; }
         double* t = cur; cur = oth; oth = t;
     }
@@ -656,18 +669,31 @@ static int amg_cycle(const npb_amg* h, int l, cycle_bufs& w, cudaStream_t st) {
 
 // x <- one cycle (V, or W on the coarse levels) on b from a zero initial guess.  b and x have
 // the fine size and must not alias the hierarchy's work vectors.
-int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
-    cudaStream_t st = ST(stream);
+// the cycle can return b . x with its last sweep when that sweep is a Jacobi sweep of a
+// diagonal-storage operator on one GPU (the preconditioned CG of the pressure solves)
+static bool amg_cycle_can_dot(const npb_amg* h) {
+    const npb_csr_mat& A0 = h->levels[0].A;
+    return h->nlevels > 1 && h->nu_post >= 1 && A0.dia_vals && !A0.halo.dist && !h->dist;
+}
+
+static int amg_vcycle_dot(const npb_amg* h, const double* b, double* x, double* dot_out, void* red,
+                          cudaStream_t st) {
     const int nl = h->nlevels;
     if (nl > 64) { npb_set_error("amg_vcycle: more than 64 levels"); return NPB_ERR_ARG; }
     cycle_bufs w;
     for (int l = 0; l < nl; ++l) { w.X[l] = h->levels[l].x; w.X2[l] = h->levels[l].x2; w.CB[l] = h->levels[l].b; }
     w.bfine = b;
     w.xfine = x;
+    w.dot_out = dot_out;
+    w.red = red;
     int rc = amg_cycle(h, 0, w, st);
     if (rc) return rc;
     NPB_CHECK_LAUNCH("amg_vcycle");
     return NPB_OK;
+}
+
+int npb_amg_vcycle(const npb_amg* h, const double* b, double* x, void* stream) {
+    return amg_vcycle_dot(h, b, x, nullptr, nullptr, ST(stream));
 }
 
 // x <- k V-cycles on A x = b (stationary iteration, zero start); r = scratch (fine size)
@@ -690,20 +716,31 @@ static int amg_pcg(const npb_amg* h, const npb_csr_mat& A, int k, const double* 
                    cudaStream_t st) {
     const int64_t n = A.nrows;
     int rc;
-    NPB_CUDA(cudaMemcpyAsync(r, b, n * 8, cudaMemcpyDeviceToDevice, st));
+    // one GPU, diagonal-storage operator: r . z comes out of the last sweep of the cycle, and
+    // direction update, operator product and p . q are one kernel (q = L z + beta q)
+    const bool fuse_rz = amg_cycle_can_dot(h);
+    const bool fuse_dir = A.dia_vals && !A.halo.dist && !h->dist && A.nrows == A.ncols;
     for (int i = 0; i < k; ++i) {
         double* rz_new = scal + (i & 1);
         double* rz_old = scal + ((i + 1) & 1);
-        if ((rc = npb_amg_vcycle(h, r, z, (void*)st))) return rc;
-        if ((rc = npb_dot_multi_launch(n, 1, r, n, z, rz_new, red, st))) return rc;
+        const double* rin = (i == 0) ? b : r;          // the first residual is b itself
+        if ((rc = amg_vcycle_dot(h, rin, z, fuse_rz ? rz_new : nullptr, red, st))) return rc;
+        if (!fuse_rz && (rc = npb_dot_multi_launch(n, 1, rin, n, z, rz_new, red, st))) return rc;
         if ((rc = npb_dist_allreduce_sum((const npb_dist*)h->dist, rz_new, 1, st))) return rc;
-        k_cg_dir<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, rz_old, i == 0, z, p);
-        NPB_COUNT_LAUNCH();
-        if ((rc = spmv_mat(A, p, nullptr, q, 0, st))) return rc;
-        if ((rc = npb_dot_multi_launch(n, 1, p, n, q, scal + 2, red, st))) return rc;
+        if (fuse_dir) {
+            if ((rc = npb_dia_cg_dir_launch(n, A.ndiag, A.dia_ld, A.dia_off, A.dia_vals, z, rz_new, rz_old,
+                                            i == 0, p, q, scal + 2, red, st))) return rc;
+        } else {
+            k_cg_dir<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, rz_old, i == 0, z, p);
+            NPB_COUNT_LAUNCH();
+            if ((rc = spmv_mat(A, p, nullptr, q, 0, st))) return rc;
+            if ((rc = npb_dot_multi_launch(n, 1, p, n, q, scal + 2, red, st))) return rc;
+        }
         if ((rc = npb_dist_allreduce_sum((const npb_dist*)h->dist, scal + 2, 1, st))) return rc;
-        k_cg_update<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, scal + 2, p, q, x, r, i == 0);
+        k_cg_update<<<npb_blocks(n, TPB), TPB, 0, st>>>(n, rz_new, scal + 2, p, q, x, rin,
+                                                       i == k - 1 ? nullptr : r, i == 0);
         NPB_COUNT_LAUNCH();
+        NPB_COUNT_BYTES(8.0 * n * (i == k - 1 ? 3 : 6));
     }
     return NPB_OK;
 }
@@ -1077,7 +1114,7 @@ int npb_cg_dir(int64_t n, const double* rz_new, const double* rz_old, int first,
 int npb_cg_update(int64_t n, const double* rz, const double* pq, const double* p,
                   const double* q, double* x, double* r, int first, void* stream) {
     if (n <= 0) return NPB_OK;
-    k_cg_update<<<npb_blocks(n, TPB), TPB, 0, ST(stream)>>>(n, rz, pq, p, q, x, r, first);
+    k_cg_update<<<npb_blocks(n, TPB), TPB, 0, ST(stream)>>>(n, rz, pq, p, q, x, r, r, first);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("cg_update");
     return NPB_OK;

@@ -627,15 +627,88 @@ constexpr int DIA_MAX = 8;
 struct dia_offsets { int32_t off[DIA_MAX]; };
 
 // ND: compile-time bound on ndiag (register arrays); R rows per thread, grid-stride over rounds.
-// Every load of a round is issued before the first is used; out-of-range columns read a clamped
-// address and are masked in the sum.
-template <int ND, int R>
+// Every load of a round has to be in flight before the first is used (the kernel has nothing
+// else to hide the latency with): rounds whose rows all have their ND neighbours in range --
+// all but the first and last few blocks -- take a path without bounds predicates, which ptxas
+// schedules as one batch of loads (with the predicated address clamps it interleaved loads and
+// their conversions, ~3 loads in flight, 3.2 TB/s); EXACT: ndiag == ND, no runtime trip count.
+template <int ND, bool EXACT>
+__device__ __forceinline__ void dia_load_row(bool fast, int ndiag, const dia_offsets& offs,
+                                             const float* __restrict__ vals, int64_t ld,
+                                             const double* __restrict__ x, int64_t r, int64_t ncols,
+                                             bool live, float (&v)[ND], double (&xv)[ND]) {
+    if (fast) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+            v[k] = 0.0f; xv[k] = 0.0;
+            if (EXACT || k < ndiag) {
+                v[k] = __ldcs(vals + (int64_t)k * ld + r);       // streamed once
+                xv[k] = __ldg(x + (r + offs.off[k]));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+            v[k] = 0.0f; xv[k] = 0.0;
+            if ((EXACT || k < ndiag) && live) {
+                const int64_t c = r + offs.off[k];
+                const bool ok = c >= 0 && c < ncols;
+                v[k] = ok ? __ldcs(vals + (int64_t)k * ld + r) : 0.0f;
+                xv[k] = ok ? __ldg(x + c) : 0.0;
+            }
+        }
+    }
+}
+
+// rows [lo, hi) all have every neighbour in [0, ncols): block-uniform
+__device__ __forceinline__ bool dia_interior(const dia_offsets& offs, int ndiag, int64_t lo, int64_t hi,
+                                             int64_t nrows, int64_t ncols) {
+    int32_t mn = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < DIA_MAX; ++k)
+        if (k < ndiag) { mn = min(mn, offs.off[k]); mx = max(mx, offs.off[k]); }
+    return hi <= nrows && lo + mn >= 0 && hi - 1 + mx < ncols;
+}
+
+// sum of one value per thread over the whole grid, deterministic: per-block partials, the last
+// block to finish adds them in a fixed order (scratch of the reductions: partial / ticket)
+__device__ __forceinline__ void grid_sum_to(double v, double* __restrict__ partial,
+                                            unsigned int* __restrict__ ticket, double* __restrict__ out) {
+    __shared__ double gs_smem[TPB / 32];
+    __shared__ bool gs_last;
+    double a[1] = {v};
+    block_sum<1>(a, gs_smem);
+    // only thread 0 publishes: a fence by every thread would wait for the block's own result
+    // stores to drain before the block can retire (measured: +40 us on a 40 us kernel of 8192
+    // short blocks)
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = gs_smem[0];
+        __threadfence();
+        gs_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (gs_last) {
+        __threadfence();
+        double t[1] = {0.0};
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += TPB) t[0] += __ldcg(partial + b);
+        __syncthreads();
+        block_sum<1>(t, gs_smem);
+        if (threadIdx.x == 0) { *out = gs_smem[0]; *ticket = 0; }
+    }
+}
+
+// DOT: the Jacobi epilogue (mode 3) also returns b . y (the r . z of a preconditioned CG step
+// whose preconditioner ends with this sweep)
+template <int ND, int R, bool DOT, bool EXACT>
 __global__ void __launch_bounds__(TPB)
 k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs,
            const float* __restrict__ vals, const double* __restrict__ x, spmv_epi e,
-           double* __restrict__ y) {
+           double* __restrict__ y, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+           double* __restrict__ dot_out) {
+    double dacc = 0.0;
     for (int64_t base = (int64_t)blockIdx.x * (TPB * R); base < nrows;
          base += (int64_t)gridDim.x * (TPB * R)) {
+        const bool fast = dia_interior(offs, ndiag, base, base + TPB * R, nrows, ncols);
         float v[R][ND];
         double xv[R][ND];
         double bv[R], dv[R], xr[R];
@@ -644,16 +717,7 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs
             const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
             const bool live = r < nrows;
             bv[j] = dv[j] = xr[j] = 0.0;
-#pragma unroll
-            for (int k = 0; k < ND; ++k) {
-                v[j][k] = 0.0f; xv[j][k] = 0.0;
-                if (k < ndiag && live) {
-                    const int64_t c = r + offs.off[k];
-                    const bool ok = c >= 0 && c < ncols;
-                    v[j][k] = ok ? __ldcs(vals + (int64_t)k * ld + r) : 0.0f;       // streamed once
-                    xv[j][k] = ok ? __ldg(x + c) : 0.0;
-                }
-            }
+            dia_load_row<ND, EXACT>(fast, ndiag, offs, vals, ld, x, r, ncols, live, v[j], xv[j]);
             if (live && e.mode >= 1) bv[j] = __ldg(e.b + r);
             if (live && e.mode == 3) { dv[j] = __ldg(e.dinv + r); xr[j] = __ldg(x + r); }
         }
@@ -672,11 +736,65 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs
                 default: out = xr[j] + e.omega * dv[j] * (bv[j] - s); break;
             }
             y[r] = out;
+            if (DOT) dacc = fma(bv[j], out, dacc);
         }
     }
+    if (DOT) grid_sum_to(dacc, partial, ticket, dot_out);
 }
 
-static int npb_dia_rows = 1;       // rows per thread (tuning switch npb_spmv_dia_set_rows)
+// One kernel for the direction update of a CG step on a DIA operator L, scalars on the device:
+//   beta = rz_new / rz_old (first: 0) ;  p <- z + beta p ;  q <- L z + beta q  (= L p) ;  *pq = p . q
+// instead of p-update, SpMV and inner product: z is read once, p and q once each.
+template <int ND, int R, bool EXACT>
+__global__ void __launch_bounds__(TPB)
+k_dia_cg_dir(int64_t nrows, int ndiag, int64_t ld, dia_offsets offs, const float* __restrict__ vals,
+             const double* __restrict__ z, const double* __restrict__ rz_new,
+             const double* __restrict__ rz_old, int first, double* __restrict__ p,
+             double* __restrict__ q, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+             double* __restrict__ pq_out) {
+    double beta = 0.0;
+    if (!first) {
+        const double den = *rz_old;
+        beta = den != 0.0 ? *rz_new / den : 0.0;
+    }
+    double dacc = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * (TPB * R); base < nrows;
+         base += (int64_t)gridDim.x * (TPB * R)) {
+        const bool fast = dia_interior(offs, ndiag, base, base + TPB * R, nrows, nrows);
+        float v[R][ND];
+        double zv[R][ND];
+        double zr[R], po[R], qo[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
+            const bool live = r < nrows;
+            dia_load_row<ND, EXACT>(fast, ndiag, offs, vals, ld, z, r, nrows, live, v[j], zv[j]);
+            zr[j] = po[j] = qo[j] = 0.0;
+            if (live) {
+                zr[j] = __ldg(z + r);
+                if (!first) { po[j] = p[r]; qo[j] = q[r]; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
+            if (r >= nrows) continue;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) s = fma((double)v[j][k], zv[j][k], s);
+            const double pn = fma(beta, po[j], zr[j]), qn = fma(beta, qo[j], s);
+            p[r] = pn;
+            q[r] = qn;
+            dacc = fma(pn, qn, dacc);
+        }
+    }
+    grid_sum_to(dacc, partial, ticket, pq_out);
+}
+
+// rows per thread (tuning switch npb_spmv_dia_set_rows).  Two: with every load of a round issued
+// up front, 2 x (2 ND + 3) loads in flight per thread reach 5.0 / 6.4 TB/s on the residual / Jacobi
+// epilogue of the 2048^2 pressure operator (one row: 4.5; tools/dia_bench.py)
+static int npb_dia_rows = 2;
 
 // CSR -> DIA image: vals[k * nrows + r] = entry of row r on offset offs[k] (rows are zero-filled
 // by the caller); *bad counts entries on an offset that is not in the table
@@ -698,12 +816,31 @@ k_csr_to_dia(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __re
 
 #define ST(s) ((cudaStream_t)(s))
 
+// scratch: RED_BLOCKS*KC*2 doubles of partials (two right-hand sides) followed by one uint ticket
+static inline double* red_partial(void* scratch) { return (double*)scratch; }
+static inline unsigned int* red_ticket(void* scratch) {
+    return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC * 2);
+}
+constexpr int64_t DIA_GRID_CAP = (int64_t)NPB_NUM_SMS * 64;
+// persistent grid of the kernels with a fused inner product: 0 = as many CTAs as are resident
+// (2 or 3 per SM by registers; measured best, tools/dia_bench.py), else CTAs per SM (tuning)
+static int npb_dia_dot_ctas = 0;
+template <class K>
+static int64_t dia_dot_grid(K kernel) {
+    if (npb_dia_dot_ctas > 0) return (int64_t)NPB_NUM_SMS * npb_dia_dot_ctas;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, TPB, 0) != cudaSuccess || nb < 1) nb = 2;
+    return (int64_t)NPB_NUM_SMS * nb;
+}
+static_assert(DIA_GRID_CAP <= (int64_t)RED_BLOCKS * KC * 2, "DIA dot partials fit the reduction scratch");
+
+// dot_out != NULL (mode 3 only): also *dot_out = b . y, through the reduction scratch `red`
 int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
                         const int32_t* offsets_host, const float* vals, const double* x, int mode,
                         const double* b, const double* dinv, double omega, double* y,
-                        cudaStream_t st) {
+                        cudaStream_t st, double* dot_out = nullptr, void* red = nullptr) {
     if (nrows <= 0) return NPB_OK;
-    if (ndiag < 1 || ndiag > DIA_MAX || ld < nrows) return NPB_ERR_ARG;
+    if (ndiag < 1 || ndiag > DIA_MAX || ld < nrows || (dot_out && (mode != 3 || !red))) return NPB_ERR_ARG;
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets_host[k] : 0;
     spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
@@ -711,18 +848,58 @@ int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
     // reads it through the non-coherent path
     const int R = npb_dia_rows;
     int64_t grid = (nrows + (int64_t)TPB * R - 1) / ((int64_t)TPB * R);
-    const int64_t cap = (int64_t)NPB_NUM_SMS * 64;
-    if (grid > cap) grid = cap;
-#define NPB_DIA_LAUNCH(ND_, R_) k_spmv_dia<ND_, R_><<<(int)grid, TPB, 0, st>>>(nrows, ncols, ndiag, ld, o, vals, x, e, y)
-    if (R == 2) {
-        if (ndiag <= 3) NPB_DIA_LAUNCH(3, 2); else if (ndiag <= 5) NPB_DIA_LAUNCH(5, 2); else NPB_DIA_LAUNCH(8, 2);
+    if (grid > DIA_GRID_CAP) grid = DIA_GRID_CAP;
+    double* pa = red ? red_partial(red) : nullptr;
+    unsigned int* ti = red ? red_ticket(red) : nullptr;
+    // exact instantiations for the 3- and 5-point stencils, a bounded generic one otherwise; with
+    // the inner product: a persistent grid (the per-block reduction + ticket at the end of
+    // thousands of one-round blocks doubled the kernel's time)
+#define NPB_DIA_LAUNCH(ND_, R_, DOT_, EX_) do { \
+        int64_t g_ = grid; \
+        if (DOT_) { const int64_t c_ = dia_dot_grid(k_spmv_dia<ND_, R_, DOT_, EX_>); if (g_ > c_) g_ = c_; } \
+        k_spmv_dia<ND_, R_, DOT_, EX_><<<(int)g_, TPB, 0, st>>>(nrows, ncols, ndiag, ld, o, vals, x, e, y, pa, ti, dot_out); \
+    } while (0)
+    if (dot_out && R == 2) {
+        if (ndiag == 3) NPB_DIA_LAUNCH(3, 2, true, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 2, true, true); else NPB_DIA_LAUNCH(8, 2, true, false);
+    } else if (dot_out) {
+        if (ndiag == 3) NPB_DIA_LAUNCH(3, 1, true, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 1, true, true); else NPB_DIA_LAUNCH(8, 1, true, false);
+    } else if (R == 2) {
+        if (ndiag == 3) NPB_DIA_LAUNCH(3, 2, false, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 2, false, true); else NPB_DIA_LAUNCH(8, 2, false, false);
     } else {
-        if (ndiag <= 3) NPB_DIA_LAUNCH(3, 1); else if (ndiag <= 5) NPB_DIA_LAUNCH(5, 1); else NPB_DIA_LAUNCH(8, 1);
+        if (ndiag == 3) NPB_DIA_LAUNCH(3, 1, false, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 1, false, true); else NPB_DIA_LAUNCH(8, 1, false, false);
     }
 #undef NPB_DIA_LAUNCH
     NPB_COUNT_LAUNCH();
     NPB_COUNT_BYTES(4.0 * ndiag * nrows + 8.0 * nrows * (2 + (mode >= 1) + 2 * (mode == 3)));
     NPB_CHECK_LAUNCH("spmv_dia");
+    return NPB_OK;
+}
+
+// p <- z + beta p, q <- L z + beta q, *pq = p . q with beta = *rz_new / *rz_old (first: 0); L square
+int npb_dia_cg_dir_launch(int64_t nrows, int ndiag, int64_t ld, const int32_t* offsets_host,
+                          const float* vals, const double* z, const double* rz_new,
+                          const double* rz_old, int first, double* p, double* q, double* pq_out,
+                          void* red, cudaStream_t st) {
+    if (nrows <= 0) return NPB_OK;
+    if (ndiag < 1 || ndiag > DIA_MAX || ld < nrows || !red) return NPB_ERR_ARG;
+    dia_offsets o;
+    for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets_host[k] : 0;
+    const int R = npb_dia_rows;
+    int64_t grid = (nrows + (int64_t)TPB * R - 1) / ((int64_t)TPB * R);
+#define NPB_DIA_LAUNCH(ND_, R_, EX_) do { \
+        int64_t g_ = grid; \
+        const int64_t c_ = dia_dot_grid(k_dia_cg_dir<ND_, R_, EX_>); if (g_ > c_) g_ = c_; \
+        k_dia_cg_dir<ND_, R_, EX_><<<(int)g_, TPB, 0, st>>>(nrows, ndiag, ld, o, vals, z, rz_new, rz_old, first, p, q, red_partial(red), red_ticket(red), pq_out); \
+    } while (0)
+    if (R == 2) {
+        if (ndiag == 3) NPB_DIA_LAUNCH(3, 2, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 2, true); else NPB_DIA_LAUNCH(8, 2, false);
+    } else {
+        if (ndiag == 3) NPB_DIA_LAUNCH(3, 1, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 1, true); else NPB_DIA_LAUNCH(8, 1, false);
+    }
+#undef NPB_DIA_LAUNCH
+    NPB_COUNT_LAUNCH();
+    NPB_COUNT_BYTES(4.0 * ndiag * nrows + 8.0 * nrows * (first ? 3 : 5));
+    NPB_CHECK_LAUNCH("dia_cg_dir");
     return NPB_OK;
 }
 
@@ -806,11 +983,6 @@ int npb_spmv_launch(int64_t nrows, int64_t nnz, const int32_t* ptr, const int32_
     return npb_spmv_ex(nrows, nnz, ptr, idx, dat, x, mode, b, nullptr, 0.0, y, 0, st, nullptr, nullptr, nullptr);
 }
 
-// scratch: RED_BLOCKS*KC*2 doubles of partials (two right-hand sides) followed by one uint ticket
-static inline double* red_partial(void* scratch) { return (double*)scratch; }
-static inline unsigned int* red_ticket(void* scratch) {
-    return (unsigned int*)((double*)scratch + (size_t)RED_BLOCKS * KC * 2);
-}
 
 int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const double* w,
                          double* out, void* scratch, cudaStream_t st) {
@@ -934,10 +1106,10 @@ int npb_spmv_set_tma_geometry(int g) {
     return old;
 }
 
-// tuning switch: ring geometry of the fp32-stored operators (0..4, see spmv_tma.cuh)
-int npb_spmv_set_tma_f32_three(int mode) {
+// tuning switch: fp32-stored operators with 5..20-entry rows on 3 resident CTAs per SM (default 1)
+int npb_spmv_set_tma_f32_three(int on) {
     const int old = npb_tma_f32_three;
-    if (mode >= 0 && mode <= 4) npb_tma_f32_three = mode;
+    npb_tma_f32_three = on ? 1 : 0;
     return old;
 }
 
@@ -994,6 +1166,13 @@ int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices,
     return NPB_OK;
 }
 
+// tuning switch: CTAs per SM of the DIA kernels with a fused inner product (0: resident count); returns the old value
+int npb_spmv_dia_set_dot_ctas(int c) {
+    const int old = npb_dia_dot_ctas;
+    if (c >= 0 && c <= 64) npb_dia_dot_ctas = c;
+    return old;
+}
+
 // tuning switch: rows per thread of the DIA kernel (1 or 2); returns the old value
 int npb_spmv_dia_set_rows(int r) {
     const int old = npb_dia_rows;
@@ -1009,7 +1188,30 @@ int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets
         npb_set_error("spmv_dia: bad mode / operands");
         return NPB_ERR_ARG;
     }
-    return npb_spmv_dia_launch(nrows, ncols, ndiag, ld, offsets, vals, x, mode, b, dinv, omega, y, ST(stream));
+    return npb_spmv_dia_launch(nrows, ncols, ndiag, ld, offsets, vals, x, mode, b, dinv, omega, y, ST(stream), nullptr, nullptr);
+}
+
+// Jacobi sweep y = x + omega dinv (b - A x) from the diagonal-storage image that also returns
+// *dot_out = b . y (device); red: npb_reduce_scratch_bytes() bytes, zeroed once
+int npb_spmv_dia_jacobi_dot(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets,
+                            const float* vals, int64_t ld, const double* x, const double* b,
+                            const double* dinv, double omega, double* y, double* dot_out,
+                            void* red, void* stream) {
+    if (!b || !dinv || x == y || !dot_out || !red) {
+        npb_set_error("spmv_dia_jacobi_dot: bad operands");
+        return NPB_ERR_ARG;
+    }
+    return npb_spmv_dia_launch(nrows, ncols, ndiag, ld, offsets, vals, x, 3, b, dinv, omega, y, ST(stream),
+                               dot_out, red);
+}
+
+// direction update of a CG step on a square diagonal-storage operator L in one kernel:
+// beta = *rz_new / *rz_old (first != 0: beta = 0), p <- z + beta p, q <- L z + beta q, *pq = p . q
+int npb_dia_cg_dir(int64_t nrows, int ndiag, const int32_t* offsets, const float* vals, int64_t ld,
+                   const double* z, const double* rz_new, const double* rz_old, int first,
+                   double* p, double* q, double* pq, void* red, void* stream) {
+    return npb_dia_cg_dir_launch(nrows, ndiag, ld, offsets, vals, z, rz_new, rz_old, first, p, q, pq, red,
+                                 ST(stream));
 }
 
 // y = b - A x

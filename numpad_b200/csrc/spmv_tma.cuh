@@ -350,12 +350,12 @@ static int spmv_tma_dispatch_g(int64_t nrows, int64_t nnz, const int32_t* ptr, c
     }
 }
 
-// fp32-stored operators (74 KB instead of 111 KB per 3072 x 3 ring) leave room for more resident
-// CTAs, i.e. more consumer warps with gathers in flight -- the kernel is bound by the gathers
-// of x, not by the stream (J in fp64 and the momentum operator in fp32 both run at ~345 G
-// gathers/s on 2 CTAs/SM).  0 = as the fp64 operators; 1 = 3 CTAs on the 3072 x 3 ring for the
-// 5..20-entry rows; 2 / 3 = 4 CTAs on 2304 x 2 / 2304 x 3 rings (all row lengths); 4 = 1 for the
-// 5..20-entry rows + 4 CTAs for the others (tuning switch npb_spmv_set_tma_f32_three)
+// fp32-stored operators (74 KB instead of 111 KB per 3072 x 3 ring) leave room for a third
+// resident CTA, i.e. more consumer warps with gathers in flight -- the kernel is bound by the
+// gathers of x, not by the stream (J in fp64 and the momentum operator in fp32 both run at
+// ~345 G gathers/s on 2 CTAs/SM).  Measured on the 2048^2 cavity step (tools/krylov_time.py):
+// Krylov phase 615 -> 572 ms; 4 CTAs on smaller rings (2304 x 2 / x 3): 630 ms.
+// 0 = as the fp64 operators (tuning switch npb_spmv_set_tma_f32_three)
 static int npb_tma_f32_three = 1;
 
 template <class T>
@@ -364,13 +364,8 @@ static int spmv_tma_dispatch(int64_t nrows, int64_t nnz, const int32_t* ptr, con
                              cudaStream_t st) {
     const int g = tma_geometry_for((double)nnz / (double)nrows);
     if constexpr (sizeof(T) == 4) {
-        const int f = npb_tma_f32_three;
-        if (g == 0 && (f == 1 || f == 4))
+        if (g == 0 && npb_tma_f32_three)
             return spmv_tma_dispatch_g<tm_geom<3072, 3, 3>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        if ((g == 0 && f == 3))
-            return spmv_tma_dispatch_g<tm_geom<2304, 3, 4>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
-        if ((g == 0 && f == 2) || (g == 2 && f >= 2))
-            return spmv_tma_dispatch_g<tm_geom<2304, 2, 4>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
     }
     switch (g) {
         case 1: return spmv_tma_dispatch_g<tm_geom<2304, 3, 2>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);

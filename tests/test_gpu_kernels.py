@@ -500,6 +500,26 @@ def test_spmv_dia_storage(dev):
         y = torch.full((n,), np.nan, dtype=torch.float64, device=dev.device())
         dev._call('npb_spmv_dia', n, n, 5, ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, xd, mode, bd, dd, 0.7, y)
         np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=1e-12 * (np.abs(want).max() + 1))
+    # fused kernels of the pressure CG: Jacobi sweep + b . y, and p / q update + p . q
+    from numpad_b200 import _lib
+    red = torch.zeros(_lib.lib().cdll.npb_reduce_scratch_bytes(), dtype=torch.uint8, device=dev.device())
+    offp = ctypes.cast(off_h, ctypes.c_void_p).value
+    y = torch.full((n,), np.nan, dtype=torch.float64, device=dev.device())
+    dot = torch.zeros(1, dtype=torch.float64, device=dev.device())
+    dev._call('npb_spmv_dia_jacobi_dot', n, n, 5, offp, vals, ld, xd, bd, dd, 0.7, y, dot, red)
+    want = x + 0.7 * dinv * (b - ax)
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=1e-12 * (np.abs(want).max() + 1))
+    np.testing.assert_allclose(float(dot.item()), b @ want, rtol=1e-12, atol=1e-9)
+    p0, q0 = rng.standard_normal(n), rng.standard_normal(n)
+    rz = t(np.array([3.0, 2.0]))
+    for first in (1, 0):
+        pd, qd = t(p0.copy()), t(q0.copy())
+        dev._call('npb_dia_cg_dir', n, 5, offp, vals, ld, xd, rz[0:], rz[1:], first, pd, qd, dot, red)
+        beta = 0.0 if first else 1.5
+        pw, qw = x + beta * p0, ax + beta * q0
+        np.testing.assert_allclose(pd.cpu().numpy(), pw, rtol=0, atol=1e-12 * (np.abs(pw).max() + 1))
+        np.testing.assert_allclose(qd.cpu().numpy(), qw, rtol=0, atol=1e-12 * (np.abs(qw).max() + 1))
+        np.testing.assert_allclose(float(dot.item()), pw @ qw, rtol=1e-11, atol=1e-8)
     # a missing offset is reported
     off_h2 = (ctypes.c_int32 * 8)(-N, -1, 0, 1, 0, 0, 0, 0)
     dev._call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, 4, ctypes.cast(off_h2, ctypes.c_void_p).value, vals, ld, bad)

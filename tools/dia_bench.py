@@ -38,3 +38,14 @@ for rows in (1, 2):
       print('mode %d: csr64 %.1f us (%.0f GB/s)  csr32 %.1f us (%.0f GB/s)  dia32 %.1f us (%.0f GB/s)' % (
           mode, t64, (12.0 * L.nnz + 4 * n + vec) / t64 / 1e3, t32, (8.0 * L.nnz + 4 * n + vec) / t32 / 1e3,
           td, (4.0 * len(offs) * n + vec) / td / 1e3))
+  # fused kernels of the pressure CG
+  red = torch.zeros(_lib.lib().cdll.npb_reduce_scratch_bytes(), dtype=torch.uint8, device='cuda')
+  dot = torch.zeros(2, dtype=torch.float64, device='cuda'); rz = torch.ones(2, dtype=torch.float64, device='cuda')
+  p = torch.randn_like(x); q = torch.randn_like(x)
+  offp = ctypes.cast(off_h, ctypes.c_void_p).value
+  for ctas in (0, 2, 3, 4):
+    _lib.lib().cdll.npb_spmv_dia_set_dot_ctas(ctas)
+    tj = timeit(lambda: _call('npb_spmv_dia_jacobi_dot', n, n, len(offs), offp, vals, ld, x, b, dinv, 0.67, y, dot, red))
+    tc = timeit(lambda: _call('npb_dia_cg_dir', n, len(offs), offp, vals, ld, x, rz[0:], rz[1:], 0, p, q, dot, red))
+    print('%2d CTAs/SM: jacobi + dot %.1f us (%.0f GB/s)   cg direction (p, q, p.q) %.1f us (%.0f GB/s)' % (
+        ctas, tj, (4.0 * len(offs) * n + 32.0 * n) / tj / 1e3, tc, (4.0 * len(offs) * n + 40.0 * n) / tc / 1e3))
