@@ -368,6 +368,29 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
                void* work, int64_t work_bytes, npb_krylov_info* info,
                void* stream);
 
+/* BiCGStab, right-preconditioned, same callbacks and stopping rule (true residual) as
+ * npb_fgmres: short recurrences, 8 work vectors; for Jacobians with a full diagonal
+ * (test/euler_kec.py, test/navierstokes.py at moderate CFL).  info->restarts counts the
+ * confirmations of the recurrence residual against the operator. */
+int64_t npb_bicgstab_workspace_bytes(int64_t n);
+int npb_bicgstab(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
+                 int maxiter, double rtol, double atol, void* work, int64_t work_bytes,
+                 npb_krylov_info* info, void* stream);
+/* Block-Jacobi preconditioner: the unknowns of block c are rows c * cs + k * ks, k < bs <= 8
+ * (cs = 1, ks = nblk: the reference's variable-major state arrays w[k, i, j]; cs = bs, ks = 1:
+ * interleaved).  Setup inverts the bs x bs diagonal blocks (dinv: bs * bs * nblk doubles,
+ * *info [device] = singular blocks, replaced by the identity); apply is an npb_apply_fn. */
+typedef struct npb_block_jacobi {        /* [host] ctx of npb_block_jacobi_apply_cb */
+    int64_t nblk;
+    int32_t bs, pad;
+    int64_t cs, ks;
+    const double* dinv;
+} npb_block_jacobi;
+int npb_block_jacobi_setup(int64_t nblk, int bs, int64_t cs, int64_t ks, const int32_t* indptr,
+                           const int32_t* indices, const double* data, double* dinv,
+                           int32_t* info, void* stream);
+int npb_block_jacobi_apply_cb(void* ctx, const double* x, double* y, void* stream);
+
 /* ---- S3: algebraic multigrid + least-squares-commutator preconditioner --
  * Setup pieces (device): diagonal extraction, MIS aggregation, dense inverse
  * of the coarsest operator.  Solve phase: npb_amg_vcycle, and the two

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
-SRCS="capi.cu scan.cu assembly.cu coo.cu krylov.cu gmres.cu bandlu.cu amg.cu dist.cu spgemm.cu blocktri.cu"
+SRCS="capi.cu scan.cu assembly.cu coo.cu krylov.cu gmres.cu bicgstab.cu bandlu.cu amg.cu dist.cu spgemm.cu blocktri.cu"
 mkdir -p build
 OBJS=""
 for f in $SRCS; do

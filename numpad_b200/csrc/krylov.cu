@@ -1102,7 +1102,7 @@ int npb_spmv_set_default_tma(int on) {
 // stages, 2 CTAs/SM; 1: 2304 x 3, 2; 2: 2304 x 2, 3; 3: 1536 x 3, 4); returns the old one
 int npb_spmv_set_tma_geometry(int g) {
     const int old = npb_tma_geometry;
-    if (g >= -1 && g <= 3) npb_tma_geometry = g;
+    if (g >= -1 && g <= 4) npb_tma_geometry = g;
     return old;
 }
 

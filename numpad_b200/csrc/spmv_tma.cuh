@@ -290,8 +290,8 @@ static inline int tma_geometry_for(double mean) {
     if (npb_tma_geometry >= 0) return npb_tma_geometry;
     return (mean <= 4.5 || mean >= 20.0) ? 2 : 0;
 }
-static inline int tma_cap(int g) { return g == 0 ? 3072 : (g == 3 ? 1536 : 2304); }
-static inline int tma_ctas(int g) { return g == 2 ? 3 : (g == 3 ? 4 : 2); }
+static inline int tma_cap(int g) { return (g == 0 || g == 4) ? 3072 : (g == 3 ? 1536 : 2304); }
+static inline int tma_ctas(int g) { return (g == 2 || g == 4) ? 3 : (g == 3 ? 4 : 2); }
 // rows below which the persistent grid cannot be filled twice over
 static inline int64_t tma_min_rows(double mean) {
     const int g = tma_geometry_for(mean);
@@ -371,6 +371,7 @@ static int spmv_tma_dispatch(int64_t nrows, int64_t nnz, const int32_t* ptr, con
         case 1: return spmv_tma_dispatch_g<tm_geom<2304, 3, 2>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
         case 2: return spmv_tma_dispatch_g<tm_geom<2304, 2, 3>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
         case 3: return spmv_tma_dispatch_g<tm_geom<1536, 3, 4>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
+        case 4: return spmv_tma_dispatch_g<tm_geom<3072, 2, 3>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
         default: return spmv_tma_dispatch_g<tm_geom<3072, 3, 2>, T>(nrows, nnz, ptr, idx, dat, x, e, y, st);
     }
 }

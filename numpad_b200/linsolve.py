@@ -21,6 +21,10 @@ from ._dev import DevCsr, device, stream_ptr, _empty
 # knobs (also settable through solve(..., linear_options={...}))
 DEFAULTS = dict(rtol=1e-12, atol=0.0, restart=100, maxiter=600, precond='auto',
                 verbose=False,
+                # Krylov method of the preconditioned solves: 'fgmres' (flexible GMRES, csrc/gmres.cu)
+                # or 'bicgstab' (csrc/bicgstab.cu; not for the saddle-point preconditioners, whose
+                # inner CG makes them non-linear); precond 'block-jacobi' takes block=(bs, layout)
+                krylov='fgmres', block=(4, 'strided'),
                 # multi-GPU: owner[i] = rank of unknown i.  When set and torch.distributed runs
                 # with more than one rank, saddle-point systems too large for the direct solver
                 # are solved row-sharded over the ranks (shard.py); every rank calls solve()
@@ -113,6 +117,45 @@ def fgmres(A, b, x0=None, precond=None, rtol=1e-12, atol=0.0, restart=60, maxite
                rnorm0=info.rnorm0, rnorm=info.rnorm)
     if rc not in (0, -5, -4):
         raise RuntimeError('npb_fgmres failed (%d): %s' % (rc, L.last_error()))
+    return x, res
+
+
+def bicgstab(A, b, x0=None, precond=None, rtol=1e-12, atol=0.0, maxiter=3000, allreduce_c=None,
+             matvec_c=None):
+    """Solve A x = b on the device with right-preconditioned BiCGStab (csrc/bicgstab.cu); same
+    conventions as fgmres().  The preconditioner must be a fixed linear operator."""
+    L = _lib.lib()
+    n = int(b.numel())
+    x = torch.zeros(n, dtype=torch.float64, device=device()) if x0 is None else x0.clone()
+    ops = KrylovOps()
+    keep = []
+    if matvec_c is not None:
+        ops.matvec, ops.matvec_ctx = matvec_c
+    else:
+        A = A.materialized()
+        view = _csr_view(A)
+        keep += [A, view]
+        ops.matvec = L.csr_matvec_cb_addr
+        ops.matvec_ctx = ctypes.addressof(view)
+    if precond is not None and hasattr(precond, 'c_apply'):
+        keep.append(precond)
+        ops.precond, ops.precond_ctx = precond.c_apply, precond.c_ctx
+    elif precond is not None:
+        cb = _lib.APPLY_FN(_wrap_apply(precond, n))
+        keep.append(cb)
+        ops.precond = ctypes.cast(cb, ctypes.c_void_p).value
+    if allreduce_c is not None:
+        ops.allreduce, ops.allreduce_ctx = allreduce_c
+    wbytes = L.cdll.npb_bicgstab_workspace_bytes(n)
+    work = _empty(wbytes, torch.uint8)
+    info = KrylovInfo()
+    rc = L.cdll.npb_bicgstab(n, ctypes.addressof(ops), b.data_ptr(), x.data_ptr(), int(maxiter),
+                             float(rtol), float(atol), work.data_ptr(), wbytes,
+                             ctypes.addressof(info), stream_ptr())
+    res = dict(status=rc, iters=info.iters, restarts=info.restarts, bnorm=info.bnorm,
+               rnorm0=info.rnorm0, rnorm=info.rnorm)
+    if rc not in (0, -5, -4):
+        raise RuntimeError('npb_bicgstab failed (%d): %s' % (rc, L.last_error()))
     return x, res
 
 
@@ -278,7 +321,7 @@ def solve(A, b, transpose=False, **opts):
         if x is not None:
             return x
         o['precond'] = 'lsc-robust' if bool((_pc.diagonal(A) == 0).any()) else 'jacobi'
-    M, method = _pc.build(A, o['precond'])
+    M, method = _pc.build(A, o['precond'], block=o['block'])
     first_try = method in ('fgmres+lsc', 'fgmres+amg')
     t_setup = _now() - t0
     if method == 'direct':
@@ -302,8 +345,12 @@ def solve(A, b, transpose=False, **opts):
     # cycles will not: fail fast and let the robust retry below take over
     maxit = min(o['maxiter'], 2 * o['restart']) if first_try else \
         (max(o['maxiter'], 2000) if method == 'fgmres+lsc-robust' else o['maxiter'])
-    x, res = fgmres(A, b, precond=pc, rtol=o['rtol'],
-                    atol=o['atol'], restart=min(o['restart'], n), maxiter=maxit)
+    if o['krylov'] == 'bicgstab' and not method.startswith('fgmres+lsc'):
+        x, res = bicgstab(A, b, precond=pc, rtol=o['rtol'], atol=o['atol'], maxiter=maxit)
+        method = method.replace('fgmres', 'bicgstab').replace('gmres', 'bicgstab')
+    else:
+        x, res = fgmres(A, b, precond=pc, rtol=o['rtol'],
+                        atol=o['atol'], restart=min(o['restart'], n), maxiter=maxit)
     res['method'] = method
     res['setup_ms'] = 1e3 * t_setup
     res['krylov_ms'] = 1e3 * (_now() - t0)

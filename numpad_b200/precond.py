@@ -12,6 +12,8 @@ build(A, kind) -> (M, method):
              V-cycle; the automatic retry when 'lsc' stagnates or diverges
              (convection-dominated Jacobians, where Jacobi smoothing diverges) when the
              block-tridiagonal direct solve does not fit
+  'jacobi' / 'block-jacobi' : diagonal / bs x bs block-diagonal scaling (full-diagonal Jacobians:
+             Euler / Navier-Stokes at moderate CFL), with FGMRES or BiCGStab (linsolve 'krylov')
   'btlu'   : block-tridiagonal direct solve over the level sets of the matrix graph
              (blocktri.py): the robust retry whenever its dense blocks fit in HBM
   'auto'   : picks from the size and structure of A
@@ -123,6 +125,37 @@ class JacobiPreconditioner:
         return 'Jacobi'
 
 
+class _BlockJacobiCtx(ctypes.Structure):
+    _fields_ = [('nblk', ctypes.c_int64), ('bs', ctypes.c_int32), ('pad', ctypes.c_int32),
+                ('cs', ctypes.c_int64), ('ks', ctypes.c_int64), ('dinv', ctypes.c_void_p)]
+
+
+class BlockJacobiPreconditioner:
+    """z = blockdiag(A)^-1 r with bs x bs blocks (bs <= 8) as a C callback (csrc/bicgstab.cu).
+    layout 'strided': block c = rows c + k * (n / bs) -- the reference's variable-major state
+    arrays w[k, i, j] (test/euler_kec.py: the 4 conserved variables of a cell);
+    'interleaved': rows c * bs + k."""
+
+    def __init__(self, A, bs=4, layout='strided'):
+        A = A.materialized()
+        n = A.shape[0]
+        if n % bs:
+            raise ValueError('block size %d does not divide n = %d' % (bs, n))
+        nblk = n // bs
+        cs, ks = (1, nblk) if layout == 'strided' else (bs, 1)
+        self.dinv = _empty(bs * bs * nblk, torch.float64)
+        info = _empty(1, torch.int32)
+        _call('npb_block_jacobi_setup', nblk, bs, cs, ks, A.indptr, A.indices, A.data, self.dinv, info)
+        self.singular_blocks = int(info.item())
+        self.ctx = _BlockJacobiCtx(nblk, bs, 0, cs, ks, self.dinv.data_ptr())
+        self.c_apply = ctypes.cast(_lib.lib().cdll.npb_block_jacobi_apply_cb, ctypes.c_void_p).value
+        self.c_ctx = ctypes.addressof(self.ctx)
+        self.bs, self.layout = bs, layout
+
+    def describe(self):
+        return 'block Jacobi (%d x %d, %s)' % (self.bs, self.bs, self.layout)
+
+
 def direct_feasible(A):
     if A.shape[0] > 200000:
         return False
@@ -152,7 +185,7 @@ def forget():
     _last['lsc'] = None
 
 
-def build(A, kind='auto'):
+def build(A, kind='auto', block=(4, 'strided')):
     """-> (preconditioner object or None, method name)"""
     if kind == 'auto':
         if direct_feasible(A):
@@ -175,4 +208,6 @@ def build(A, kind='auto'):
         return amg.AmgPreconditioner(A, theta=0.25, nu=2), 'fgmres+amg'
     if kind == 'jacobi':
         return JacobiPreconditioner(A), 'fgmres+jacobi'
+    if kind == 'block-jacobi':
+        return BlockJacobiPreconditioner(A, *block), 'fgmres+block-jacobi'
     raise ValueError('unknown preconditioner %r' % kind)

@@ -82,13 +82,13 @@ def test_struct_layouts_match_the_header(tmp_path):
     import shutil
     if shutil.which('gcc') is None:
         pytest.skip('gcc unavailable')
-    from numpad_b200 import amg
+    from numpad_b200 import amg, precond
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = [('npb_halo', amg.Halo), ('npb_csr_mat', amg.CsrMat), ('npb_amg_level', amg.AmgLevel),
              ('npb_amg', amg.AmgStruct), ('npb_amg_precond', amg.AmgPrecondStruct),
              ('npb_lsc', amg.LscStruct), ('npb_csr_view', _lib.CsrView),
              ('npb_krylov_ops', _lib.KrylovOps), ('npb_krylov_info', _lib.KrylovInfo),
-             ('npb_scales', _lib.Scales)]
+             ('npb_scales', _lib.Scales), ('npb_block_jacobi', precond._BlockJacobiCtx)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "numpad_b200.h"', 'int main(void) {']
     for name, cls in pairs:
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

@@ -14,12 +14,16 @@ ap.add_argument('--grid', type=int, default=2048)
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--f32three', type=int, default=-1)
 ap.add_argument('--coarse-max', type=int, default=0)
+ap.add_argument('--f32-min-rows', type=int, default=-1)
 a = ap.parse_args()
 if a.f32three >= 0:
     _lib.lib().cdll.npb_spmv_set_tma_f32_three(a.f32three)
 if a.coarse_max:
     from numpad_b200 import amg
     amg.COARSE_MAX = a.coarse_max
+if a.f32_min_rows >= 0:
+    from numpad_b200 import amg as _amg
+    _amg.F32_MIN_ROWS = a.f32_min_rows
 P = CavityProblem(npd, a.grid); u0 = P.fixed_state()
 u = npd.array(u0.copy()); res = P.residual(u, npd.array(u0), 1.0, 0)
 J = npd.diff_dev(res, u).materialized(); b = res._dev.reshape(-1).contiguous()
