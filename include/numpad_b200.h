@@ -235,6 +235,17 @@ int npb_spmv_dia_set_rows(int rows_per_thread);      /* tuning switch (1 or 2), 
 int npb_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
                  int64_t ld, const double* x, int mode, const double* b, const double* dinv,
                  double omega, double* y, void* stream);
+/* hybrid image: diagonals + an ELL part (width <= 8, column-major like the diagonals) for the
+ * entries on none of the offsets -- operators most of whose entries are on a few diagonals (the
+ * momentum block of the cavity: 5 of 9 per row).  npb_csr_dia_remainder gives the ELL width. */
+int npb_csr_dia_remainder(int64_t nrows, const int32_t* indptr, const int32_t* indices, int ndiag,
+                          const int32_t* offsets, int32_t* maxw, void* stream);
+int npb_csr_to_hyb(int64_t nrows, int64_t ncols, const int32_t* indptr, const int32_t* indices,
+                   const double* data, int ndiag, const int32_t* offsets, float* vals, int64_t ld,
+                   int ell_w, int32_t* ell_idx, float* ell_val, int64_t* bad, void* stream);
+int npb_spmv_hyb(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
+                 int64_t ld, int ell_w, const int32_t* ell_idx, const float* ell_val, const double* x,
+                 int mode, const double* b, const double* dinv, double omega, double* y, void* stream);
 /* fused kernels of the preconditioned CG on a diagonal-storage operator (pressure solves of the
  * LSC preconditioner): the Jacobi sweep that ends a multigrid cycle also returns b . y; the
  * direction update p <- z + beta p, q <- L z + beta q (= L p) and p . q are one kernel
@@ -426,6 +437,9 @@ typedef struct npb_csr_mat {
                                        ndiag <= 8 constant offsets col - row; preferred over CSR */
     int32_t ndiag, dia_ld;          /* dia_ld: floats between consecutive diagonals (>= nrows) */
     int32_t dia_off[8];
+    const int32_t* ell_idx;         /* hybrid image (ell_w > 0): the entries on none of the diagonals, */
+    const float* ell_val;           /* slot k of row r at [k * dia_ld + r] */
+    int32_t ell_w, pad2;
 } npb_csr_mat;
 
 typedef struct npb_amg_level {      /* [host] */

@@ -30,7 +30,9 @@ class CsrMat(ctypes.Structure):
                 ('indptr', ctypes.c_void_p), ('indices', ctypes.c_void_p),
                 ('data', ctypes.c_void_p), ('halo', Halo), ('data32', ctypes.c_void_p),
                 ('dia_vals', ctypes.c_void_p), ('ndiag', ctypes.c_int32), ('dia_ld', ctypes.c_int32),
-                ('dia_off', ctypes.c_int32 * 8)]
+                ('dia_off', ctypes.c_int32 * 8),
+                ('ell_idx', ctypes.c_void_p), ('ell_val', ctypes.c_void_p),
+                ('ell_w', ctypes.c_int32), ('pad2', ctypes.c_int32)]
 
 
 class AmgLevel(ctypes.Structure):
@@ -96,15 +98,20 @@ def f32_values(A):
 # Laplacian L = -D G of the cavity: 5) are also kept in diagonal storage (fp32, no column
 # indices, coalesced reads of x instead of gathers): csrc/krylov.cu k_spmv_dia.  0 disables.
 DIA_MIN_ROWS = 200000
+HYB_IMAGES = True       # also the hybrid (diagonals + ELL remainder) images, see dia_image
 _dia_cache = {}
 
 
 def dia_image(A):
-    """-> (offsets list, vals float32[ndiag * ld], ld) or None.  The candidate offsets come from a
-    strided sample of the entries; the conversion kernel verifies EVERY entry against them."""
+    """-> (offsets list, vals float32[ndiag * ld], ld, ell) or None; ell = None for a pure
+    diagonal-storage image, else (width, idx int32[width * ld], val float32[width * ld]) -- the
+    hybrid image of an operator MOST of whose entries sit on a few diagonals (the momentum block
+    of the cavity: 5 of 9 per row on 7 diagonals, 4 cross-coupling entries with drifting offsets).
+    The candidate offsets come from a strided sample of the entries; the conversion kernel checks
+    EVERY entry against them."""
     n = A.shape[0]
     if (not DIA_MIN_ROWS or n < DIA_MIN_ROWS or A.shape[0] != A.shape[1] or A.nnz == 0
-            or A.nnz > 8 * n):
+            or A.nnz > 16 * n):
         return None
     key = (A.data.data_ptr(), A.nnz)
     hit = _dia_cache.get(key)
@@ -112,18 +119,40 @@ def dia_image(A):
         return hit[1]
     import weakref
     step = max(1, A.nnz // 200000)
-    offs = torch.unique((A.indices[::step].to(torch.int64) - A.rows()[::step].to(torch.int64)))
+    d = (A.indices[::step].to(torch.int64) - A.rows()[::step].to(torch.int64))
+    offs, cnt = torch.unique(d, return_counts=True)
     out = None
-    if 1 <= offs.numel() <= 8 and 4.0 * offs.numel() * n < 0.8 * (8.0 * A.nnz + 4.0 * n):
+    csr_bytes = 8.0 * A.nnz + 4.0 * n
+    bad = _empty(1, torch.int64)
+    if 1 <= offs.numel() <= 8 and 4.0 * offs.numel() * n < 0.8 * csr_bytes:
         off_list = [int(v) for v in offs.tolist()]
         off_h = (ctypes.c_int32 * 8)(*(off_list + [0] * (8 - len(off_list))))
         ld = (n + 31) // 32 * 32                     # every diagonal 128-byte aligned
         vals = _empty(len(off_list) * ld, torch.float32)
-        bad = _empty(1, torch.int64)
         _call('npb_csr_to_dia', n, A.indptr, A.indices, A.data, len(off_list),
               ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, bad)
         if int(bad.item()) == 0:
-            out = (off_list, vals, ld)
+            out = (off_list, vals, ld, None)
+    elif HYB_IMAGES and offs.numel() > 8:
+        # diagonals that hold an entry in at least a quarter of the rows (as the sample sees it)
+        rows_in_sample = d.numel() * n / max(A.nnz, 1)
+        strong = offs[cnt.to(torch.float64) >= 0.25 * rows_in_sample]
+        if 1 <= strong.numel() <= 8:
+            off_list = [int(v) for v in strong.tolist()]
+            nd = len(off_list)
+            off_h = (ctypes.c_int32 * 8)(*(off_list + [0] * (8 - nd)))
+            offp = ctypes.cast(off_h, ctypes.c_void_p).value
+            maxw = _empty(1, torch.int32)
+            _call('npb_csr_dia_remainder', n, A.indptr, A.indices, nd, offp, maxw)
+            w = int(maxw.item())
+            if 1 <= w <= 8 and (4.0 * nd + 8.0 * w) * n < 0.85 * csr_bytes:
+                ld = (n + 31) // 32 * 32
+                vals = _empty(nd * ld, torch.float32)
+                eidx, eval_ = _empty(w * ld, torch.int32), _empty(w * ld, torch.float32)
+                _call('npb_csr_to_hyb', n, A.shape[1], A.indptr, A.indices, A.data, nd, offp, vals, ld,
+                      w, eidx, eval_, bad)
+                if int(bad.item()) == 0:
+                    out = (off_list, vals, ld, (w, eidx, eval_))
     if len(_dia_cache) > 16:
         _dia_cache.clear()
     _dia_cache[key] = (weakref.ref(A.data), out)
@@ -140,11 +169,14 @@ def csr_mat(A, keep=None):
     if keep is not None:
         d = dia_image(A)
         if d is not None:
-            offs, vals, ld = d
+            offs, vals, ld, ell = d
             keep.append(vals)
             m.dia_vals, m.ndiag, m.dia_ld = vals.data_ptr(), len(offs), ld
             for k, o in enumerate(offs):
                 m.dia_off[k] = o
+            if ell is not None:
+                keep += [ell[1], ell[2]]
+                m.ell_w, m.ell_idx, m.ell_val = ell[0], ell[1].data_ptr(), ell[2].data_ptr()
         v = f32_values(A) if d is None else None
         if v is not None:
             keep.append(v)

@@ -35,7 +35,8 @@ int npb_dot_multi_launch(int64_t n, int k, const double* V, int64_t ld, const do
 int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
                         const int32_t* offsets_host, const float* vals, const double* x, int mode,
                         const double* b, const double* dinv, double omega, double* y,
-                        cudaStream_t st, double* dot_out, void* red);
+                        cudaStream_t st, double* dot_out, void* red, int ell_w, const int32_t* ell_idx,
+                        const float* ell_val);
 int npb_dia_cg_dir_launch(int64_t nrows, int ndiag, int64_t ld, const int32_t* offsets_host,
                           const float* vals, const double* z, const double* rz_new,
                           const double* rz_old, int first, double* p, double* q, double* pq_out,
@@ -515,6 +516,11 @@ struct npb_csr_mat {
     const float* dia_vals;
     int32_t ndiag, dia_ld;     // dia_ld: floats between consecutive diagonals (>= nrows)
     int32_t dia_off[8];
+    // hybrid image (ell_w > 0): the entries on none of the diagonals in an ELL part of that
+    // width, slot k of row r at [k * dia_ld + r]
+    const int32_t* ell_idx;
+    const float* ell_val;
+    int32_t ell_w, pad2;
 };
 
 // y = epilogue(M x): 0: Mx  1: b - Mx  2: b + Mx  3: x + omega dinv (b - Mx); a sharded
@@ -525,7 +531,7 @@ static inline int spmv_mat(const npb_csr_mat& M, const double* x, const double* 
                            double omega = 0.0, double* dot_out = nullptr, void* red = nullptr) {
     if (M.dia_vals && !M.halo.dist)
         return npb_spmv_dia_launch(M.nrows, M.ncols, M.ndiag, M.dia_ld, M.dia_off, M.dia_vals, x, mode, b,
-                                   dinv, omega, y, st, dot_out, red);
+                                   dinv, omega, y, st, dot_out, red, M.ell_w, M.ell_idx, M.ell_val);
     if (M.halo.dist) {
         npb_halo h = M.halo;
         const double* xh = nullptr;
@@ -673,7 +679,7 @@ static int amg_cycle(const npb_amg* h, int l, cycle_bufs& w, cudaStream_t st) {
 // diagonal-storage operator on one GPU (the preconditioned CG of the pressure solves)
 static bool amg_cycle_can_dot(const npb_amg* h) {
     const npb_csr_mat& A0 = h->levels[0].A;
-    return h->nlevels > 1 && h->nu_post >= 1 && A0.dia_vals && !A0.halo.dist && !h->dist;
+    return h->nlevels > 1 && h->nu_post >= 1 && A0.dia_vals && A0.ell_w == 0 && !A0.halo.dist && !h->dist;
 }
 
 static int amg_vcycle_dot(const npb_amg* h, const double* b, double* x, double* dot_out, void* red,
@@ -719,7 +725,7 @@ static int amg_pcg(const npb_amg* h, const npb_csr_mat& A, int k, const double* 
     // one GPU, diagonal-storage operator: r . z comes out of the last sweep of the cycle, and
     // direction update, operator product and p . q are one kernel (q = L z + beta q)
     const bool fuse_rz = amg_cycle_can_dot(h);
-    const bool fuse_dir = A.dia_vals && !A.halo.dist && !h->dist && A.nrows == A.ncols;
+    const bool fuse_dir = A.dia_vals && A.ell_w == 0 && !A.halo.dist && !h->dist && A.nrows == A.ncols;
     for (int i = 0; i < k; ++i) {
         double* rz_new = scal + (i & 1);
         double* rz_old = scal + ((i + 1) & 1);
@@ -797,9 +803,9 @@ struct npb_lsc {
 
 // the host structs above are declared a second time in include/numpad_b200.h (and mirrored
 // with ctypes, tests/test_abi.py): a one-sided edit must not compile
-static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 168, "npb_csr_mat layout");
-static_assert(sizeof(npb_amg_level) == 584 && sizeof(npb_amg) == 56, "npb_amg layout");
-static_assert(sizeof(npb_amg_precond) == 200 && sizeof(npb_lsc) == 888, "npb_lsc layout");
+static_assert(sizeof(npb_halo) == 64 && sizeof(npb_csr_mat) == 192, "npb_csr_mat layout");
+static_assert(sizeof(npb_amg_level) == 656 && sizeof(npb_amg) == 56, "npb_amg layout");
+static_assert(sizeof(npb_amg_precond) == 224 && sizeof(npb_lsc) == 984, "npb_lsc layout");
 
 // y = d .* x as an npb_apply_fn (Jacobi preconditioner; ctx = npb_diag_ctx)
 struct npb_diag_ctx { int64_t n; const double* d; };

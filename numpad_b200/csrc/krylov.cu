@@ -699,12 +699,18 @@ __device__ __forceinline__ void grid_sum_to(double v, double* __restrict__ parti
 
 // DOT: the Jacobi epilogue (mode 3) also returns b . y (the r . z of a preconditioned CG step
 // whose preconditioner ends with this sweep)
-template <int ND, int R, bool DOT, bool EXACT>
+// NW > 0: hybrid image -- the entries that are on none of the diagonals sit in an ELL part of
+// width ell_w <= NW (column-major like the diagonals: ell_idx / ell_val [k * ld + r], unused slots
+// hold a zero value and a valid column): the momentum block of the cavity has 5 of its 9 entries
+// per row on 7 diagonals and 4 cross-coupling entries whose offsets drift with the grid row --
+// 4 gathers per row instead of 9, and no row pointers.
+template <int ND, int R, bool DOT, bool EXACT, int NW>
 __global__ void __launch_bounds__(TPB)
 k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs,
            const float* __restrict__ vals, const double* __restrict__ x, spmv_epi e,
            double* __restrict__ y, double* __restrict__ partial, unsigned int* __restrict__ ticket,
-           double* __restrict__ dot_out) {
+           double* __restrict__ dot_out, int ell_w, const int32_t* __restrict__ ell_idx,
+           const float* __restrict__ ell_val) {
     double dacc = 0.0;
     for (int64_t base = (int64_t)blockIdx.x * (TPB * R); base < nrows;
          base += (int64_t)gridDim.x * (TPB * R)) {
@@ -712,6 +718,23 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs
         float v[R][ND];
         double xv[R][ND];
         double bv[R], dv[R], xr[R];
+        int32_t ei[R][NW > 0 ? NW : 1];
+        float ev[R][NW > 0 ? NW : 1];
+        if (NW > 0) {
+            // the column indices of the ELL part first: their gathers depend on them
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    ei[j][k] = 0; ev[j][k] = 0.0f;
+                    if (k < ell_w && r < nrows) {
+                        ei[j][k] = __ldcs(ell_idx + (int64_t)k * ld + r);
+                        ev[j][k] = __ldcs(ell_val + (int64_t)k * ld + r);
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
@@ -721,6 +744,13 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs
             if (live && e.mode >= 1) bv[j] = __ldg(e.b + r);
             if (live && e.mode == 3) { dv[j] = __ldg(e.dinv + r); xr[j] = __ldg(x + r); }
         }
+        double ex[R][NW > 0 ? NW : 1];
+        if (NW > 0) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int k = 0; k < NW; ++k) ex[j][k] = (k < ell_w) ? __ldg(x + ei[j][k]) : 0.0;
+        }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int64_t r = base + (int64_t)j * TPB + threadIdx.x;
@@ -728,6 +758,10 @@ k_spmv_dia(int64_t nrows, int64_t ncols, int ndiag, int64_t ld, dia_offsets offs
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < ND; ++k) s = fma((double)v[j][k], xv[j][k], s);
+            if (NW > 0) {
+#pragma unroll
+                for (int k = 0; k < NW; ++k) s = fma((double)ev[j][k], ex[j][k], s);
+            }
             double out;
             switch (e.mode) {
                 case 0: out = s; break;
@@ -796,22 +830,53 @@ k_dia_cg_dir(int64_t nrows, int ndiag, int64_t ld, dia_offsets offs, const float
 // epilogue of the 2048^2 pressure operator (one row: 4.5; tools/dia_bench.py)
 static int npb_dia_rows = 2;
 
-// CSR -> DIA image: vals[k * nrows + r] = entry of row r on offset offs[k] (rows are zero-filled
-// by the caller); *bad counts entries on an offset that is not in the table
+// CSR -> DIA image: vals[k * ld + r] = entry of row r on offset offs[k] (zero-filled by the
+// caller).  Entries on other offsets: ell_w == 0 -> counted in *bad; ell_w > 0 -> they go to the ELL
+// part (slot order = column order; more than ell_w of them in a row count as bad).  Unused ELL
+// slots: value 0, column min(r, ncols - 1).
 __global__ void __launch_bounds__(TPB)
-k_csr_to_dia(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+k_csr_to_dia(int64_t nrows, int64_t ncols, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
              const double* __restrict__ dat, int ndiag, int64_t ld, dia_offsets offs,
-             float* __restrict__ vals, int64_t* __restrict__ bad) {
+             float* __restrict__ vals, int64_t* __restrict__ bad, int ell_w,
+             int32_t* __restrict__ ell_idx, float* __restrict__ ell_val) {
     const int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (r >= nrows) return;
+    int w = 0;
     for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
         const int32_t o = idx[k] - (int32_t)r;
         int hit = -1;
         for (int d = 0; d < ndiag; ++d)
             if (offs.off[d] == o) hit = d;
         if (hit >= 0) vals[(int64_t)hit * ld + r] = (float)dat[k];
-        else atomicAdd((unsigned long long*)bad, 1ull);
+        else if (w < ell_w) {
+            ell_idx[(int64_t)w * ld + r] = idx[k];
+            ell_val[(int64_t)w * ld + r] = (float)dat[k];
+            ++w;
+        } else atomicAdd((unsigned long long*)bad, 1ull);
     }
+    for (; w < ell_w; ++w) {
+        ell_idx[(int64_t)w * ld + r] = (int32_t)(r < ncols ? r : ncols - 1);
+        ell_val[(int64_t)w * ld + r] = 0.0f;
+    }
+}
+
+// *maxw = largest number of entries of a row that are on none of the offsets
+__global__ void __launch_bounds__(TPB)
+k_dia_remainder(int64_t nrows, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                int ndiag, dia_offsets offs, int32_t* __restrict__ maxw) {
+    const int64_t r = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    int w = 0;
+    if (r < nrows) {
+        for (int32_t k = ptr[r], e = ptr[r + 1]; k < e; ++k) {
+            const int32_t o = idx[k] - (int32_t)r;
+            bool hit = false;
+            for (int d = 0; d < ndiag; ++d) hit |= offs.off[d] == o;
+            w += hit ? 0 : 1;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, d));
+    if ((threadIdx.x & 31) == 0 && w > 0) atomicMax(maxw, w);
 }
 
 #define ST(s) ((cudaStream_t)(s))
@@ -838,9 +903,12 @@ static_assert(DIA_GRID_CAP <= (int64_t)RED_BLOCKS * KC * 2, "DIA dot partials fi
 int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
                         const int32_t* offsets_host, const float* vals, const double* x, int mode,
                         const double* b, const double* dinv, double omega, double* y,
-                        cudaStream_t st, double* dot_out = nullptr, void* red = nullptr) {
+                        cudaStream_t st, double* dot_out = nullptr, void* red = nullptr,
+                        int ell_w = 0, const int32_t* ell_idx = nullptr, const float* ell_val = nullptr) {
     if (nrows <= 0) return NPB_OK;
-    if (ndiag < 1 || ndiag > DIA_MAX || ld < nrows || (dot_out && (mode != 3 || !red))) return NPB_ERR_ARG;
+    if (ndiag < 1 || ndiag > DIA_MAX || ld < nrows || (dot_out && (mode != 3 || !red)) || ell_w < 0 ||
+        ell_w > 8 || (ell_w > 0 && (!ell_idx || !ell_val || dot_out)))
+        return NPB_ERR_ARG;
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets_host[k] : 0;
     spmv_epi e{mode, b, dinv, omega, nullptr, 0x7fffffff, {nullptr, 0, 0, 0}};
@@ -854,12 +922,22 @@ int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
     // exact instantiations for the 3- and 5-point stencils, a bounded generic one otherwise; with
     // the inner product: a persistent grid (the per-block reduction + ticket at the end of
     // thousands of one-round blocks doubled the kernel's time)
-#define NPB_DIA_LAUNCH(ND_, R_, DOT_, EX_) do { \
+#define NPB_DIA_LAUNCH_W(ND_, R_, DOT_, EX_, NW_) do { \
         int64_t g_ = grid; \
-        if (DOT_) { const int64_t c_ = dia_dot_grid(k_spmv_dia<ND_, R_, DOT_, EX_>); if (g_ > c_) g_ = c_; } \
-        k_spmv_dia<ND_, R_, DOT_, EX_><<<(int)g_, TPB, 0, st>>>(nrows, ncols, ndiag, ld, o, vals, x, e, y, pa, ti, dot_out); \
+        if (DOT_) { const int64_t c_ = dia_dot_grid(k_spmv_dia<ND_, R_, DOT_, EX_, NW_>); if (g_ > c_) g_ = c_; } \
+        k_spmv_dia<ND_, R_, DOT_, EX_, NW_><<<(int)g_, TPB, 0, st>>>(nrows, ncols, ndiag, ld, o, vals, x, e, y, pa, ti, dot_out, ell_w, ell_idx, ell_val); \
     } while (0)
-    if (dot_out && R == 2) {
+#define NPB_DIA_LAUNCH(ND_, R_, DOT_, EX_) NPB_DIA_LAUNCH_W(ND_, R_, DOT_, EX_, 0)
+    if (ell_w > 0) {
+        // hybrid image: two rows per thread, ELL width bounded by 4 or 8
+        grid = (nrows + (int64_t)TPB * 2 - 1) / ((int64_t)TPB * 2);
+        if (grid > DIA_GRID_CAP) grid = DIA_GRID_CAP;
+        if (ell_w <= 4) {
+            if (ndiag == 5) NPB_DIA_LAUNCH_W(5, 2, false, true, 4); else if (ndiag == 7) NPB_DIA_LAUNCH_W(7, 2, false, true, 4); else NPB_DIA_LAUNCH_W(8, 2, false, false, 4);
+        } else {
+            if (ndiag == 5) NPB_DIA_LAUNCH_W(5, 2, false, true, 8); else if (ndiag == 7) NPB_DIA_LAUNCH_W(7, 2, false, true, 8); else NPB_DIA_LAUNCH_W(8, 2, false, false, 8);
+        }
+    } else if (dot_out && R == 2) {
         if (ndiag == 3) NPB_DIA_LAUNCH(3, 2, true, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 2, true, true); else NPB_DIA_LAUNCH(8, 2, true, false);
     } else if (dot_out) {
         if (ndiag == 3) NPB_DIA_LAUNCH(3, 1, true, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 1, true, true); else NPB_DIA_LAUNCH(8, 1, true, false);
@@ -869,7 +947,9 @@ int npb_spmv_dia_launch(int64_t nrows, int64_t ncols, int ndiag, int64_t ld,
         if (ndiag == 3) NPB_DIA_LAUNCH(3, 1, false, true); else if (ndiag == 5) NPB_DIA_LAUNCH(5, 1, false, true); else NPB_DIA_LAUNCH(8, 1, false, false);
     }
 #undef NPB_DIA_LAUNCH
+#undef NPB_DIA_LAUNCH_W
     NPB_COUNT_LAUNCH();
+    NPB_COUNT_BYTES(8.0 * ell_w * nrows);
     NPB_COUNT_BYTES(4.0 * ndiag * nrows + 8.0 * nrows * (2 + (mode >= 1) + 2 * (mode == 3)));
     NPB_CHECK_LAUNCH("spmv_dia");
     return NPB_OK;
@@ -1160,10 +1240,59 @@ int npb_csr_to_dia(int64_t nrows, const int32_t* indptr, const int32_t* indices,
     NPB_CUDA(cudaMemsetAsync(vals, 0, sizeof(float) * (size_t)ndiag * (size_t)ld, ST(stream)));
     dia_offsets o;
     for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets[k] : 0;
-    k_csr_to_dia<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, data, ndiag, ld, o, vals, bad);
+    k_csr_to_dia<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, nrows, indptr, indices, data, ndiag, ld, o,
+                                                                vals, bad, 0, nullptr, nullptr);
     NPB_COUNT_LAUNCH();
     NPB_CHECK_LAUNCH("csr_to_dia");
     return NPB_OK;
+}
+
+// hybrid image (diagonals + ELL remainder) of an operator most of whose entries sit on `ndiag`
+// constant offsets.  npb_csr_dia_remainder: *maxw (device, reset here) = the largest number of
+// entries of a row on none of the offsets = the ELL width the image needs.  npb_csr_to_hyb: fills
+// the diagonals (as npb_csr_to_dia) and the ELL part, ell_idx / ell_val: ell_w * ld entries, slot k
+// of row r at [k * ld + r]; *bad = entries that fit neither.
+int npb_csr_dia_remainder(int64_t nrows, const int32_t* indptr, const int32_t* indices, int ndiag,
+                          const int32_t* offsets, int32_t* maxw, void* stream) {
+    if (ndiag < 1 || ndiag > DIA_MAX || !maxw) return NPB_ERR_ARG;
+    NPB_CUDA(cudaMemsetAsync(maxw, 0, sizeof(int32_t), ST(stream)));
+    if (nrows <= 0) return NPB_OK;
+    dia_offsets o;
+    for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets[k] : 0;
+    k_dia_remainder<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, indptr, indices, ndiag, o, maxw);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_dia_remainder");
+    return NPB_OK;
+}
+
+int npb_csr_to_hyb(int64_t nrows, int64_t ncols, const int32_t* indptr, const int32_t* indices,
+                   const double* data, int ndiag, const int32_t* offsets, float* vals, int64_t ld,
+                   int ell_w, int32_t* ell_idx, float* ell_val, int64_t* bad, void* stream) {
+    if (ndiag < 1 || ndiag > DIA_MAX || !bad || ld < nrows || ell_w < 1 || ell_w > 8 || !ell_idx || !ell_val ||
+        ncols < 1)
+        return NPB_ERR_ARG;
+    NPB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int64_t), ST(stream)));
+    if (nrows <= 0) return NPB_OK;
+    NPB_CUDA(cudaMemsetAsync(vals, 0, sizeof(float) * (size_t)ndiag * (size_t)ld, ST(stream)));
+    dia_offsets o;
+    for (int k = 0; k < DIA_MAX; ++k) o.off[k] = k < ndiag ? offsets[k] : 0;
+    k_csr_to_dia<<<npb_blocks(nrows, TPB), TPB, 0, ST(stream)>>>(nrows, ncols, indptr, indices, data, ndiag, ld, o,
+                                                                vals, bad, ell_w, ell_idx, ell_val);
+    NPB_COUNT_LAUNCH();
+    NPB_CHECK_LAUNCH("csr_to_hyb");
+    return NPB_OK;
+}
+
+// y = epilogue(A x) from a hybrid image (same modes as npb_spmv_epilogue)
+int npb_spmv_hyb(int64_t nrows, int64_t ncols, int ndiag, const int32_t* offsets, const float* vals,
+                 int64_t ld, int ell_w, const int32_t* ell_idx, const float* ell_val, const double* x,
+                 int mode, const double* b, const double* dinv, double omega, double* y, void* stream) {
+    if (mode < 0 || mode > 3 || (mode >= 1 && !b) || (mode == 3 && (!dinv || x == y))) {
+        npb_set_error("spmv_hyb: bad mode / operands");
+        return NPB_ERR_ARG;
+    }
+    return npb_spmv_dia_launch(nrows, ncols, ndiag, ld, offsets, vals, x, mode, b, dinv, omega, y, ST(stream),
+                               nullptr, nullptr, ell_w, ell_idx, ell_val);
 }
 
 // tuning switch: CTAs per SM of the DIA kernels with a fused inner product (0: resident count); returns the old value

@@ -404,6 +404,64 @@ def test_dcgs2_passes(dev, n, k):
         np.testing.assert_allclose(float(nrm.item()), w_new @ w_new, rtol=1e-12)
 
 
+def test_spmv_hybrid_dia_ell_storage(dev):
+    """hybrid image (diagonals + ELL remainder) of an operator most of whose entries sit on a few
+    diagonals: amg.dia_image finds the strong offsets and the ELL width, the conversion places
+    every entry, the SpMV matches scipy for every epilogue; rows with fewer remainder entries than
+    the width and a remainder-free operator (-> pure DIA image) included"""
+    import torch
+    import ctypes
+    from numpad_b200 import amg
+    N = 220
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(N, N))
+    lap = (sp.kron(sp.identity(N), T) + sp.kron(T, sp.identity(N))).tocsr()
+    n = lap.shape[0]
+    rng = np.random.RandomState(5)
+    # remainder: 0..3 entries per row at drifting offsets (like the cross-coupling of the cavity's
+    # momentum block)
+    rows = np.repeat(np.arange(n), 3)
+    drift = (np.arange(n) // N)[rows] + np.tile(np.array([7, 3 * N + 1, -5 * N]), n)
+    cols = rows + drift
+    ok = (cols >= 0) & (cols < n) & (rng.random(rows.size) < 0.8)
+    rem = sp.csr_matrix((rng.standard_normal(ok.sum()), (rows[ok], cols[ok])), shape=(n, n))
+    a = sp.csr_matrix(lap + rem)
+    a.data = a.data.astype(np.float32).astype(np.float64)
+    a.sort_indices()
+    old = amg.DIA_MIN_ROWS
+    amg.DIA_MIN_ROWS = 1000
+    try:
+        A = dev.DevCsr.from_scipy(a)
+        img = amg.dia_image(A)
+        assert img is not None and img[3] is not None
+        offs, vals, ld, (w, eidx, eval_) = img
+        assert sorted(offs) == [-N, -1, 0, 1, N] and 1 <= w <= 3
+        off_h = (ctypes.c_int32 * 8)(*(offs + [0] * (8 - len(offs))))
+        x, b, dinv = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+        t = lambda v: torch.from_numpy(v).to(dev.device())
+        xd, bd, dd = t(x), t(b), t(dinv)
+        ax = a @ x
+        for mode, want in enumerate([ax, b - ax, b + ax, x + 0.7 * dinv * (b - ax)]):
+            y = torch.full((n,), np.nan, dtype=torch.float64, device=dev.device())
+            dev._call('npb_spmv_hyb', n, n, len(offs), ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld,
+                      w, eidx, eval_, xd, mode, bd, dd, 0.7, y)
+            np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=1e-12 * (np.abs(want).max() + 1))
+        keep = []
+        m = amg.csr_mat(A, keep)
+        assert m.ndiag == 5 and m.ell_w == w and m.ell_idx and not m.data32
+        # too narrow an ELL part is reported
+        bad = torch.empty(1, dtype=torch.int64, device=dev.device())
+        if w > 1:
+            dev._call('npb_csr_to_hyb', n, n, A.indptr, A.indices, A.data, len(offs),
+                      ctypes.cast(off_h, ctypes.c_void_p).value, vals, ld, w - 1, eidx, eval_, bad)
+            assert int(bad.item()) > 0
+        # an operator without remainder keeps its pure diagonal image
+        L = dev.DevCsr.from_scipy(sp.csr_matrix(lap))
+        img2 = amg.dia_image(L)
+        assert img2 is not None and img2[3] is None
+    finally:
+        amg.DIA_MIN_ROWS = old
+
+
 @pytest.mark.parametrize('kind', ['mis1', 'mis2'])
 def test_aggregation_properties(dev, kind):
     """MIS aggregation on a 2-D 5-point operator: every node gets an aggregate id in

@@ -15,7 +15,7 @@ M = amg.LscPreconditioner(J)
 L = M.Lm
 n = L.shape[0]
 x = torch.randn(n, dtype=torch.float64, device='cuda'); b = torch.randn_like(x); dinv = torch.rand_like(x); y = torch.empty_like(x)
-offs, vals, ld = amg.dia_image(L)
+offs, vals, ld, _ = amg.dia_image(L)
 off_h = (ctypes.c_int32 * 8)(*(offs + [0] * (8 - len(offs))))
 v32 = L.data.float()
 def timeit(fn, reps=200):
