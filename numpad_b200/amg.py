@@ -98,7 +98,11 @@ def f32_values(A):
 # Laplacian L = -D G of the cavity: 5) are also kept in diagonal storage (fp32, no column
 # indices, coalesced reads of x instead of gathers): csrc/krylov.cu k_spmv_dia.  0 disables.
 DIA_MIN_ROWS = 200000
-HYB_IMAGES = True       # also the hybrid (diagonals + ELL remainder) images, see dia_image
+# also build hybrid (diagonals + ELL remainder) images, see dia_image.  OFF: measured on the momentum
+# block of the 2048^2 cavity (tools/hyb_bench.py), the hybrid kernel takes 212 us per Jacobi sweep
+# against 169 us of the TMA-pipelined fp32 CSR kernel (which already runs at 0.88 of the HBM peak
+# there): fewer gathers, but two dependent load phases per row at 2 CTAs / SM
+HYB_IMAGES = False
 _dia_cache = {}
 
 

@@ -24,6 +24,11 @@ namespace {
 constexpr int SG_THREADS = 256;
 constexpr int SG_ITEMS = 8;
 constexpr int SG_CAP = SG_THREADS * SG_ITEMS;       // partial products per batch
+#ifndef SG_RADIX
+#define SG_RADIX 6
+#endif
+// digits of SG_RADIX bits: the compressed keys of a stencil-like batch have ~18-20 significant bits
+typedef cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double, SG_RADIX> sg_sort_t;
 
 // ub[i] = max(1, sum over entries (i,k) of max(1, nnz(B_k))): products, entries and rows of a
 // batch are all bounded by the sum of ub over its rows
@@ -73,7 +78,7 @@ k_sg_batches(int64_t m, const int32_t* __restrict__ ubptr, int64_t T, int64_t nb
 
 struct sg_smem {
     union {
-        typename cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>::TempStorage sort;
+        typename sg_sort_t::TempStorage sort;
         typename cub::BlockScan<int, SG_THREADS>::TempStorage scan;
         typename cub::BlockReduce<int, SG_THREADS>::TempStorage red;
     } tmp;
@@ -156,7 +161,7 @@ k_sg_numeric(const int32_t* __restrict__ brow, const int32_t* __restrict__ aptr,
         v8[j] = S.val[p];
     }
     __syncthreads();
-    cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double>(S.tmp.sort).Sort(k8, v8, 0, cb + rbits);
+    sg_sort_t(S.tmp.sort).Sort(k8, v8, 0, cb + rbits);
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < SG_ITEMS; ++j) {

@@ -427,8 +427,8 @@ def test_spmv_hybrid_dia_ell_storage(dev):
     a = sp.csr_matrix(lap + rem)
     a.data = a.data.astype(np.float32).astype(np.float64)
     a.sort_indices()
-    old = amg.DIA_MIN_ROWS
-    amg.DIA_MIN_ROWS = 1000
+    old, old_h = amg.DIA_MIN_ROWS, amg.HYB_IMAGES
+    amg.DIA_MIN_ROWS, amg.HYB_IMAGES = 1000, True
     try:
         A = dev.DevCsr.from_scipy(a)
         img = amg.dia_image(A)
@@ -459,7 +459,7 @@ def test_spmv_hybrid_dia_ell_storage(dev):
         img2 = amg.dia_image(L)
         assert img2 is not None and img2[3] is None
     finally:
-        amg.DIA_MIN_ROWS = old
+        amg.DIA_MIN_ROWS, amg.HYB_IMAGES = old, old_h
 
 
 @pytest.mark.parametrize('kind', ['mis1', 'mis2'])
