@@ -152,6 +152,7 @@ int npb_csr_prune_numeric_checked(int64_t nrows, const int32_t* indptr, const in
  * scratch tidx / tval of `total` entries, cnt / tstart[m]; the caller scans cnt into
  * c_indptr, allocates C and calls compact. */
 int npb_spgemm_rows_cap(void);
+int npb_spgemm_set_warp_rows(int on);   /* tuning / test: 0 = rows of <= 512 products stay on the CTA-batched kernel; returns old */
 int64_t npb_spgemm_rows_batches(int64_t total, int64_t max_ub);
 int npb_spgemm_rows_bound(int64_t m, const int32_t* a_indptr, const int32_t* a_indices,
                           const int32_t* b_indptr, int32_t* ub, int32_t* ubptr,

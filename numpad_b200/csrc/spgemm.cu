@@ -25,9 +25,10 @@ constexpr int SG_THREADS = 256;
 constexpr int SG_ITEMS = 8;
 constexpr int SG_CAP = SG_THREADS * SG_ITEMS;       // partial products per batch
 #ifndef SG_RADIX
-#define SG_RADIX 6
+#define SG_RADIX 4
 #endif
-// digits of SG_RADIX bits: the compressed keys of a stencil-like batch have ~18-20 significant bits
+// digits of SG_RADIX bits (6-bit digits need fewer passes over the ~18-20 significant key bits but a
+// larger rank storage: measured 1.2-1.7x SLOWER on the Galerkin products of the 2048^2 cavity)
 typedef cub::BlockRadixSort<unsigned long long, SG_THREADS, SG_ITEMS, double, SG_RADIX> sg_sort_t;
 
 // ub[i] = max(1, sum over entries (i,k) of max(1, nnz(B_k))): products, entries and rows of a
@@ -204,6 +205,139 @@ k_sg_numeric(const int32_t* __restrict__ brow, const int32_t* __restrict__ aptr,
     }
 }
 
+// ---- one warp per row -----------------------------------------------------------------
+// The Galerkin products of the multigrid setup (R (A P)) and most products of the chain rule have
+// SHORT rows: 20..150 partial products.  A CTA-wide radix sort of 2048 of them (above) costs ~10
+// sort passes per batch; here every warp owns one row at a time: the products of the row are
+// expanded into the warp's slice of shared memory (lane e takes entry e of the A row: one round
+// of dependent loads for all entries), the keys (column, position) are sorted in REGISTERS with a
+// bitonic network of shuffles (CAP / 32 keys per lane; the position makes the keys unique, so the
+// order of equal columns is the generation order, as in the stable radix sort), runs are summed in
+// that order by the lane that holds their head, survivors ranked with warp ballots.  Same output contract as
+// k_sg_numeric (tidx / tval at ubptr[row], cnt, tstart), bit-identical results.
+// ascending bitonic sort of 32 * K unique keys held by a warp, element e = r * 32 + lane in register
+// r: partners less than 32 apart are exchanged with shuffles, the others are registers of the same
+// lane (a first version sorted in shared memory: ~0.3 us per compare-exchange round, 118 us for a
+// 512-key row -- every round a dependent load / store pair with two-way bank conflicts)
+template <int K>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&x)[K], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * K; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const int rq = r ^ rj;
+                    if (rq > r) {
+                        const bool up = (((r * 32 + lane) & k) == 0);
+                        const unsigned long long a = x[r], b = x[rq];
+                        if ((a > b) == up) { x[r] = b; x[rq] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, x[r], j);
+                    const bool up = (((r * 32 + lane) & k) == 0);
+                    const bool lower = (lane & j) == 0;
+                    const unsigned long long lo = x[r] < other ? x[r] : other;
+                    const unsigned long long hi = x[r] < other ? other : x[r];
+                    x[r] = (lower == up) ? lo : hi;
+                }
+            }
+        }
+    }
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(256)
+k_sg_rows_warp(int64_t m, const int32_t* __restrict__ aptr, const int32_t* __restrict__ aidx,
+               const double* __restrict__ adat, npb_scales sa, const int32_t* __restrict__ bptr,
+               const int32_t* __restrict__ bidx, const double* __restrict__ bdat, npb_scales sb,
+               const int32_t* __restrict__ ubptr, int prune, int32_t* __restrict__ tidx,
+               double* __restrict__ tval, int32_t* __restrict__ cnt, int32_t* __restrict__ tstart) {
+    extern __shared__ __align__(16) unsigned char sgw_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(sgw_raw) + (size_t)warp * CAP;
+    double* val = reinterpret_cast<double*>(sgw_raw + (size_t)8 * CAP * 8) + (size_t)warp * CAP;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < m; row += nwarps) {
+        const int32_t e0 = aptr[row], ne = aptr[row + 1] - e0;
+        // 1. expansion
+        int count = 0;
+        for (int c0 = 0; c0 < ne; c0 += 32) {
+            const int e = c0 + lane;
+            int32_t b0 = 0, len = 0;
+            double a = 0.0;
+            if (e < ne) {
+                const int32_t k = aidx[e0 + e];
+                a = npb_apply(sa, adat[e0 + e]);
+                b0 = bptr[k];
+                len = bptr[k + 1] - b0;
+            }
+            int off = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, off, d);
+                if (lane >= d) off += t;
+            }
+            const int chunk_total = __shfl_sync(0xffffffffu, off, 31);
+            off = count + off - len;
+            for (int t = 0; t < len; ++t) {
+                const int p = off + t;
+                key[p] = ((unsigned long long)(uint32_t)bidx[b0 + t] << 16) | (unsigned long long)p;
+                val[p] = __dmul_rn(a, npb_apply(sb, bdat[b0 + t]));
+            }
+            count += chunk_total;
+        }
+        __syncwarp();
+        // 2. sort the keys in registers (the values stay where the expansion put them: the low 16
+        // bits of a key are the position of its value)
+        {
+            constexpr int K = CAP / 32;
+            unsigned long long x[K];
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const int p = r * 32 + lane;
+                x[r] = p < count ? key[p] : ~0ull;
+            }
+            warp_bitonic_sort<K>(x, lane);
+#pragma unroll
+            for (int r = 0; r < K; ++r) key[r * 32 + lane] = x[r];
+        }
+        __syncwarp();
+        // 3. run sums by the lane that holds the head, survivors ranked in column order
+        const int64_t t0 = ubptr[row];
+        int kept = 0;
+        for (int p0 = 0; p0 < count; p0 += 32) {
+            const int p = p0 + lane;
+            int keep = 0;
+            double s = 0.0;
+            uint32_t col = 0;
+            if (p < count) {
+                col = (uint32_t)(key[p] >> 16);
+                if (p == 0 || (uint32_t)(key[p - 1] >> 16) != col) {
+                    s = val[(int)(key[p] & 0xffffull)];
+                    for (int q = p + 1; q < count && (uint32_t)(key[q] >> 16) == col; ++q)
+                        s = __dadd_rn(s, val[(int)(key[q] & 0xffffull)]);
+                    keep = (!prune || s != 0.0) ? 1 : 0;
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int r = kept + __popc(mask & ((1u << lane) - 1u));
+                tidx[t0 + r] = (int32_t)col;
+                tval[t0 + r] = s;
+            }
+            kept += __popc(mask);
+        }
+        if (lane == 0) { cnt[row] = kept; tstart[row] = (int32_t)t0; }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_sg_compact(int64_t m, const int32_t* __restrict__ cnt, const int32_t* __restrict__ tstart,
              const int32_t* __restrict__ cptr, const int32_t* __restrict__ tidx,
@@ -289,6 +423,15 @@ extern "C" {
 
 int npb_spgemm_rows_cap(void) { return SG_CAP; }
 
+// tuning / test switch: 0 keeps rows of <= 512 partial products on the CTA-batched kernel too;
+// returns the old value
+static int npb_sg_warp_rows = 1;
+int npb_spgemm_set_warp_rows(int on) {
+    const int old = npb_sg_warp_rows;
+    npb_sg_warp_rows = on ? 1 : 0;
+    return old;
+}
+
 // phase 1: ub (m), ubptr (m + 1) = exclusive scan; stats[0] = total products bound,
 // stats[1] = largest ub.  The caller checks stats[1] <= npb_spgemm_rows_cap() / 2.
 int npb_spgemm_rows_bound(int64_t m, const int32_t* a_indptr, const int32_t* a_indices,
@@ -315,6 +458,36 @@ int npb_spgemm_rows_numeric(int64_t m, int64_t total, int64_t max_ub, const int3
                             int32_t* tstart, void* stream) {
     cudaStream_t st = ST(stream);
     if (max_ub > SG_CAP / 2) { npb_set_error("spgemm_rows: row with %lld products", (long long)max_ub); return NPB_ERR_ARG; }
+    if (npb_sg_warp_rows && max_ub > 16 && max_ub <= 512 && m > 0) {
+        // short rows: one warp per row (no batches; cnt / tstart are written for every row).  Rows of
+        // <= 16 products (D G of the cavity: 8) leave half a warp idle and stay on the batches.
+        // Measured on the 21 products of the 2048^2 preconditioner setup (tools/profile_setup.py):
+        // 55.4 -> 46.1 ms in total, the two largest 12.0 -> 9.0 and 12.0 -> 7.9 ms; the warp kernel is
+        // bound by its four dependent rounds of global loads per row (row pointers, A entries, B row
+        // pointers, B entries), not by the sort
+        int64_t g = (m + 7) / 8;
+        const int64_t gcap = (int64_t)NPB_NUM_SMS * 32;
+        if (g > gcap) g = gcap;
+#define NPB_SGW(CAP_) do { \
+            const size_t shw = (size_t)8 * (CAP_) * 16; \
+            static bool conf_ = false; \
+            if (!conf_ && shw > 48 * 1024) { \
+                NPB_CUDA(cudaFuncSetAttribute(k_sg_rows_warp<CAP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw)); \
+                conf_ = true; \
+            } \
+            k_sg_rows_warp<CAP_><<<(unsigned)g, 256, shw, st>>>(m, a_indptr, a_indices, a_data, *a_scales, b_indptr, \
+                b_indices, b_data, *b_scales, ubptr, prune, tidx, tval, cnt, tstart); \
+        } while (0)
+        if (max_ub <= 32) NPB_SGW(32);
+        else if (max_ub <= 64) NPB_SGW(64);
+        else if (max_ub <= 128) NPB_SGW(128);
+        else if (max_ub <= 256) NPB_SGW(256);
+        else NPB_SGW(512);
+#undef NPB_SGW
+        NPB_COUNT_LAUNCH();
+        NPB_CHECK_LAUNCH("spgemm_rows_warp");
+        return NPB_OK;
+    }
     const int64_t T = SG_CAP - max_ub;
     const int64_t nb = total / T + 1;
     k_sg_batches<<<npb_blocks(nb + 1, 256), 256, 0, st>>>(m, ubptr, T, nb, brow);

@@ -507,6 +507,19 @@ def test_row_batched_spgemm(dev, m, k, n, da, db):
         a = a.tolil(); a[0] = 0; a[0, 0] = 2.0; a[0, 1] = 2.0; a = sp.csr_matrix(a); a.sort_indices()
     A, B = dev.DevCsr.from_scipy(a), dev.DevCsr.from_scipy(b)
     fast = dev._csr_times_csr_rows(A, B)
+    # the warp-per-row kernel (rows of <= 512 partial products) and the CTA-batched kernel give
+    # the same bits
+    from numpad_b200 import _lib as _l
+    was = _l.lib().cdll.npb_spgemm_set_warp_rows(0)
+    try:
+        batched = dev._csr_times_csr_rows(A, B)
+    finally:
+        _l.lib().cdll.npb_spgemm_set_warp_rows(was)
+    assert (fast is None) == (batched is None)
+    if fast is not None:
+        assert fast.nnz == batched.nnz
+        assert torch.equal(fast.indptr, batched.indptr) and torch.equal(fast.indices, batched.indices)
+        assert torch.equal(fast.data, batched.data)
     old = dev.USE_SPGEMM_ROWS
     dev.USE_SPGEMM_ROWS = False
     try:

@@ -12,7 +12,11 @@ from numpad_b200.workloads.cavity import CavityProblem
 
 ap = argparse.ArgumentParser(); ap.add_argument('--grid', type=int, default=1024)
 ap.add_argument('--quiet', action='store_true')
+ap.add_argument('--warp-rows', type=int, default=-1)
 a = ap.parse_args()
+if a.warp_rows >= 0:
+    from numpad_b200 import _lib
+    _lib.lib().cdll.npb_spgemm_set_warp_rows(a.warp_rows)
 P = CavityProblem(npd, a.grid); u0 = P.fixed_state()
 u = npd.array(u0.copy()); res = P.residual(u, npd.array(u0), 1.0, 0)
 J = npd.diff_dev(res, u).materialized()
