@@ -164,7 +164,9 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
         NPB_CUDA(cudaMallocHost(&h_pin, sizeof(double) * 4 * (m + 8)));
         h_pin_elems = (size_t)4 * (m + 8);
     }
-    double* h_up = h_pin + 2 * (m + 8);
+    // (the upload half is addressed through the static pointer at every use: a nested npb_fgmres --
+    // the Jacobi-GMRES momentum solve of the robust preconditioner -- may have re-allocated the buffer)
+#define h_up (h_pin + 2 * (m + 8))
 
     auto allreduce = [&](double* buf, int count) -> int {
         if (ops->allreduce) return ops->allreduce(ops->allreduce_ctx, buf, count, stream);
@@ -321,6 +323,7 @@ done:
     }
     return rc ? rc : status;
 #undef GM_TRY
+#undef h_up
 }
 
 }  // extern "C"
