@@ -190,7 +190,7 @@ int npb_fgmres(int64_t n, const npb_krylov_ops* ops, const double* b, double* x,
         return 0;
     };
     int rc = 0, status = NPB_ERR_NOCONV;
-    int iters = 0, restarts = 0, reorth = 0;
+    int iters = 0, restarts = 0;
     double bnorm = 0, rnorm = 0, rnorm0 = 0;
 #define GM_TRY(expr) do { rc = (expr); if (rc) goto done; } while (0)
 
@@ -318,7 +318,7 @@ done:
     if (info) {
         info->iters = iters; info->restarts = restarts;
         info->status = rc ? rc : status;
-        info->pad = reorth;      // (re-orthogonalisation is part of every step)
+        info->pad = 0;
         info->bnorm = bnorm; info->rnorm0 = rnorm0; info->rnorm = rnorm;
     }
     return rc ? rc : status;
